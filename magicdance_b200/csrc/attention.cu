@@ -1,0 +1,360 @@
+// Fused attention for sm_100a: softmax([Q K0^T | Q K1^T] * scale) [V0 ; V1], FlashAttention-style
+// online softmax, both GEMMs on tcgen05 with TMEM accumulators, operands fed by TMA.
+//
+// The two key/value sources are the layer's own tokens (source 0) and the appearance bank
+// (source 1): the reference concatenates them with torch.cat before to_k/to_v
+// (ldm/modules/attention.py:303-307); here the tile loop simply walks source 0's tiles and then
+// source 1's, so no concatenated K/V buffer ever exists.
+//
+// One CTA = 128 queries x 1 head x 1 batch element.  Warp roles:
+//   warp 0     TMA producer: Q once; K tile [BKV][d] and V^T tile [d][BKV] per step, 2-stage ring.
+//              Head slices are cut out of the [tokens][heads*d] activations by a 3-D tensor map
+//              (d, heads, tokens) whose innermost extent is d, so the 64-wide box is zero-filled
+//              beyond d — that is the K-dim padding 40->48 / 80->128 / 160->192 for free.
+//   warp 1     MMA issuer: S = Q K^T (M=128, N=BKV) into TMEM; after the softmax warps publish P
+//              (fp16, smem, 128B-swizzled K-major) O += P V (M=128, N=DV) into TMEM.
+//   warps 2-5  softmax: thread == query row.  tcgen05.ld S, running max / sum in the log2 domain,
+//              lazy O rescale (only when the max grows by > 2^8), write P, final O / l -> fp16.
+#include "common.cuh"
+
+namespace mdb {
+
+constexpr int kAttnThreads = 192;
+constexpr int kBQ = 128;
+
+template <int D, int BKV>
+struct AttnCfg {
+  static constexpr int kDkChunks = (D + 63) / 64;
+  static constexpr int kDV = (D + 15) / 16 * 16;  // PV N and number of QK K-steps * 16
+  static constexpr int kKSteps = kDV / 16;
+  static constexpr int kKvChunks = BKV / 64;
+  static constexpr int kQBytes = kDkChunks * kBQ * 128;
+  static constexpr int kKBytes = kDkChunks * BKV * 128;
+  static constexpr int kVBytes = kKvChunks * kDV * 128;
+  static constexpr int kPBytes = kKvChunks * kBQ * 128;
+  static constexpr int kStages = 2;
+  static constexpr int kSmem = kQBytes + kStages * (kKBytes + kVBytes) + kPBytes + 1024;
+  static constexpr int kTmemCols = (BKV + kDV <= 128) ? 128 : (BKV + kDV <= 256 ? 256 : 512);
+  static constexpr int kOCol = BKV;  // O accumulator starts after S
+};
+
+struct AttnKParams {
+  CUtensorMap tmQ, tmK0, tmV0, tmK1, tmV1;
+  __half* out;
+  long long ldo;
+  int nq, n0, n1;
+  int kv0_batches, kv1_batches;
+  int ldv0_batch, ldv1_batch;
+  int bank_batches;
+  float scale_log2;
+};
+
+template <int D, int BKV>
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_constant__ AttnKParams p) {
+  using C = AttnCfg<D, BKV>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t q_bar, s_full, p_full, o_done;
+  __shared__ __align__(8) uint64_t kv_full[C::kStages], kv_empty[C::kStages];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + C::kQBytes;
+  uint8_t* sP = sKV + C::kStages * (C::kKBytes + C::kVBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+
+  const int t0 = (p.n0 + BKV - 1) / BKV;
+  const int t1 = (b < p.bank_batches && p.n1 > 0) ? (p.n1 + BKV - 1) / BKV : 0;
+  const int n_tiles = t0 + t1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK0);
+    tma_prefetch_desc(&p.tmV0);
+    mbar_init(&q_bar, 1);
+    mbar_init(&s_full, 1);
+    mbar_init(&p_full, 128);
+    mbar_init(&o_done, 1);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, C::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&q_bar, C::kQBytes);
+      for (int dc = 0; dc < C::kDkChunks; ++dc)
+        tma_load_3d(sQ + dc * (kBQ * 128), &p.tmQ, &q_bar, dc * 64, head, b * p.nq + q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % C::kStages;
+        const uint32_t ph = (j / C::kStages) & 1;
+        const bool src1 = j >= t0;
+        const int key0 = (src1 ? (j - t0) : j) * BKV;
+        const CUtensorMap* tk = src1 ? &p.tmK1 : &p.tmK0;
+        const CUtensorMap* tv = src1 ? &p.tmV1 : &p.tmV0;
+        const int nsrc = src1 ? p.n1 : p.n0;
+        const int kvb = src1 ? (p.kv1_batches > 1 ? b : 0) : (p.kv0_batches > 1 ? b : 0);
+        const int ldvb = src1 ? p.ldv1_batch : p.ldv0_batch;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_expect_tx(&kv_full[s], C::kKBytes + C::kVBytes);
+        uint8_t* sk = sKV + s * (C::kKBytes + C::kVBytes);
+        uint8_t* sv = sk + C::kKBytes;
+        for (int dc = 0; dc < C::kDkChunks; ++dc)
+          tma_load_3d(sk + dc * (BKV * 128), tk, &kv_full[s], dc * 64, head, kvb * nsrc + key0);
+        for (int kc = 0; kc < C::kKvChunks; ++kc)
+          tma_load_2d(sv + kc * (C::kDV * 128), tv, &kv_full[s], kvb * ldvb + key0 + kc * 64, head * D);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(kBQ, BKV);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(kBQ, C::kDV);
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      mbar_wait(&q_bar, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % C::kStages;
+        const uint32_t ph = (j / C::kStages) & 1;
+        mbar_wait(&kv_full[s], ph);
+        tc_fence_after_sync();
+        const uint32_t k_addr = smem_u32(sKV + s * (C::kKBytes + C::kVBytes));
+        const uint32_t v_addr = k_addr + C::kKBytes;
+        // S = Q K^T : K-steps of 16 over the (zero-padded) head dim
+#pragma unroll
+        for (int ks = 0; ks < C::kKSteps; ++ks) {
+          const int dc = ks >> 2, kk = ks & 3;
+          const uint64_t da = umma_desc_k_sw128(q_addr + dc * (kBQ * 128)) + 2 * kk;
+          const uint64_t db = umma_desc_k_sw128(k_addr + dc * (BKV * 128)) + 2 * kk;
+          umma_f16_ss(tmem_base, da, db, idesc_qk, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full);
+        // wait for P(j) (and the O rescale) from the softmax warps
+        mbar_wait(&p_full, j & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          const int kc = ks >> 2, kk = ks & 3;
+          const uint64_t da = umma_desc_k_sw128(p_addr + kc * (kBQ * 128)) + 2 * kk;
+          const uint64_t db = umma_desc_k_sw128(v_addr + kc * (C::kDV * 128)) + 2 * kk;
+          umma_f16_ss(tmem_base + C::kOCol, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(&o_done);
+      }
+    }
+  } else {
+    // ---------------- softmax / correction / epilogue warps ----------------
+    const int g = warp & 3;
+    const int r = g * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
+    const uint32_t t_o = t_s + C::kOCol;
+    float m_run = -INFINITY;
+    float l_run = 0.f;
+    uint8_t* p_row = sP + (r >> 3) * 1024 + (r & 7) * 128;
+    const int sw = r & 7;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const bool src1 = j >= t0;
+      const int key0 = (src1 ? (j - t0) : j) * BKV;
+      const int valid = min(BKV, (src1 ? p.n1 : p.n0) - key0);
+      mbar_wait(&s_full, j & 1);
+      tc_fence_after_sync();
+      float sv[BKV];
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t rr[32];
+        tmem_ld_x32(t_s + c * 32, rr);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sv[c * 32 + i] = __uint_as_float(rr[i]) * p.scale_log2;
+      }
+      float mt = -INFINITY;
+      if (valid == BKV) {
+#pragma unroll
+        for (int i = 0; i < BKV; ++i) mt = fmaxf(mt, sv[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < BKV; ++i) {
+          if (i >= valid) sv[i] = -INFINITY;
+          mt = fmaxf(mt, sv[i]);
+        }
+      }
+      float m_new = m_run;
+      if (mt - m_run > 8.0f) m_new = mt;  // lazy: tolerate p <= 2^8 before paying for a rescale
+      const float alpha = exp2f(m_run - m_new);  // m_run = -inf on the first tile -> 0
+      float lsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < BKV; ++i) {
+        sv[i] = exp2f(sv[i] - m_new);
+        lsum += sv[i];
+      }
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+
+      if (j > 0) {
+        // PV(j-1) must have finished before P is overwritten / O is rescaled
+        mbar_wait(&o_done, (j - 1) & 1);
+        tc_fence_after_sync();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+          for (int c = 0; c < C::kDV / 16; ++c) {
+            uint32_t oo[16];
+            tmem_ld_x16(t_o + c * 16, oo);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) oo[i] = __float_as_uint(__uint_as_float(oo[i]) * alpha);
+            tmem_st_x16(t_o + c * 16, oo);
+          }
+          tmem_wait_st();
+        }
+      }
+      // P -> smem, K-major 128B-swizzled: 16-byte unit u of row r lands at unit (u ^ (r & 7))
+#pragma unroll
+      for (int u = 0; u < BKV / 8; ++u) {
+        uint4 pk;
+        pk.x = pack_half2(sv[u * 8 + 0], sv[u * 8 + 1]);
+        pk.y = pack_half2(sv[u * 8 + 2], sv[u * 8 + 3]);
+        pk.z = pack_half2(sv[u * 8 + 4], sv[u * 8 + 5]);
+        pk.w = pack_half2(sv[u * 8 + 6], sv[u * 8 + 7]);
+        const int kc = u >> 3, uu = u & 7;
+        *reinterpret_cast<uint4*>(p_row + kc * (kBQ * 128) + ((uu ^ sw) << 4)) = pk;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&p_full);
+    }
+
+    // final: O / l -> fp16
+    mbar_wait(&o_done, (n_tiles - 1) & 1);
+    tc_fence_after_sync();
+    const float inv_l = 1.0f / l_run;
+    const int q = q0 + r;
+    __half* op = p.out + (static_cast<long long>(b) * p.nq + q) * p.ldo + head * D;
+#pragma unroll
+    for (int c = 0; c < C::kDV / 16; ++c) {
+      uint32_t oo[16];
+      tmem_ld_x16(t_o + c * 16, oo);
+      tmem_wait_ld();
+      if (q < p.nq) {
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          if (c * 16 + h8 * 8 < D) {
+            uint4 o4;
+            o4.x = pack_half2(__uint_as_float(oo[h8 * 8 + 0]) * inv_l, __uint_as_float(oo[h8 * 8 + 1]) * inv_l);
+            o4.y = pack_half2(__uint_as_float(oo[h8 * 8 + 2]) * inv_l, __uint_as_float(oo[h8 * 8 + 3]) * inv_l);
+            o4.z = pack_half2(__uint_as_float(oo[h8 * 8 + 4]) * inv_l, __uint_as_float(oo[h8 * 8 + 5]) * inv_l);
+            o4.w = pack_half2(__uint_as_float(oo[h8 * 8 + 6]) * inv_l, __uint_as_float(oo[h8 * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(op + c * 16 + h8 * 8) = o4;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+void count_launch(int n = 1);
+
+template <int D, int BKV>
+static int launch_attn(const AttnKParams& kp, dim3 grid, cudaStream_t st) {
+  using C = AttnCfg<D, BKV>;
+  static bool attr_set = false;
+  auto kern = attn_tc_kernel<D, BKV>;
+  if (!attr_set) {
+    MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    attr_set = true;
+  }
+  kern<<<grid, kAttnThreads, C::kSmem, st>>>(kp);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return MDB_OK;
+}
+
+template <int D, int BKV>
+static int build_and_launch(const mdb_attn_desc* a, cudaStream_t st) {
+  using C = AttnCfg<D, BKV>;
+  AttnKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const int hd = a->heads * a->d;
+  int rc;
+  {
+    uint64_t dims[3] = {(uint64_t)a->d, (uint64_t)a->heads, (uint64_t)a->batch * a->nq};
+    uint64_t str[2] = {(uint64_t)a->d * 2, (uint64_t)a->ldq * 2};
+    uint32_t box[3] = {64, 1, kBQ};
+    if ((rc = make_tmap_f16(&kp.tmQ, a->q, 3, dims, str, box))) return rc;
+  }
+  auto mk_kv = [&](const void* k, long long ldk, const void* vt, long long ldvt, int n, int nb, int ldvb,
+                   CUtensorMap* tk, CUtensorMap* tv) -> int {
+    uint64_t dims[3] = {(uint64_t)a->d, (uint64_t)a->heads, (uint64_t)nb * n};
+    uint64_t str[2] = {(uint64_t)a->d * 2, (uint64_t)ldk * 2};
+    uint32_t box[3] = {64, 1, (uint32_t)BKV};
+    int r = make_tmap_f16(tk, k, 3, dims, str, box);
+    if (r) return r;
+    uint64_t vdims[2] = {(uint64_t)nb * ldvb, (uint64_t)hd};
+    uint64_t vstr[1] = {(uint64_t)ldvt * 2};
+    uint32_t vbox[2] = {64, (uint32_t)C::kDV};
+    return make_tmap_f16(tv, vt, 2, vdims, vstr, vbox);
+  };
+  if ((rc = mk_kv(a->k0, a->ldk0, a->vt0, a->ldvt0, a->n0, a->kv0_batches, a->ldv0_batch, &kp.tmK0, &kp.tmV0))) return rc;
+  if (a->n1 > 0) {
+    if ((rc = mk_kv(a->k1, a->ldk1, a->vt1, a->ldvt1, a->n1, a->kv1_batches, a->ldv1_batch, &kp.tmK1, &kp.tmV1)))
+      return rc;
+  }
+  kp.out = static_cast<__half*>(a->out);
+  kp.ldo = a->ldo;
+  kp.nq = a->nq;
+  kp.n0 = a->n0;
+  kp.n1 = a->n1;
+  kp.kv0_batches = a->kv0_batches;
+  kp.kv1_batches = a->kv1_batches;
+  kp.ldv0_batch = a->ldv0_batch;
+  kp.ldv1_batch = a->ldv1_batch;
+  kp.bank_batches = a->n1 > 0 ? a->bank_batches : 0;
+  kp.scale_log2 = a->scale * 1.4426950408889634f;
+  dim3 grid((a->nq + kBQ - 1) / kBQ, a->heads, a->batch);
+  return launch_attn<D, BKV>(kp, grid, st);
+}
+
+}  // namespace mdb
+
+using namespace mdb;
+
+extern "C" int mdb_attention_f16(const mdb_attn_desc* a, mdb_stream_t stream) {
+  MDB_REQUIRE(a != nullptr, "mdb_attention_f16: null descriptor");
+  MDB_REQUIRE(a->q && a->k0 && a->vt0 && a->out, "mdb_attention_f16: null operand");
+  MDB_REQUIRE(a->batch > 0 && a->heads > 0 && a->nq > 0 && a->n0 > 0 && a->n1 >= 0,
+              "mdb_attention_f16: bad shape");
+  MDB_REQUIRE(a->n1 == 0 || (a->k1 && a->vt1), "mdb_attention_f16: n1 > 0 needs k1/vt1");
+  MDB_REQUIRE(a->kv0_batches == 1 || a->kv0_batches == a->batch, "mdb_attention_f16: kv0_batches must be 1 or batch");
+  MDB_REQUIRE(a->n1 == 0 || a->kv1_batches == 1 || a->kv1_batches >= a->bank_batches,
+              "mdb_attention_f16: kv1_batches must be 1 or cover bank_batches");
+  MDB_REQUIRE(a->ldv0_batch >= a->n0 && a->ldv0_batch % 8 == 0, "mdb_attention_f16: ldv0_batch must be >= n0 and %% 8");
+  MDB_REQUIRE(a->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "mdb_attention_f16: out alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (a->d) {
+    case 40: return build_and_launch<40, 128>(a, st);
+    case 80: return build_and_launch<80, 64>(a, st);
+    case 160: return build_and_launch<160, 64>(a, st);
+    default:
+      set_error("mdb_attention_f16: head dim %d not supported (40, 80, 160)", a->d);
+      return MDB_ERR_UNSUPPORTED;
+  }
+}

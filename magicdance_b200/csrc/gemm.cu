@@ -1,0 +1,467 @@
+// tcgen05 GEMM / 3x3 implicit-GEMM convolution for sm_100a.
+//
+//   D[M,N] = epilogue(A[M,K] * B[N,K]^T), fp16 operands, fp32 accumulation in TMEM.
+//
+// One CTA computes one 128 x BN output tile (optionally one K-split of it).  Warp roles:
+//   warp 0     TMA producer   — streams 128x64 A tiles and BNx64 B tiles (128B-swizzled) through a
+//                               kStages-deep smem ring; completion on `full` mbarriers.  In conv
+//                               mode the A tile of tap (kh,kw) is a 4-D TMA box over the NHWC
+//                               activation shifted by (kw-1, kh-1): out-of-bounds rows/cols are
+//                               zero-filled by TMA, which IS the pad-1 halo — no im2col buffer.
+//   warp 1     MMA issuer     — one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per
+//                               stage, tcgen05.commit releases the stage (`empty`) and finally
+//                               signals `acc_full`.  Also owns the TMEM allocation.
+//   warps 2-5  epilogue       — tcgen05.ld the accumulator (thread == output row), apply bias /
+//                               per-batch bias (timestep embedding) / residual / GEGLU, store fp16.
+// Two CTAs fit per SM (3 stages, <=108 KB smem, <=256 TMEM columns each) so one CTA's epilogue
+// overlaps the other's main loop.
+#include "common.cuh"
+
+namespace mdb {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // 64 halves = 128 B = one swizzle row
+constexpr int kStages = 3;
+constexpr int kGemmThreads = 192;
+
+struct GemmKParams {
+  CUtensorMap tmA;
+  CUtensorMap tmA2;
+  CUtensorMap tmB;
+  __half* d;
+  long long ldd;
+  const float* bias;
+  long long bias_batch_stride;
+  const __half* residual;
+  long long ldr;
+  float* ws;
+  int rows_per_batch;
+  int m, n;
+  int k_chunks;        // total K / 64
+  int k1_chunks;       // chunks taken from tmA (plain mode); rest from tmA2
+  int chunks_per_split;
+  int splits;
+  int conv;            // conv mode
+  int chunks_per_tap;  // c / 64
+  int w, hw;           // conv geometry
+  int y_box;           // rows of the image covered by one M tile (hw >= 128) or h (hw < 128)
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTotal = kStages * kStageBytes + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ void epi_store_chunk(const GemmKParams& p, long long row, int col0, int ncols,
+                                                float (&v)[32]) {
+  // v holds columns col0 .. col0+31 of `row` (fp32 accumulators); bias + residual, then fp16 store
+  const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
+  if (p.bias != nullptr) {
+    const float* bp = p.bias + brow * p.bias_batch_stride + col0;
+    if (ncols == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b4 = *reinterpret_cast<const float4*>(bp + j);
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    } else {
+      for (int j = 0; j < ncols; ++j) v[j] += bp[j];
+    }
+  }
+  __half* dp = p.d + row * p.ldd + col0;
+  if (ncols == 32) {
+    if (p.residual != nullptr) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 r4 = rp[q];
+        const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __half22float2(h2[e]);
+          v[q * 8 + e * 2] += f.x;
+          v[q * 8 + e * 2 + 1] += f.y;
+        }
+      }
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(dp);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 o;
+      o.x = pack_half2(v[q * 8 + 0], v[q * 8 + 1]);
+      o.y = pack_half2(v[q * 8 + 2], v[q * 8 + 3]);
+      o.z = pack_half2(v[q * 8 + 4], v[q * 8 + 5]);
+      o.w = pack_half2(v[q * 8 + 6], v[q * 8 + 7]);
+      d4[q] = o;
+    }
+  } else {
+    for (int j = 0; j < ncols; ++j) {
+      float x = v[j];
+      if (p.residual != nullptr) x += __half2float(p.residual[row * p.ldr + col0 + j]);
+      dp[j] = __float2half_rn(x);
+    }
+  }
+}
+
+template <int BN, bool GEGLU>
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM;
+  const int n0 = blockIdx.y * BN;
+  const int split = blockIdx.z;
+  const int kc_begin = split * p.chunks_per_split;
+  const int kc_end = min(p.k_chunks, kc_begin + p.chunks_per_split);
+  const int n_iter = kc_end - kc_begin;
+  constexpr uint32_t kTmemCols = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0 && n_iter > 0) {
+      // conv geometry of this M tile
+      int b0 = 0, y0 = 0;
+      if (p.conv) {
+        b0 = m0 / p.hw;
+        y0 = (p.hw >= kBM) ? (m0 % p.hw) / p.w : 0;
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], S::kStageBytes);
+        uint8_t* sa = smem + s * S::kStageBytes;
+        uint8_t* sb = sa + S::kABytes;
+        const int kc = kc_begin + it;
+        if (p.conv) {
+          const int tap = kc / p.chunks_per_tap;
+          const int cc = kc - tap * p.chunks_per_tap;
+          const int kh = tap / 3, kw = tap - kh * 3;
+          tma_load_4d(sa, &p.tmA, &full_bar[s], cc * kBK, kw - 1, y0 + kh - 1, b0);
+        } else if (kc < p.k1_chunks) {
+          tma_load_2d(sa, &p.tmA, &full_bar[s], kc * kBK, m0);
+        } else {
+          tma_load_2d(sa, &p.tmA2, &full_bar[s], (kc - p.k1_chunks) * kBK, m0);
+        }
+        tma_load_2d(sb, &p.tmB, &full_bar[s], kc * kBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_iter > 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
+        const uint32_t b_addr = a_addr + S::kABytes;
+        const uint64_t da = umma_desc_k_sw128(a_addr);
+        const uint64_t db = umma_desc_k_sw128(b_addr);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 halves (32 B) along K inside the 128B swizzle row: +2 in the >>4 address field
+          umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&acc_bar);
+    }
+  } else if (n_iter > 0) {
+    // ---------------- epilogue warps 2..5 ----------------
+    const int g = warp & 3;  // TMEM lane group this warp may access
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after_sync();
+    const long long row = static_cast<long long>(m0) + g * 32 + lane;
+    const bool row_ok = row < p.m;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
+    if constexpr (!GEGLU) {
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int col0 = n0 + ch * 32;
+        if (col0 >= p.n) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_x32(taddr + ch * 32, r);
+        tmem_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const int ncols = min(32, p.n - col0);
+        if (p.splits > 1) {
+          if (row_ok) {
+            float* wp = p.ws + row * p.n + col0;
+            for (int j = 0; j < ncols; ++j) atomicAdd(wp + j, v[j]);
+          }
+        } else if (row_ok) {
+          epi_store_chunk(p, row, col0, ncols, v);
+        }
+      }
+    } else {
+      // GEGLU: chunk pairs (value, gate); output column = n0/2 + pair*32 + j
+      const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
+#pragma unroll 1
+      for (int pr = 0; pr < BN / 64; ++pr) {
+        const int col0 = n0 + pr * 64;
+        if (col0 >= p.n) break;
+        uint32_t rv[32], rg[32];
+        tmem_ld_x32(taddr + pr * 64, rv);
+        tmem_ld_x32(taddr + pr * 64 + 32, rg);
+        tmem_wait_ld();
+        if (row_ok) {
+          const float* bp = (p.bias != nullptr) ? p.bias + brow * p.bias_batch_stride + col0 : nullptr;
+          uint4* d4 = reinterpret_cast<uint4*>(p.d + row * p.ldd + (col0 >> 1));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int j = q * 8 + e;
+              float a = __uint_as_float(rv[j]);
+              float gt = __uint_as_float(rg[j]);
+              if (bp != nullptr) {
+                a += bp[j];
+                gt += bp[32 + j];
+              }
+              o[e] = a * gelu_erf_f(gt);
+            }
+            uint4 o4;
+            o4.x = pack_half2(o[0], o[1]);
+            o4.y = pack_half2(o[2], o[3]);
+            o4.z = pack_half2(o[4], o[5]);
+            o4.w = pack_half2(o[6], o[7]);
+            d4[q] = o4;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// split-K second pass: ws (fp32 [M][N]) -> bias/residual -> fp16 D
+__global__ void splitk_finalize_kernel(GemmKParams p) {
+  const long long total = static_cast<long long>(p.m) * p.n;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / p.n;
+    const int col = static_cast<int>(i - row * p.n);
+    float v = p.ws[i];
+    if (p.bias != nullptr) {
+      const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
+      v += p.bias[brow * p.bias_batch_stride + col];
+    }
+    if (p.residual != nullptr) v += __half2float(p.residual[row * p.ldr + col]);
+    p.d[row * p.ldd + col] = __float2half_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  if (g_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+      return MDB_ERR_CUDA;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("TMA base address %p is not 16-byte aligned", base);
+    return MDB_ERR_INVALID;
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    if (gstr[i] % 16 != 0) {
+      set_error("TMA stride %d (%llu bytes) is not a multiple of 16", i, (unsigned long long)gstr[i]);
+      return MDB_ERR_INVALID;
+    }
+  }
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu,%llu box %u,%u)", (int)r, rank,
+              (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0), bx[0], rank > 1 ? bx[1] : 0);
+    return MDB_ERR_CUDA;
+  }
+  return MDB_OK;
+}
+
+void count_launch(int n = 1);
+
+template <int BN, bool GEGLU>
+static int launch_gemm(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<BN, GEGLU>;
+  if (!attr_set) {
+    MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
+    attr_set = true;
+  }
+  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(kp);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return MDB_OK;
+}
+
+}  // namespace mdb
+
+using namespace mdb;
+
+extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
+  MDB_REQUIRE(g != nullptr, "mdb_gemm_f16: null descriptor");
+  MDB_REQUIRE(g->m > 0 && g->n > 0 && g->k > 0, "mdb_gemm_f16: bad shape m=%d n=%d k=%d", g->m, g->n, g->k);
+  MDB_REQUIRE(g->k % kBK == 0, "mdb_gemm_f16: K=%d must be a multiple of 64", g->k);
+  MDB_REQUIRE(g->a && g->b && g->d, "mdb_gemm_f16: null operand");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool geglu = g->epilogue == MDB_EPI_GEGLU;
+  GemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.d = static_cast<__half*>(g->d);
+  kp.ldd = g->ldd;
+  kp.bias = g->bias;
+  kp.bias_batch_stride = g->bias_batch_stride;
+  kp.rows_per_batch = g->rows_per_batch > 0 ? g->rows_per_batch : 1;
+  kp.residual = static_cast<const __half*>(g->residual);
+  kp.ldr = g->ldr;
+  kp.m = g->m;
+  kp.n = g->n;
+  kp.k_chunks = g->k / kBK;
+  kp.conv = g->conv;
+  MDB_REQUIRE(g->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(g->d) & 15) == 0,
+              "mdb_gemm_f16: D must be 16B aligned with ldd %% 8 == 0 (ldd=%lld)", (long long)g->ldd);
+  if (g->residual) {
+    MDB_REQUIRE(g->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0,
+                "mdb_gemm_f16: residual must be 16B aligned with ldr %% 8 == 0");
+    MDB_REQUIRE(!geglu, "mdb_gemm_f16: residual is not supported with the GEGLU epilogue");
+  }
+
+  int rc;
+  if (g->conv) {
+    MDB_REQUIRE(g->a2 == nullptr, "mdb_gemm_f16: conv mode takes a single source");
+    MDB_REQUIRE(g->c % kBK == 0 && g->k == 9 * g->c, "mdb_gemm_f16: conv needs c %% 64 == 0 and k == 9c (c=%d k=%d)",
+                g->c, g->k);
+    MDB_REQUIRE(g->m == g->nb * g->h * g->w, "mdb_gemm_f16: conv m != nb*h*w");
+    const int hw = g->h * g->w;
+    uint32_t box[4];
+    if (hw >= kBM) {
+      MDB_REQUIRE(kBM % g->w == 0 && hw % kBM == 0,
+                  "mdb_gemm_f16: conv tile needs w | 128 and 128 | h*w (h=%d w=%d)", g->h, g->w);
+      box[0] = kBK; box[1] = g->w; box[2] = kBM / g->w; box[3] = 1;
+    } else {
+      MDB_REQUIRE(kBM % hw == 0, "mdb_gemm_f16: conv tile needs h*w | 128 (h=%d w=%d)", g->h, g->w);
+      box[0] = kBK; box[1] = g->w; box[2] = g->h; box[3] = kBM / hw;
+    }
+    uint64_t dims[4] = {(uint64_t)g->c, (uint64_t)g->w, (uint64_t)g->h, (uint64_t)g->nb};
+    uint64_t str[3] = {(uint64_t)g->c * 2, (uint64_t)g->c * g->w * 2, (uint64_t)g->c * hw * 2};
+    rc = make_tmap_f16(&kp.tmA, g->a, 4, dims, str, box);
+    if (rc) return rc;
+    kp.chunks_per_tap = g->c / kBK;
+    kp.w = g->w;
+    kp.hw = hw;
+    kp.k1_chunks = kp.k_chunks;
+  } else {
+    const int k1 = g->a2 ? g->k1 : g->k;
+    MDB_REQUIRE(k1 % kBK == 0 && k1 > 0 && k1 <= g->k, "mdb_gemm_f16: k1=%d must be a multiple of 64 within K", k1);
+    uint32_t box[2] = {kBK, kBM};
+    uint64_t dims[2] = {(uint64_t)k1, (uint64_t)g->m};
+    uint64_t str[1] = {(uint64_t)g->lda * 2};
+    rc = make_tmap_f16(&kp.tmA, g->a, 2, dims, str, box);
+    if (rc) return rc;
+    if (g->a2) {
+      uint64_t dims2[2] = {(uint64_t)(g->k - k1), (uint64_t)g->m};
+      uint64_t str2[1] = {(uint64_t)g->lda2 * 2};
+      rc = make_tmap_f16(&kp.tmA2, g->a2, 2, dims2, str2, box);
+      if (rc) return rc;
+    }
+    kp.k1_chunks = k1 / kBK;
+  }
+
+  int bn;
+  if (geglu) {
+    MDB_REQUIRE(g->n % 128 == 0, "mdb_gemm_f16: GEGLU needs N %% 128 == 0 (N=%d)", g->n);
+    bn = 128;
+  } else {
+    bn = (g->n % 160 == 0) ? 160 : 128;
+  }
+  {
+    uint32_t box[2] = {kBK, (uint32_t)bn};
+    uint64_t dims[2] = {(uint64_t)g->k, (uint64_t)g->n};
+    uint64_t str[1] = {(uint64_t)g->ldb * 2};
+    rc = make_tmap_f16(&kp.tmB, g->b, 2, dims, str, box);
+    if (rc) return rc;
+  }
+
+  int splits = g->splits > 1 ? g->splits : 1;
+  if (splits > kp.k_chunks) splits = kp.k_chunks;
+  if (geglu) splits = 1;
+  kp.chunks_per_split = (kp.k_chunks + splits - 1) / splits;
+  splits = (kp.k_chunks + kp.chunks_per_split - 1) / kp.chunks_per_split;  // no empty splits
+  kp.splits = splits;
+  kp.ws = g->splitk_ws;
+  if (splits > 1) {
+    MDB_REQUIRE(g->splitk_ws != nullptr, "mdb_gemm_f16: splits > 1 needs splitk_ws");
+    MDB_CHECK_CUDA(cudaMemsetAsync(g->splitk_ws, 0, sizeof(float) * (size_t)g->m * g->n, st));
+  }
+
+  dim3 grid((g->m + kBM - 1) / kBM, (g->n + bn - 1) / bn, splits);
+  if (geglu) rc = launch_gemm<128, true>(kp, grid, st);
+  else if (bn == 160) rc = launch_gemm<160, false>(kp, grid, st);
+  else rc = launch_gemm<128, false>(kp, grid, st);
+  if (rc) return rc;
+  if (splits > 1) {
+    const long long total = (long long)g->m * g->n;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_finalize_kernel<<<blocks, 256, 0, st>>>(kp);
+    MDB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return MDB_OK;
+}

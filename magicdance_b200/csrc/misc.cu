@@ -1,0 +1,409 @@
+// HBM-bound helper kernels of the denoising step: direct 3x3 conv for non-GEMM-shaped layers,
+// im2col (stride-2 downsample), nearest x2 upsample, residual add, timestep embedding, skinny
+// Linear for the timestep MLPs, NCHW fp32 <-> NHWC fp16 boundary converts, fused CFG + DDIM update.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace mdb {
+
+// ---------------------------------------------------------------------------------------------
+// plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n = 1);
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------------------------
+// direct 3x3 conv, pad 1, stride 1|2, NHWC fp16, fp32 accumulate.
+// CTA: 8x8 output pixels x 32 output channels; input patch (with halo) and the weight slab for a
+// 16-channel slice of cin are staged in shared memory; each thread owns 1 pixel x 8 couts.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDcTile = 8;
+constexpr int kDcCout = 32;
+constexpr int kDcCin = 16;
+
+template <int STRIDE>
+__global__ void __launch_bounds__(256) direct_conv3x3_kernel(const __half* __restrict__ x, const __half* __restrict__ wt,
+                                                             const float* __restrict__ bias,
+                                                             const __half* __restrict__ residual, __half* __restrict__ y,
+                                                             int h, int w, int cin, int cout, int ho, int wo, int silu) {
+  constexpr int PH = (kDcTile - 1) * STRIDE + 3;  // patch height/width
+  __shared__ float s_in[PH * PH * kDcCin];
+  __shared__ float s_w[kDcCout * 9 * kDcCin];
+  const int tiles_x = (wo + kDcTile - 1) / kDcTile;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int co0 = blockIdx.y * kDcCout;
+  const int b = blockIdx.z;
+  const int px = threadIdx.x % 64;            // pixel within tile
+  const int cgp = threadIdx.x / 64;           // cout group of 8 (4 groups)
+  const int oy = ty * kDcTile + px / kDcTile, ox = tx * kDcTile + px % kDcTile;
+  const int iy0 = ty * kDcTile * STRIDE - 1, ix0 = tx * kDcTile * STRIDE - 1;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+  for (int c0 = 0; c0 < cin; c0 += kDcCin) {
+    const int cs = min(kDcCin, cin - c0);
+    for (int i = threadIdx.x; i < PH * PH * kDcCin; i += blockDim.x) {
+      const int ci = i % kDcCin, pp = i / kDcCin;
+      const int yy = iy0 + pp / PH, xx = ix0 + pp % PH;
+      float v = 0.f;
+      if (ci < cs && yy >= 0 && yy < h && xx >= 0 && xx < w)
+        v = __half2float(x[((static_cast<long long>(b) * h + yy) * w + xx) * cin + c0 + ci]);
+      s_in[i] = v;
+    }
+    for (int i = threadIdx.x; i < kDcCout * 9 * kDcCin; i += blockDim.x) {
+      const int ci = i % kDcCin, t = (i / kDcCin) % 9, co = i / (kDcCin * 9);
+      float v = 0.f;
+      if (ci < cs && co0 + co < cout) v = __half2float(wt[(static_cast<long long>(co0 + co) * 9 + t) * cin + c0 + ci]);
+      s_w[i] = v;
+    }
+    __syncthreads();
+    const int py = (px / kDcTile) * STRIDE, pxx = (px % kDcTile) * STRIDE;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float* ip = &s_in[((py + t / 3) * PH + pxx + t % 3) * kDcCin];
+#pragma unroll
+      for (int ci = 0; ci < kDcCin; ++ci) {
+        const float xv = ip[ci];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += xv * s_w[((cgp * 8 + j) * 9 + t) * kDcCin + ci];
+      }
+    }
+    __syncthreads();
+  }
+  if (oy < ho && ox < wo) {
+    const long long o = ((static_cast<long long>(b) * ho + oy) * wo + ox) * cout;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = co0 + cgp * 8 + j;
+      if (co < cout) {
+        float v = acc[j] + (bias ? bias[co] : 0.f);
+        if (silu) v = silu_f(v);
+        if (residual) v += __half2float(residual[o + co]);
+        y[o + co] = __float2half_rn(v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void im2col3x3s2_kernel(const __half* __restrict__ x, __half* __restrict__ col, int batch, int h, int w,
+                                   int c) {
+  const int ho = h / 2, wo = w / 2, vecs = c / 8;
+  const long long total = static_cast<long long>(batch) * ho * wo * 9 * vecs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vecs);
+    long long r = i / vecs;
+    const int t = static_cast<int>(r % 9);
+    r /= 9;  // output pixel index
+    const int ox = static_cast<int>(r % wo);
+    const int oy = static_cast<int>((r / wo) % ho);
+    const int b = static_cast<int>(r / (static_cast<long long>(wo) * ho));
+    const int yy = oy * 2 - 1 + t / 3, xx = ox * 2 - 1 + t % 3;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+      val = *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * h + yy) * w + xx) * c + v * 8);
+    *reinterpret_cast<uint4*>(col + (r * 9 + t) * c + v * 8) = val;
+  }
+}
+
+__global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ y, int batch, int h, int w, int c) {
+  const int vecs = c / 8;
+  const long long total = static_cast<long long>(batch) * (2 * h) * (2 * w) * vecs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vecs);
+    long long r = i / vecs;
+    const int ox = static_cast<int>(r % (2 * w));
+    const int oy = static_cast<int>((r / (2 * w)) % (2 * h));
+    const int b = static_cast<int>(r / (static_cast<long long>(4) * w * h));
+    const uint4 val = *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * h + oy / 2) * w + ox / 2) * c + v * 8);
+    *reinterpret_cast<uint4*>(y + r * c + v * 8) = val;
+  }
+}
+
+__global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ y,
+                           long long n_per_batch, int batch, int b_batches) {
+  const long long vec_per = n_per_batch / 8;
+  const long long total = vec_per * batch;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long bi = (b_batches == 1) ? (i % vec_per) : i;
+    uint4 ua = reinterpret_cast<const uint4*>(a)[i];
+    uint4 ub = reinterpret_cast<const uint4*>(b)[bi];
+    __half2* ha = reinterpret_cast<__half2*>(&ua);
+    const __half2* hb = reinterpret_cast<const __half2*>(&ub);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
+      ha[e] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+    }
+    reinterpret_cast<uint4*>(y)[i] = ua;
+  }
+}
+
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int batch, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * half) return;
+  const int b = i / half, k = i % half;
+  const float freq = expf(-logf(10000.0f) * static_cast<float>(k) / static_cast<float>(half));
+  const float arg = static_cast<float>(t[b]) * freq;
+  out[b * dim + k] = cosf(arg);
+  out[b * dim + half + k] = sinf(arg);
+}
+
+// out[r][n] = sum_k f(x[r][k]) * W[n][k] + bias[n]; one warp per output column n, all rows at once
+template <int ROWS>
+__global__ void skinny_linear_kernel(const float* __restrict__ x, const __half* __restrict__ w,
+                                     const float* __restrict__ bias, float* __restrict__ out, int rows, int n, int k,
+                                     int silu_in, int silu_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  float acc[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+  const __half* wr = w + static_cast<long long>(warp) * k;
+  for (int kk = lane * 8; kk < k; kk += 32 * 8) {
+    uint4 u = *reinterpret_cast<const uint4*>(wr + kk);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+    float wf[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __half22float2(h2[e]);
+      wf[2 * e] = f.x; wf[2 * e + 1] = f.y;
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      if (r < rows) {
+        const float* xr = x + static_cast<long long>(r) * k + kk;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float xv = xr[e];
+          if (silu_in) xv = silu_f(xv);
+          acc[r] += xv * wf[e];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+  }
+  if (lane == 0) {
+    for (int r = 0; r < rows && r < ROWS; ++r) {
+      float v = acc[r] + (bias ? bias[warp] : 0.f);
+      if (silu_out) v = silu_f(v);
+      out[static_cast<long long>(r) * n + warp] = v;
+    }
+  }
+}
+
+__global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int batch, int c, int h,
+                                            int w) {
+  const long long total = static_cast<long long>(batch) * c * h * w;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // i indexes the NHWC output
+    const int ch = static_cast<int>(i % c);
+    long long r = i / c;
+    const int xx = static_cast<int>(r % w);
+    const int yy = static_cast<int>((r / w) % h);
+    const int b = static_cast<int>(r / (static_cast<long long>(w) * h));
+    y[i] = __float2half_rn(x[((static_cast<long long>(b) * c + ch) * h + yy) * w + xx]);
+  }
+}
+
+__global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, int batch, int c, int h,
+                                            int w) {
+  const long long total = static_cast<long long>(batch) * c * h * w;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // i indexes the NCHW output
+    const int xx = static_cast<int>(i % w);
+    long long r = i / w;
+    const int yy = static_cast<int>(r % h);
+    r /= h;
+    const int ch = static_cast<int>(r % c);
+    const int b = static_cast<int>(r / c);
+    y[i] = __half2float(x[((static_cast<long long>(b) * h + yy) * w + xx) * c + ch]);
+  }
+}
+
+__global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ ec,
+                                       const float* __restrict__ eu, const float* __restrict__ noise,
+                                       float* __restrict__ x_prev, float* __restrict__ pred_x0, long long n, float scale,
+                                       float sqrt_at, float sqrt_aprev, float dir_coef, float sigma, float s1m) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float u = eu[i];
+    const float e = u + scale * (ec[i] - u);
+    const float p0 = (x[i] - s1m * e) / sqrt_at;
+    float xp = sqrt_aprev * p0 + dir_coef * e;
+    if (noise != nullptr) xp += sigma * noise[i];
+    x_prev[i] = xp;
+    pred_x0[i] = p0;
+  }
+}
+
+static inline int grid_for(long long total, int threads = 256, int cap = 148 * 16) {
+  long long b = (total + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace mdb
+
+using namespace mdb;
+
+extern "C" int mdb_abi_version(void) { return MDB_ABI_VERSION; }
+extern "C" const char* mdb_last_error(void) { return mdb::g_err; }
+extern "C" int64_t mdb_launch_count(void) { return mdb::g_launches.load(); }
+
+extern "C" int mdb_device_check(void) {
+  int dev = 0;
+  MDB_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  MDB_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    return MDB_ERR_UNSUPPORTED;
+  }
+  return MDB_OK;
+}
+
+extern "C" int mdb_conv3x3_direct_f16(const void* x, const void* wt, const float* bias, const void* residual, void* y,
+                                      int32_t batch, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t stride,
+                                      int32_t silu, mdb_stream_t stream) {
+  MDB_REQUIRE(x && wt && y, "mdb_conv3x3_direct_f16: null pointer");
+  MDB_REQUIRE(stride == 1 || stride == 2, "mdb_conv3x3_direct_f16: stride must be 1 or 2");
+  const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
+  dim3 grid(((wo + kDcTile - 1) / kDcTile) * ((ho + kDcTile - 1) / kDcTile), (cout + kDcCout - 1) / kDcCout, batch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (stride == 1)
+    direct_conv3x3_kernel<1><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(wt), bias,
+                                                   static_cast<const __half*>(residual), static_cast<__half*>(y), h, w,
+                                                   cin, cout, ho, wo, silu);
+  else
+    direct_conv3x3_kernel<2><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(wt), bias,
+                                                   static_cast<const __half*>(residual), static_cast<__half*>(y), h, w,
+                                                   cin, cout, ho, wo, silu);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return MDB_OK;
+}
+
+extern "C" int mdb_im2col3x3s2_f16(const void* x, void* col, int32_t batch, int32_t h, int32_t w, int32_t c,
+                                   mdb_stream_t stream) {
+  MDB_REQUIRE(x && col, "mdb_im2col3x3s2_f16: null pointer");
+  MDB_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "mdb_im2col3x3s2_f16: need c %% 8 == 0 and even h, w");
+  const long long total = static_cast<long long>(batch) * (h / 2) * (w / 2) * 9 * (c / 8);
+  im2col3x3s2_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<__half*>(col), batch, h, w, c);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return MDB_OK;
+}
+
+extern "C" int mdb_upsample2x_f16(const void* x, void* y, int32_t batch, int32_t h, int32_t w, int32_t c,
+                                  mdb_stream_t stream) {
+  MDB_REQUIRE(x && y && c % 8 == 0, "mdb_upsample2x_f16: bad arguments");
+  const long long total = static_cast<long long>(batch) * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<__half*>(y), batch, h, w, c);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return MDB_OK;
+}
+
+extern "C" int mdb_add_f16(const void* a, const void* b, void* y, int64_t n_per_batch, int32_t batch, int32_t b_batches,
+                           mdb_stream_t stream) {
+  MDB_REQUIRE(a && b && y && n_per_batch % 8 == 0, "mdb_add_f16: bad arguments");
+  MDB_REQUIRE(b_batches == 1 || b_batches == batch, "mdb_add_f16: b_batches must be 1 or batch");
+  add_kernel<<<grid_for(n_per_batch / 8 * batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<__half*>(y), n_per_batch, batch,
+      b_batches);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return MDB_OK;
+}
+
+extern "C" int mdb_timestep_embedding_f32(const int64_t* t, float* out, int32_t batch, int32_t dim, mdb_stream_t stream) {
+  MDB_REQUIRE(t && out && dim % 2 == 0, "mdb_timestep_embedding_f32: bad arguments");
+  const int total = batch * dim / 2;
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, out, batch, dim);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return MDB_OK;
+}
+
+extern "C" int mdb_skinny_linear_f32(const float* x, const void* w, const float* bias, float* out, int32_t rows,
+                                     int32_t n, int32_t k, int32_t silu_in, int32_t silu_out, mdb_stream_t stream) {
+  MDB_REQUIRE(x && w && out, "mdb_skinny_linear_f32: null pointer");
+  MDB_REQUIRE(rows >= 1 && rows <= 16 && k % 8 == 0, "mdb_skinny_linear_f32: rows must be 1..16 and k %% 8 == 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 256;
+  const int blocks = (n * 32 + threads - 1) / threads;
+  const __half* wp = static_cast<const __half*>(w);
+  if (rows <= 2)
+    skinny_linear_kernel<2><<<blocks, threads, 0, st>>>(x, wp, bias, out, rows, n, k, silu_in, silu_out);
+  else if (rows <= 8)
+    skinny_linear_kernel<8><<<blocks, threads, 0, st>>>(x, wp, bias, out, rows, n, k, silu_in, silu_out);
+  else
+    skinny_linear_kernel<16><<<blocks, threads, 0, st>>>(x, wp, bias, out, rows, n, k, silu_in, silu_out);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return MDB_OK;
+}
+
+extern "C" int mdb_nchw_f32_to_nhwc_f16(const float* x, void* y, int32_t batch, int32_t c, int32_t h, int32_t w,
+                                        mdb_stream_t stream) {
+  MDB_REQUIRE(x && y, "mdb_nchw_f32_to_nhwc_f16: null pointer");
+  const long long total = static_cast<long long>(batch) * c * h * w;
+  nchw_f32_to_nhwc_f16_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__half*>(y), batch, c, h, w);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return MDB_OK;
+}
+
+extern "C" int mdb_nhwc_f16_to_nchw_f32(const void* x, float* y, int32_t batch, int32_t c, int32_t h, int32_t w,
+                                        mdb_stream_t stream) {
+  MDB_REQUIRE(x && y, "mdb_nhwc_f16_to_nchw_f32: null pointer");
+  const long long total = static_cast<long long>(batch) * c * h * w;
+  nhwc_f16_to_nchw_f32_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), y, batch, c, h, w);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return MDB_OK;
+}
+
+extern "C" int mdb_cfg_ddim_update_f32(const float* x, const float* eps_c, const float* eps_u, const float* noise,
+                                       float* x_prev, float* pred_x0, int64_t n, float scale, float a_t, float a_prev,
+                                       float sigma, float sqrt_one_minus_a_t, mdb_stream_t stream) {
+  MDB_REQUIRE(x && eps_c && eps_u && x_prev && pred_x0 && n > 0, "mdb_cfg_ddim_update_f32: bad arguments");
+  MDB_REQUIRE(sigma == 0.f || noise != nullptr, "mdb_cfg_ddim_update_f32: sigma != 0 needs a noise tensor");
+  const float dir = sqrtf(fmaxf(1.0f - a_prev - sigma * sigma, 0.f));
+  cfg_ddim_update_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, eps_c, eps_u, sigma != 0.f ? noise : nullptr, x_prev, pred_x0, n, scale, sqrtf(a_t), sqrtf(a_prev), dir, sigma,
+      sqrt_one_minus_a_t);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return MDB_OK;
+}

@@ -1,0 +1,213 @@
+// GroupNorm(32) [+SiLU] and LayerNorm over channels-last fp16 activations (HBM-bound kernels).
+//
+// GroupNorm runs as (memset) -> stats -> apply:
+//   stats : each CTA owns a slab of rows of one batch element, threads own 8 consecutive channels
+//           (one 16-byte load per row), per-channel partial sums are folded to per-group sums with
+//           warp shuffles / shared atomics and added to stats[b][32][{sum,sumsq}] (fp32).
+//   apply : y = (x - mean) * rstd * gamma + beta, optional SiLU, 8 channels per thread; the input
+//           may be the channel concatenation of two tensors, which is how torch.cat([h, skip], 1)
+//           (cldm.py:104) disappears: the normalised copy is the only concatenated buffer.
+#include "common.cuh"
+
+namespace mdb {
+
+void count_launch(int n = 1);
+
+constexpr int kGnRowsPerCta = 64;
+
+__device__ __forceinline__ const uint4* gn_src(const __half* x1, int c1, const __half* x2, int c2, long long row,
+                                                int ch) {
+  // channel ch (multiple of 8) of concatenated row -> address of its 16-byte vector
+  return (ch < c1) ? reinterpret_cast<const uint4*>(x1 + row * c1 + ch)
+                   : reinterpret_cast<const uint4*>(x2 + row * c2 + (ch - c1));
+}
+
+__global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
+                                float* __restrict__ stats, int hw) {
+  extern __shared__ float sh[];  // [2][32] group sums
+  const int c = c1 + c2;
+  const int cg = c / 32;
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * kGnRowsPerCta;
+  const int rows = min(kGnRowsPerCta, hw - row0);
+  const int vecs = c / 8;
+  if (threadIdx.x < 64) sh[threadIdx.x] = 0.f;
+  __syncthreads();
+  // thread -> (vector index v, row phase); blockDim.x >= vecs is guaranteed by the launcher
+  const int v = threadIdx.x % vecs;
+  const int rphase = threadIdx.x / vecs;
+  const int rstride = blockDim.x / vecs;
+  if (rphase < rstride) {
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    for (int r = rphase; r < rows; r += rstride) {
+      const long long row = static_cast<long long>(b) * hw + row0 + r;
+      uint4 u = *gn_src(x1, c1, x2, c2, row, v * 8);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h2[e]);
+        s[2 * e] += f.x; q[2 * e] += f.x * f.x;
+        s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
+      }
+    }
+    // fold the 8 channels into (at most two) groups
+    const int g_first = (v * 8) / cg;
+    float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (v * 8 + i) / cg;
+      if (g == g_first) { sa += s[i]; qa += q[i]; } else { sb += s[i]; qb += q[i]; }
+    }
+    atomicAdd(&sh[g_first], sa);
+    atomicAdd(&sh[32 + g_first], qa);
+    if ((v * 8 + 7) / cg != g_first) {  // cg >= 10 so a vector spans at most two groups
+      atomicAdd(&sh[g_first + 1], sb);
+      atomicAdd(&sh[32 + g_first + 1], qb);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    atomicAdd(&stats[(b * 32 + threadIdx.x) * 2 + 0], sh[threadIdx.x]);
+    atomicAdd(&stats[(b * 32 + threadIdx.x) * 2 + 1], sh[32 + threadIdx.x]);
+  }
+}
+
+__global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ stats, __half* __restrict__ y, int batch, int hw, float eps,
+                                int silu) {
+  const int c = c1 + c2;
+  const int cg = c / 32;
+  const int vecs = c / 8;
+  const long long total = static_cast<long long>(batch) * hw * vecs;
+  const float inv_n = 1.0f / (static_cast<float>(cg) * hw);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / vecs;
+    const int v = static_cast<int>(i - row * vecs);
+    const int b = static_cast<int>(row / hw);
+    uint4 u = *gn_src(x1, c1, x2, c2, row, v * 8);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 t = __half22float2(h2[e]);
+      f[2 * e] = t.x; f[2 * e + 1] = t.y;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = v * 8 + e;
+      const int g = ch / cg;
+      const float mean = stats[(b * 32 + g) * 2] * inv_n;
+      const float var = fmaxf(stats[(b * 32 + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      float o = (f[e] - mean) * rstd * gamma[ch] + beta[ch];
+      if (silu) o = silu_f(o);
+      f[e] = o;
+    }
+    uint4 o4;
+    o4.x = pack_half2(f[0], f[1]); o4.y = pack_half2(f[2], f[3]);
+    o4.z = pack_half2(f[4], f[5]); o4.w = pack_half2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(y + row * c + v * 8) = o4;
+  }
+}
+
+// LayerNorm: one warp per row, row cached in registers (c <= 1280 -> <= 40 values per lane)
+template <int VPL>  // half2 pairs per lane
+__global__ void layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, __half* __restrict__ y, long long rows, int c,
+                                 float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const __half2* xr = reinterpret_cast<const __half2*>(x + static_cast<long long>(warp) * c);
+  float2 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = __half22float2(xr[lane + i * 32]);
+    s += v[i].x + v[i].y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / c;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean;
+    q += dx * dx + dy * dy;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / c + eps);
+  __half2* yr = reinterpret_cast<__half2*>(y + static_cast<long long>(warp) * c);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int ch = (lane + i * 32) * 2;
+    const float a = (v[i].x - mean) * rstd * gamma[ch] + beta[ch];
+    const float bb = (v[i].y - mean) * rstd * gamma[ch + 1] + beta[ch + 1];
+    yr[lane + i * 32] = __floats2half2_rn(a, bb);
+  }
+}
+
+}  // namespace mdb
+
+using namespace mdb;
+
+extern "C" int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* gamma,
+                                 const float* beta, void* y, float* stats_ws, int32_t batch, int32_t hw, float eps,
+                                 int32_t silu, mdb_stream_t stream) {
+  const int c = c1 + (x2 ? c2 : 0);
+  if (!x2) c2 = 0;
+  MDB_REQUIRE(x1 && y && gamma && beta && stats_ws, "mdb_groupnorm_f16: null pointer");
+  MDB_REQUIRE(c % 32 == 0 && c1 % 8 == 0 && c2 % 8 == 0 && c / 32 >= 8,
+              "mdb_groupnorm_f16: channels must be multiples of 8, c %% 32 == 0 and c/32 >= 8 (c1=%d c2=%d)", c1, c2);
+  MDB_REQUIRE(c / 8 <= 512, "mdb_groupnorm_f16: too many channels (%d)", c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MDB_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * batch * 64, st));
+  const int vecs = c / 8;
+  int threads = ((512 / vecs) * vecs);  // whole number of row phases
+  if (threads < vecs) threads = vecs;
+  dim3 grid((hw + kGnRowsPerCta - 1) / kGnRowsPerCta, batch);
+  gn_stats_kernel<<<grid, threads, 64 * sizeof(float), st>>>(static_cast<const __half*>(x1), c1,
+                                                             static_cast<const __half*>(x2), c2, stats_ws, hw);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  const long long total = static_cast<long long>(batch) * hw * vecs;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gn_apply_kernel<<<blocks, 256, 0, st>>>(static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2,
+                                          gamma, beta, stats_ws, static_cast<__half*>(y), batch, hw, eps, silu);
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch(2);
+  return MDB_OK;
+}
+
+extern "C" int mdb_layernorm_f16(const void* x, const float* gamma, const float* beta, void* y, int64_t rows,
+                                 int32_t c, float eps, mdb_stream_t stream) {
+  MDB_REQUIRE(x && y && gamma && beta, "mdb_layernorm_f16: null pointer");
+  MDB_REQUIRE(c % 64 == 0 && c <= 1280, "mdb_layernorm_f16: c must be a multiple of 64 and <= 1280 (c=%d)", c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int vpl = c / 64;
+  const int threads = 256;
+  const int blocks = static_cast<int>((rows * 32 + threads - 1) / threads);
+  const __half* xp = static_cast<const __half*>(x);
+  __half* yp = static_cast<__half*>(y);
+#define MDB_LN_CASE(V)                                                                       \
+  case V:                                                                                    \
+    layernorm_kernel<V><<<blocks, threads, 0, st>>>(xp, gamma, beta, yp, rows, c, eps);      \
+    break;
+  switch (vpl) {
+    MDB_LN_CASE(5)
+    MDB_LN_CASE(10)
+    MDB_LN_CASE(20)
+    default:
+      set_error("mdb_layernorm_f16: unsupported width %d (320, 640, 1280)", c);
+      return MDB_ERR_UNSUPPORTED;
+  }
+#undef MDB_LN_CASE
+  MDB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return MDB_OK;
+}
