@@ -126,7 +126,8 @@ int mdb_layernorm_f16(const void* x, const float* gamma, const float* beta, void
  * (cin or cout not a multiple of 64): the ControlNet hint encoder (cldm.py:599-615), the 4->320
  * input conv (openaimodel.py:554-558) and the 320->4 output conv (openaimodel.py:744-748).
  *   x NHWC fp16 [B][h][w][cin]; wt fp16 [cout][3][3][cin]; y NHWC fp16 [B][ho][wo][cout];
- *   optional residual (same shape as y) added before the optional SiLU is applied? No: y = act(conv+bias) + residual */
+ *   y = act(conv(x) + bias) + residual, act = SiLU when silu != 0, residual (same shape as y) optional
+ *   (the ControlNet's `h += guided_hint`, cldm.py:745-749). */
 int mdb_conv3x3_direct_f16(const void* x, const void* wt, const float* bias, const void* residual, void* y,
                            int32_t batch, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t stride,
                            int32_t silu, mdb_stream_t stream);
@@ -160,10 +161,11 @@ int mdb_nhwc_f16_to_nchw_f32(const void* x, float* y, int32_t batch, int32_t c, 
 /* CFG combine + DDIM update in one pass (ddim.py:605,617-645; eps-parameterisation):
  *   e = e_u + scale (e_c - e_u); pred_x0 = (x - sqrt(1-a_t) e)/sqrt(a_t);
  *   x_prev = sqrt(a_prev) pred_x0 + sqrt(1 - a_prev - sigma^2) e + sigma * noise   (noise may be NULL when sigma == 0)
- * all tensors fp32, n elements. */
+ * all tensors fp32, n elements.  coef is a DEVICE array of 6 floats
+ *   {scale, sqrt(a_t), sqrt(a_prev), sqrt(1 - a_prev - sigma^2), sigma, sqrt(1 - a_t)}
+ * so that one captured CUDA graph serves every DDIM step. */
 int mdb_cfg_ddim_update_f32(const float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_prev,
-                            float* pred_x0, int64_t n, float scale, float a_t, float a_prev, float sigma,
-                            float sqrt_one_minus_a_t, mdb_stream_t stream);
+                            float* pred_x0, int64_t n, const float* coef, mdb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -247,8 +247,12 @@ __global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, float*
 
 __global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ ec,
                                        const float* __restrict__ eu, const float* __restrict__ noise,
-                                       float* __restrict__ x_prev, float* __restrict__ pred_x0, long long n, float scale,
-                                       float sqrt_at, float sqrt_aprev, float dir_coef, float sigma, float s1m) {
+                                       float* __restrict__ x_prev, float* __restrict__ pred_x0, long long n,
+                                       const float* __restrict__ coef) {
+  // coef (device, so one captured CUDA graph serves all 50 steps):
+  //   {cfg scale, sqrt(a_t), sqrt(a_prev), sqrt(1 - a_prev - sigma^2), sigma, sqrt(1 - a_t)}
+  const float scale = coef[0], sqrt_at = coef[1], sqrt_aprev = coef[2], dir_coef = coef[3], sigma = coef[4],
+              s1m = coef[5];
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float u = eu[i];
@@ -395,14 +399,11 @@ extern "C" int mdb_nhwc_f16_to_nchw_f32(const void* x, float* y, int32_t batch, 
 }
 
 extern "C" int mdb_cfg_ddim_update_f32(const float* x, const float* eps_c, const float* eps_u, const float* noise,
-                                       float* x_prev, float* pred_x0, int64_t n, float scale, float a_t, float a_prev,
-                                       float sigma, float sqrt_one_minus_a_t, mdb_stream_t stream) {
-  MDB_REQUIRE(x && eps_c && eps_u && x_prev && pred_x0 && n > 0, "mdb_cfg_ddim_update_f32: bad arguments");
-  MDB_REQUIRE(sigma == 0.f || noise != nullptr, "mdb_cfg_ddim_update_f32: sigma != 0 needs a noise tensor");
-  const float dir = sqrtf(fmaxf(1.0f - a_prev - sigma * sigma, 0.f));
-  cfg_ddim_update_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, eps_c, eps_u, sigma != 0.f ? noise : nullptr, x_prev, pred_x0, n, scale, sqrtf(a_t), sqrtf(a_prev), dir, sigma,
-      sqrt_one_minus_a_t);
+                                       float* x_prev, float* pred_x0, int64_t n, const float* coef,
+                                       mdb_stream_t stream) {
+  MDB_REQUIRE(x && eps_c && eps_u && x_prev && pred_x0 && coef && n > 0, "mdb_cfg_ddim_update_f32: bad arguments");
+  cfg_ddim_update_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, eps_c, eps_u, noise, x_prev,
+                                                                                     pred_x0, n, coef);
   MDB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return MDB_OK;

@@ -1,0 +1,533 @@
+"""Host-side schedule of the denoising hot path over the sm_100a kernels (magicdance_b200.ops).
+
+Implements, for the reference's three networks and their glue:
+  ControlledUnetModelAttnPose.forward   model_lib/ControlNet/cldm/cldm.py:59-112
+  ControlNetReferenceOnly.forward       cldm.py:469-497   ('write' mode -> attention bank)
+  ControlNet.forward                    cldm.py:736-757   (13 pose residuals)
+  ControlLDMReferenceOnlyPose.apply_model  cldm.py:1099-1117
+built from the blocks of ldm/modules/diffusionmodules/openaimodel.py:79-295 and
+ldm/modules/attention.py:50-77,146-385.
+
+Data layout in HBM: activations fp16 channels-last, held as 2-D [B*H*W, C] matrices (the same
+buffer is the NHWC image for convolutions and the token matrix for the transformer blocks, so
+the reference's `b c h w -> b (h w) c` rearranges vanish); weights fp16 K-major (see pack_*);
+norm parameters, biases and the timestep path fp32.
+
+Weights are read from a plain state dict with the reference's key names, repacked
+once here.  Nothing in this file computes on the CPU or through torch operators on the per-step
+path: torch only allocates buffers.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+
+UNET = "model.diffusion_model."
+APPEARANCE = "appearance_control_model."
+POSE = "pose_control_model."
+
+
+@dataclass(frozen=True)
+class NetConfig:
+    """kwargs of the three nets in models/cldm_v15_reference_only_pose.yaml:21-72"""
+    in_channels: int = 4
+    out_channels: int = 4
+    hint_channels: int = 3
+    model_channels: int = 320
+    attention_resolutions: tuple = (4, 2, 1)
+    num_res_blocks: int = 2
+    channel_mult: tuple = (1, 2, 4, 4)
+    num_heads: int = 8
+    context_dim: int = 768
+
+    @staticmethod
+    def from_kwargs(**kw):
+        keys = NetConfig.__dataclass_fields__.keys()
+        d = {k: (tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in kw.items() if k in keys}
+        return NetConfig(**d)
+
+
+def block_plan(cfg: NetConfig):
+    """(input_blocks, middle_block, output_blocks) as lists of (kind, index-in-block, cin, cout);
+    mirrors how UNetModel.__init__ (openaimodel.py:562-750) lays out its ModuleLists, which fixes
+    the state-dict key of every layer."""
+    mc = cfg.model_channels
+    inp = [[("conv_in", 0, cfg.in_channels, mc)]]
+    chans = [mc]
+    ch, ds = mc, 1
+    for level, mult in enumerate(cfg.channel_mult):
+        for _ in range(cfg.num_res_blocks):
+            blk = [("res", 0, ch, mult * mc)]
+            ch = mult * mc
+            if ds in cfg.attention_resolutions:
+                blk.append(("attn", 1, ch, ch))
+            inp.append(blk)
+            chans.append(ch)
+        if level != len(cfg.channel_mult) - 1:
+            inp.append([("down", 0, ch, ch)])
+            chans.append(ch)
+            ds *= 2
+    mid = [("res", 0, ch, ch), ("attn", 1, ch, ch), ("res", 2, ch, ch)]
+    out = []
+    for level, mult in list(enumerate(cfg.channel_mult))[::-1]:
+        for i in range(cfg.num_res_blocks + 1):
+            ich = chans.pop()
+            blk = [("res", 0, ch + ich, mult * mc)]
+            ch = mult * mc
+            if ds in cfg.attention_resolutions:
+                blk.append(("attn", len(blk), ch, ch))
+            if level and i == cfg.num_res_blocks:
+                blk.append(("up", len(blk), ch, ch))
+                ds //= 2
+            out.append(blk)
+    return inp, mid, out
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing
+# ------------------------------------------------------------------------------------------------
+def _f16(t, device):
+    return t.detach().to(device=device, dtype=torch.float16).contiguous()
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def pack_conv3x3(w, device):
+    """Conv2d OIHW fp32 -> [O][kh][kw][I] fp16 viewed as [O, 9*I] (K order = tap-major, channel-minor)."""
+    o, i, kh, kw = w.shape
+    return _f16(w.detach().to(device).permute(0, 2, 3, 1).reshape(o, kh * kw * i), device)
+
+
+def pack_conv1x1(w, device):
+    return _f16(w.detach().reshape(w.shape[0], w.shape[1]), device)
+
+
+def pack_geglu(w, b, device):
+    """GEGLU.proj (attention.py:53-56): rows [0,4C) are values, [4C,8C) gates.  Interleave them in
+    blocks of 32 rows [value | gate] so that one GEMM tile holds matching value/gate columns."""
+    n = w.shape[0] // 2
+    idx = torch.arange(n).reshape(-1, 32)
+    order = torch.cat([idx, idx + n], dim=1).reshape(-1)
+    return _f16(w.detach()[order], device), _f32(b.detach()[order], device)
+
+
+class ResW:
+    pass
+
+
+class AttnW:
+    pass
+
+
+class PackedNet:
+    """One network's weights (UNet / appearance twin / pose ControlNet) repacked for the kernels."""
+
+    def __init__(self, sd, prefix, cfg: NetConfig, kind: str, device):
+        self.cfg, self.kind, self.prefix, self.device = cfg, kind, prefix, device
+        self.inp, self.mid, self.out = block_plan(cfg)
+        g = lambda k: sd[prefix + k]
+        mc = cfg.model_channels
+        self.te0_w, self.te0_b = _f16(g("time_embed.0.weight"), device), _f32(g("time_embed.0.bias"), device)
+        self.te2_w, self.te2_b = _f16(g("time_embed.2.weight"), device), _f32(g("time_embed.2.bias"), device)
+        self.layers = {}
+        emb_w, emb_b, off = [], [], 0
+        blocks = [(f"input_blocks.{i}.", b) for i, b in enumerate(self.inp)]
+        blocks.append(("middle_block.", self.mid))
+        if kind != "controlnet":
+            blocks += [(f"output_blocks.{i}.", b) for i, b in enumerate(self.out)]
+        for bp, blk in blocks:
+            for kind_, j, cin, cout in blk:
+                p = f"{bp}{j}."
+                if kind_ == "conv_in":
+                    self.layers[p] = (pack_conv3x3(g(p + "weight"), device), _f32(g(p + "bias"), device))
+                elif kind_ == "res":
+                    r = ResW()
+                    r.cin, r.cout = cin, cout
+                    r.gn1 = (_f32(g(p + "in_layers.0.weight"), device), _f32(g(p + "in_layers.0.bias"), device))
+                    r.w1 = pack_conv3x3(g(p + "in_layers.2.weight"), device)
+                    r.gn2 = (_f32(g(p + "out_layers.0.weight"), device), _f32(g(p + "out_layers.0.bias"), device))
+                    r.w2 = pack_conv3x3(g(p + "out_layers.3.weight"), device)
+                    r.b2 = _f32(g(p + "out_layers.3.bias"), device)
+                    if (prefix + p + "skip_connection.weight") in sd:
+                        r.skip_w = pack_conv1x1(g(p + "skip_connection.weight"), device)
+                        r.skip_b = _f32(g(p + "skip_connection.bias"), device)
+                    else:
+                        r.skip_w = r.skip_b = None
+                    # emb_layers Linear (openaimodel.py:238-244) stacked for one skinny GEMM per call;
+                    # the first conv's bias is folded into the stacked bias.
+                    emb_w.append(g(p + "emb_layers.1.weight").detach())
+                    emb_b.append(g(p + "emb_layers.1.bias").detach() + g(p + "in_layers.2.bias").detach())
+                    r.emb_off = off
+                    off += cout
+                    self.layers[p] = r
+                elif kind_ == "attn":
+                    self.layers[p] = self._pack_attn(g, p, cin, device)
+                elif kind_ == "down":
+                    self.layers[p] = (pack_conv3x3(g(p + "op.weight"), device), _f32(g(p + "op.bias"), device))
+                elif kind_ == "up":
+                    self.layers[p] = (pack_conv3x3(g(p + "conv.weight"), device), _f32(g(p + "conv.bias"), device))
+        self.emb_w = _f16(torch.cat(emb_w, 0), device)
+        self.emb_b = _f32(torch.cat(emb_b, 0), device)
+        self.emb_total = off
+        if kind == "unet":
+            self.out_gn = (_f32(g("out.0.weight"), device), _f32(g("out.0.bias"), device))
+            self.out_w, self.out_b = pack_conv3x3(g("out.2.weight"), device), _f32(g("out.2.bias"), device)
+        if kind == "controlnet":
+            self.hint = []
+            for i in range(8):
+                w = g(f"input_hint_block.{2 * i}.weight")
+                self.hint.append((pack_conv3x3(w, device), _f32(g(f"input_hint_block.{2 * i}.bias"), device),
+                                  w.shape[1], w.shape[0]))
+            self.zero = []
+            for i in range(len(self.inp)):
+                self.zero.append((pack_conv1x1(g(f"zero_convs.{i}.0.weight"), device),
+                                  _f32(g(f"zero_convs.{i}.0.bias"), device)))
+            self.zero.append((pack_conv1x1(g("middle_block_out.0.weight"), device),
+                              _f32(g("middle_block_out.0.bias"), device)))
+
+    def _pack_attn(self, g, p, c, device):
+        a = AttnW()
+        a.c, a.heads, a.d = c, self.cfg.num_heads, c // self.cfg.num_heads
+        a.gn = (_f32(g(p + "norm.weight"), device), _f32(g(p + "norm.bias"), device))
+        a.pin_w, a.pin_b = pack_conv1x1(g(p + "proj_in.weight"), device), _f32(g(p + "proj_in.bias"), device)
+        a.pout_w, a.pout_b = pack_conv1x1(g(p + "proj_out.weight"), device), _f32(g(p + "proj_out.bias"), device)
+        t = p + "transformer_blocks.0."
+        for i in (1, 2, 3):
+            setattr(a, f"ln{i}", (_f32(g(t + f"norm{i}.weight"), device), _f32(g(t + f"norm{i}.bias"), device)))
+        # self-attention: q and k projections share one GEMM ([2C, C]); v is produced transposed
+        a.wqk = _f16(torch.cat([g(t + "attn1.to_q.weight").detach(), g(t + "attn1.to_k.weight").detach()], 0), device)
+        a.wv = _f16(g(t + "attn1.to_v.weight"), device)
+        a.wo, a.bo = _f16(g(t + "attn1.to_out.0.weight"), device), _f32(g(t + "attn1.to_out.0.bias"), device)
+        a.wq2 = _f16(g(t + "attn2.to_q.weight"), device)
+        a.wk2 = _f16(g(t + "attn2.to_k.weight"), device)
+        a.wv2 = _f16(g(t + "attn2.to_v.weight"), device)
+        a.wo2, a.bo2 = _f16(g(t + "attn2.to_out.0.weight"), device), _f32(g(t + "attn2.to_out.0.bias"), device)
+        a.wff1, a.bff1 = pack_geglu(g(t + "ff.net.0.proj.weight"), g(t + "ff.net.0.proj.bias"), device)
+        a.wff2, a.bff2 = _f16(g(t + "ff.net.2.weight"), device), _f32(g(t + "ff.net.2.bias"), device)
+        return a
+
+    def attn_layers(self):
+        """AttnW objects in execution order (the order of the attention bank, attention.py:287-298)."""
+        order = []
+        blocks = [(f"input_blocks.{i}.", b) for i, b in enumerate(self.inp)] + [("middle_block.", self.mid)]
+        if self.kind != "controlnet":
+            blocks += [(f"output_blocks.{i}.", b) for i, b in enumerate(self.out)]
+        for bp, blk in blocks:
+            for kind_, j, _, _ in blk:
+                if kind_ == "attn":
+                    order.append(self.layers[f"{bp}{j}."])
+        return order
+
+
+# ------------------------------------------------------------------------------------------------
+# execution
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Act:
+    """fp16 channels-last activation: data is [B*H*W, C]"""
+    data: torch.Tensor
+    b: int
+    h: int
+    w: int
+
+    @property
+    def c(self):
+        return self.data.shape[1]
+
+    @property
+    def hw(self):
+        return self.h * self.w
+
+
+def _igemm_ok(h, w, c):
+    hw = h * w
+    if c % 64:
+        return False
+    if hw >= 128:
+        return 128 % w == 0 and hw % 128 == 0
+    return 128 % hw == 0
+
+
+def _auto_splits(m, n, k):
+    """Split-K factor: small-M layers (8x8 / 16x16 latents) would otherwise run on a handful of SMs and
+    stream their weights at a fraction of HBM bandwidth."""
+    if os.environ.get("MDB_SPLITK", "1") == "0":
+        return 1
+    bn = 160 if n % 160 == 0 else 128
+    tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
+    chunks = k // 64
+    if tiles >= 96 or chunks < 8:
+        return 1
+    s = min(16, max(1, 148 // tiles), chunks // 4)
+    return max(1, s)
+
+
+class DenoiseEngine:
+    """Runs the three networks of ControlLDMReferenceOnlyPose on one GPU."""
+
+    def __init__(self, state_dict, cfg: NetConfig | None = None, device="cuda"):
+        ops.ensure_device()
+        self.cfg = cfg or NetConfig()
+        self.device = torch.device(device)
+        self.unet = PackedNet(state_dict, UNET, self.cfg, "unet", self.device)
+        self.appearance = PackedNet(state_dict, APPEARANCE, self.cfg, "appearance", self.device)
+        self.pose = PackedNet(state_dict, POSE, self.cfg, "controlnet", self.device)
+        self._ctx_cache = {}
+
+    # ---- small pieces -------------------------------------------------------------------------
+    def time_bias(self, net: PackedNet, t: torch.Tensor):
+        """timestep_embedding -> time_embed MLP -> all emb_layers of the net (util.py:189-209,
+        openaimodel.py:547-551,238-244).  Returns fp32 [B, sum(cout)] = emb_out + conv1 bias."""
+        e = ops.timestep_embedding(t, self.cfg.model_channels)
+        e = ops.skinny_linear(e, net.te0_w, net.te0_b, silu_out=True)
+        e = ops.skinny_linear(e, net.te2_w, net.te2_b)
+        return ops.skinny_linear(e, net.emb_w, net.emb_b, silu_in=True)
+
+    def context_kv(self, net: PackedNet, ctx16: torch.Tensor, key):
+        """Text keys/values of every attn2 (CrossAttention.to_k/to_v on the CLIP context,
+        attention.py:172-174); depends only on the context -> cached per (net, context)."""
+        ck = (net.prefix, key)
+        hit = self._ctx_cache.get(ck)
+        if hit is not None:
+            return hit
+        b, n, cd = ctx16.shape
+        flat = ctx16.reshape(b * n, cd)
+        ldv = (n + 7) // 8 * 8
+        res = []
+        for a in net.attn_layers():
+            k = ops.gemm(flat, a.wk2)
+            # V^T [C, b*ldv]: per batch element the GEMM  wv2 @ tokens^T  writes its [C, n] block in place
+            # (columns n..ldv of each block stay zero: the kernel masks those keys, and 0 * 0 is finite)
+            vt = torch.zeros((a.c, b * ldv), dtype=torch.float16, device=self.device)
+            for i in range(b):
+                ops.gemm(a.wv2, flat[i * n:(i + 1) * n], out=vt[:, i * ldv:i * ldv + n])
+            res.append((k, vt, n, b, ldv))
+        if len(self._ctx_cache) > 8:
+            self._ctx_cache.clear()
+        self._ctx_cache[ck] = res
+        return res
+
+    # ---- blocks -------------------------------------------------------------------------------
+    def _conv3(self, x: Act, w, bias, *, cout, residual=None, bias_batch_stride=0):
+        cin = x.c
+        if _igemm_ok(x.h, x.w, cin) and cout % 8 == 0 and cout >= 64:
+            m = x.b * x.hw
+            y = ops.gemm(x.data, w, bias=bias, bias_batch_stride=bias_batch_stride, rows_per_batch=x.hw,
+                         residual=residual, conv=(x.b, x.h, x.w, cin), splits=_auto_splits(m, cout, 9 * cin))
+        else:
+            assert bias_batch_stride == 0
+            y = ops.conv3x3_direct(x.data, w, bias, batch=x.b, h=x.h, w=x.w, cin=cin, cout=cout, residual=residual)
+        return Act(y, x.b, x.h, x.w)
+
+    def _res(self, r: ResW, x: Act, skip: Act | None, emb_all):
+        x2 = None if skip is None else skip.data
+        h = ops.groupnorm(x.data, *r.gn1, batch=x.b, hw=x.hw, eps=1e-5, silu=True, x2=x2)
+        bias = emb_all[:, r.emb_off:r.emb_off + r.cout]
+        h = self._conv3(Act(h, x.b, x.h, x.w), r.w1, bias, cout=r.cout, bias_batch_stride=emb_all.stride(0))
+        h2 = ops.groupnorm(h.data, *r.gn2, batch=x.b, hw=x.hw, eps=1e-5, silu=True)
+        if r.skip_w is None:
+            assert skip is None
+            res = x.data
+        else:
+            m = x.b * x.hw
+            res = ops.gemm(x.data, r.skip_w, bias=r.skip_b, a2=x2, splits=_auto_splits(m, r.cout, r.cin))
+        return self._conv3(Act(h2, x.b, x.h, x.w), r.w2, r.b2, cout=r.cout, residual=res)
+
+    def _transformer(self, a: AttnW, x: Act, ctx_kv, mode, bank, bank_kv, bank_batches):
+        b, n, c = x.b, x.hw, a.c
+        m = b * n
+        h = ops.groupnorm(x.data, *a.gn, batch=b, hw=n, eps=1e-6, silu=False)
+        h = ops.gemm(h, a.pin_w, bias=a.pin_b, splits=_auto_splits(m, c, c))
+        # --- attn1 (self / self + bank) ---
+        n1 = ops.layernorm(h, *a.ln1)
+        if mode == "write":
+            bank.append(n1)
+        qk = ops.gemm(n1, a.wqk, splits=_auto_splits(m, 2 * c, c))
+        vt = ops.gemm(a.wv, n1, splits=_auto_splits(c, m, c))  # [C, B*N] == V^T
+        kw = {}
+        if mode == "read" and bank_kv is not None:
+            k1, vt1, nb1, kvb1 = bank_kv
+            kw = dict(k1=k1, vt1=vt1, n1=nb1, kv1_batches=kvb1, bank_batches=min(bank_batches, b))
+        at = ops.attention(qk[:, :c], qk[:, c:], vt, n, heads=a.heads, d=a.d, batch=b, nq=n, **kw)
+        h = ops.gemm(at, a.wo, bias=a.bo, residual=h, splits=_auto_splits(m, c, c))
+        # --- attn2 (text) ---
+        n2 = ops.layernorm(h, *a.ln2)
+        q2 = ops.gemm(n2, a.wq2, splits=_auto_splits(m, c, c))
+        kt, vtt, nt, kvb, ldv = ctx_kv
+        at2 = ops.attention(q2, kt, vtt, nt, heads=a.heads, d=a.d, batch=b, nq=n, kv0_batches=kvb if kvb == b else 1,
+                            ldv0_batch=ldv)
+        h = ops.gemm(at2, a.wo2, bias=a.bo2, residual=h, splits=_auto_splits(m, c, c))
+        # --- GEGLU feed-forward ---
+        n3 = ops.layernorm(h, *a.ln3)
+        ff = ops.gemm(n3, a.wff1, bias=a.bff1, epilogue=ops.EPI_GEGLU)
+        h = ops.gemm(ff, a.wff2, bias=a.bff2, residual=h, splits=_auto_splits(m, c, 4 * c))
+        y = ops.gemm(h, a.pout_w, bias=a.pout_b, residual=x.data, splits=_auto_splits(m, c, c))
+        return Act(y, x.b, x.h, x.w)
+
+    def _run_block(self, net, bp, blk, x: Act, skip, emb_all, ctx_kvs, state):
+        for kind, j, cin, cout in blk:
+            p = f"{bp}{j}."
+            lw = net.layers[p]
+            if kind == "conv_in":
+                x = self._conv3(x, lw[0], lw[1], cout=cout, residual=state.get("hint"))
+            elif kind == "res":
+                x = self._res(lw, x, skip, emb_all)
+                skip = None
+            elif kind == "attn":
+                i = state["attn_i"]
+                bank_kv = state["bank_kv"][i] if state.get("bank_kv") is not None else None
+                x = self._transformer(lw, x, ctx_kvs[i], state["mode"], state.get("bank"), bank_kv,
+                                      state.get("bank_batches", 0))
+                state["attn_i"] = i + 1
+            elif kind == "down":
+                col = ops.im2col3x3s2(x.data, batch=x.b, h=x.h, w=x.w, c=x.c)
+                m = x.b * (x.h // 2) * (x.w // 2)
+                y = ops.gemm(col, lw[0], bias=lw[1], splits=_auto_splits(m, cout, 9 * cin))
+                x = Act(y, x.b, x.h // 2, x.w // 2)
+            elif kind == "up":
+                up = ops.upsample2x(x.data, batch=x.b, h=x.h, w=x.w, c=x.c)
+                x = self._conv3(Act(up, x.b, 2 * x.h, 2 * x.w), lw[0], lw[1], cout=cout)
+        return x
+
+    # ---- the three networks -------------------------------------------------------------------
+    def _prep(self, x_nchw, context):
+        x = x_nchw.to(device=self.device, dtype=torch.float32)
+        b, c, h, w = x.shape
+        act = Act(ops.nchw_f32_to_nhwc_f16(x), b, h, w)
+        ctx16 = context.to(device=self.device, dtype=torch.float16).contiguous()
+        key = (context.data_ptr(), context._version, tuple(context.shape), str(context.device))
+        return act, ctx16, key
+
+    def appearance_write(self, ref_latent, t, context):
+        """ControlNetReferenceOnly.forward 'write' (cldm.py:469-497): returns the bank, a list of 16
+        norm1(x) token matrices [B*N_l, C_l] fp16 (attention.py:287-298).  Layers after the last
+        norm1 (dead compute in the reference) are skipped."""
+        net = self.appearance
+        x, ctx16, key = self._prep(ref_latent, context)
+        ctx_kvs = self.context_kv(net, ctx16, key)
+        emb_all = self.time_bias(net, t)
+        state = {"mode": "write", "attn_i": 0, "bank": []}
+        hs = []
+        for i, blk in enumerate(net.inp):
+            x = self._run_block(net, f"input_blocks.{i}.", blk, x, None, emb_all, ctx_kvs, state)
+            hs.append(x)
+        x = self._run_block(net, "middle_block.", net.mid, x, None, emb_all, ctx_kvs, state)
+        n_total = len(net.attn_layers())
+        for i, blk in enumerate(net.out):
+            if state["attn_i"] >= n_total:
+                break
+            x = self._run_block(net, f"output_blocks.{i}.", blk, x, hs.pop(), emb_all, ctx_kvs, state)
+        return state["bank"]
+
+    def project_bank(self, bank, batches):
+        """K/V of the bank under the DENOISING UNet's attn1.to_k/to_v (attention.py:289,307):
+        algebraically identical to projecting cat([x_norm1] + bank) (SURVEY §8a semantics 1).
+        Returns per layer (K [batches*N, C], V^T [C, batches*N], N, batches)."""
+        res = []
+        layers = self.unet.attn_layers()
+        assert len(layers) == len(bank)
+        for a, n1 in zip(layers, bank):
+            c = a.c
+            rows = n1.shape[0]
+            k1 = ops.gemm(n1, a.wqk[c:], splits=_auto_splits(rows, c, c))
+            vt1 = ops.gemm(a.wv, n1, splits=_auto_splits(c, rows, c))
+            res.append((k1, vt1, rows // batches, batches))
+        return res
+
+    def hint_features(self, pose_map):
+        """ControlNet.input_hint_block (cldm.py:599-615); depends only on the pose map."""
+        net = self.pose
+        hint = pose_map.to(device=self.device, dtype=torch.float32)
+        b, c, h, w = hint.shape
+        x = ops.nchw_f32_to_nhwc_f16(hint)
+        strides = (1, 1, 2, 1, 2, 1, 2, 1)
+        for i, ((wt, bias, cin, cout), s) in enumerate(zip(net.hint, strides)):
+            last = i == len(strides) - 1
+            if last and _igemm_ok(h, w, cin):
+                x = ops.gemm(x, wt, bias=bias, conv=(b, h, w, cin))
+            else:
+                x = ops.conv3x3_direct(x, wt, bias, batch=b, h=h, w=w, cin=cin, cout=cout, stride=s, silu=not last)
+            h, w = (h + 2 - 3) // s + 1, (w + 2 - 3) // s + 1
+        return x  # [B*h*w, model_channels]
+
+    def controlnet(self, x_noisy, hint_feat, t, context):
+        """ControlNet.forward (cldm.py:736-757) -> 13 residuals as fp16 [B*H*W, C] matrices."""
+        net = self.pose
+        x, ctx16, key = self._prep(x_noisy, context)
+        ctx_kvs = self.context_kv(net, ctx16, key)
+        emb_all = self.time_bias(net, t)
+        state = {"mode": "plain", "attn_i": 0, "hint": hint_feat}
+        outs = []
+        for i, blk in enumerate(net.inp):
+            x = self._run_block(net, f"input_blocks.{i}.", blk, x, None, emb_all, ctx_kvs, state)
+            state["hint"] = None
+            zw, zb = net.zero[i]
+            outs.append(ops.gemm(x.data, zw, bias=zb, splits=_auto_splits(x.b * x.hw, x.c, x.c)))
+        x = self._run_block(net, "middle_block.", net.mid, x, None, emb_all, ctx_kvs, state)
+        zw, zb = net.zero[-1]
+        outs.append(ops.gemm(x.data, zw, bias=zb, splits=_auto_splits(x.b * x.hw, x.c, x.c)))
+        return outs
+
+    def unet_forward(self, x_noisy, t, context, bank_kv=None, pose=None, uc=False, bank_batches=None, taps=None):
+        """ControlledUnetModelAttnPose.forward (cldm.py:59-112).  uc=True: plain SD UNet without bank
+        or pose residuals (cldm.py:70-84).  bank_kv: project_bank() output.  Returns eps as NCHW fp32."""
+        net = self.unet
+        x, ctx16, key = self._prep(x_noisy, context)
+        b = x.b
+        ctx_kvs = self.context_kv(net, ctx16, key)
+        emb_all = self.time_bias(net, t)
+        state = {"mode": "plain" if uc else "read", "attn_i": 0}
+        pose = None if (uc or pose is None) else list(pose)
+        state["bank_kv"] = None if uc else bank_kv
+        state["bank_batches"] = b if bank_batches is None else bank_batches
+        hs = []
+        for i, blk in enumerate(net.inp):
+            x = self._run_block(net, f"input_blocks.{i}.", blk, x, None, emb_all, ctx_kvs, state)
+            hs.append(x)
+            if taps is not None:
+                taps.append(x)
+        x = self._run_block(net, "middle_block.", net.mid, x, None, emb_all, ctx_kvs, state)
+        if taps is not None:
+            taps.append(x)
+        if pose is not None:
+            x = Act(ops.add(x.data, pose.pop(), batch=b), x.b, x.h, x.w)
+        for i, blk in enumerate(net.out):
+            skip = hs.pop()
+            if pose is not None:
+                skip = Act(ops.add(skip.data, pose.pop(), batch=b), skip.b, skip.h, skip.w)
+            x = self._run_block(net, f"output_blocks.{i}.", blk, x, skip, emb_all, ctx_kvs, state)
+            if taps is not None:
+                taps.append(x)
+        hn = ops.groupnorm(x.data, *net.out_gn, batch=b, hw=x.hw, eps=1e-5, silu=True)
+        y = self._conv3(Act(hn, b, x.h, x.w), net.out_w, net.out_b, cout=self.cfg.out_channels)
+        return ops.nhwc_f16_to_nchw_f32(y.data, batch=b, c=self.cfg.out_channels, h=x.h, w=x.w)
+
+    # ---- glue ---------------------------------------------------------------------------------
+    def apply_model(self, x_noisy, t, context, pose_map, reference_image_noisy, uc=False, hint_feat=None,
+                    bank_kv=None, return_parts=False):
+        """ControlLDMReferenceOnlyPose.apply_model (cldm.py:1099-1117).  Unlike the reference, the
+        unconditional call does not run the pose ControlNet whose output it would discard
+        (cldm.py:1112-1114 vs 70-84)."""
+        t = t.to(device=self.device, dtype=torch.int64)
+        bank = None
+        if not uc:
+            if bank_kv is None and reference_image_noisy is not None:
+                rb = reference_image_noisy.shape[0]
+                bank = self.appearance_write(reference_image_noisy, t[:rb], context[:rb])
+                bank_kv = self.project_bank(bank, rb)
+            if hint_feat is None:
+                hint_feat = self.hint_features(pose_map)
+            pose = self.controlnet(x_noisy, hint_feat, t, context)
+        else:
+            pose, bank_kv = None, None
+        taps = [] if return_parts else None
+        eps = self.unet_forward(x_noisy, t, context, bank_kv=bank_kv, pose=pose, uc=uc, taps=taps)
+        if return_parts:
+            return eps, bank, pose, taps
+        return eps

@@ -1,0 +1,255 @@
+"""Torch-tensor front end of the C ABI (include/magicdance_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current CUDA stream; every function
+below launches OUR kernels through ctypes.  No function has a PyTorch/CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+EPI_NONE, EPI_GEGLU = 0, 1
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"magicdance_b200: {name} must be a CUDA tensor (no CPU fallback exists for the hot path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"magicdance_b200: {name} must be {dtype}, got {t.dtype}")
+
+
+def ensure_device():
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("magicdance_b200: no CUDA device visible; the hot path has no CPU fallback")
+    _lib.check(lib.mdb_device_check(), "device_check")
+    return lib
+
+
+def launch_count() -> int:
+    return int(_lib.load().mdb_launch_count())
+
+
+_ws_cache = {}
+
+
+def _workspace(key, numel, dtype, device):
+    t = _ws_cache.get((key, device))
+    if t is None or t.numel() < numel or t.dtype != dtype:
+        t = torch.empty(max(numel, 1), dtype=dtype, device=device)
+        _ws_cache[(key, device)] = t
+    return t
+
+
+def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, residual=None, epilogue=EPI_NONE,
+         a2=None, conv=None, splits=1, m=None):
+    """D = epilogue(A @ W^T).  a: [M, K1] fp16 (last dim contiguous, row stride arbitrary) or, with
+    conv=(nb, h, w, c), an NHWC activation; w: [N, K] fp16; a2: optional second K-range source."""
+    lib = _lib.load()
+    _chk(a, torch.float16, "a")
+    _chk(w, torch.float16, "w")
+    g = _lib.GemmDesc()
+    n, k = w.shape
+    if conv is not None:
+        nb, h, wd, c = conv
+        m = nb * h * wd
+        assert a.is_contiguous() and a.numel() == m * c
+        g.conv, g.nb, g.h, g.w, g.c = 1, nb, h, wd, c
+        g.a, g.lda, g.k1 = a.data_ptr(), c, k
+    else:
+        assert a.dim() == 2 and a.stride(1) == 1
+        m = a.shape[0] if m is None else m
+        g.a, g.lda, g.k1 = a.data_ptr(), a.stride(0), a.shape[1]
+        if a2 is not None:
+            _chk(a2, torch.float16, "a2")
+            assert a2.dim() == 2 and a2.stride(1) == 1 and a2.shape[0] == a.shape[0]
+            g.a2, g.lda2 = a2.data_ptr(), a2.stride(0)
+            assert a.shape[1] + a2.shape[1] == k
+        else:
+            assert a.shape[1] == k, (a.shape, w.shape)
+    n_out = n // 2 if epilogue == EPI_GEGLU else n
+    if out is None:
+        out = torch.empty((m, n_out), dtype=torch.float16, device=a.device)
+    _chk(out, torch.float16, "out")
+    assert out.dim() == 2 and out.stride(1) == 1 and out.shape[0] >= m and out.shape[1] == n_out, (out.shape, m, n_out)
+    assert w.stride(1) == 1
+    g.b, g.ldb = w.data_ptr(), w.stride(0)
+    g.d, g.ldd = out.data_ptr(), out.stride(0)
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+        g.bias, g.bias_batch_stride, g.rows_per_batch = bias.data_ptr(), bias_batch_stride, rows_per_batch
+    if residual is not None:
+        _chk(residual, torch.float16, "residual")
+        assert residual.dim() == 2 and residual.stride(1) == 1
+        g.residual, g.ldr = residual.data_ptr(), residual.stride(0)
+    g.m, g.n, g.k, g.epilogue = m, n, k, epilogue
+    if splits > 1:
+        ws = _workspace("splitk", m * n, torch.float32, a.device)
+        g.splits, g.splitk_ws = splits, ws.data_ptr()
+    else:
+        g.splits = 1
+    _lib.check(lib.mdb_gemm_f16(C.byref(g), _stream()), "gemm_f16")
+    return out
+
+
+def attention(q, k0, vt0, n0, *, heads, d, batch, nq, out=None, kv0_batches=None, ldv0_batch=None,
+              k1=None, vt1=None, n1=0, kv1_batches=1, ldv1_batch=None, bank_batches=0, scale=None):
+    """softmax([q k0^T | q k1^T] * scale) [v0 ; v1]; k*: [rows, heads*d] (row stride free), vt*: [heads*d, cols]."""
+    lib = _lib.load()
+    for t, nm in ((q, "q"), (k0, "k0"), (vt0, "vt0")):
+        _chk(t, torch.float16, nm)
+    a = _lib.AttnDesc()
+    hd = heads * d
+    if out is None:
+        out = torch.empty((batch * nq, hd), dtype=torch.float16, device=q.device)
+    a.q, a.ldq = q.data_ptr(), q.stride(0)
+    a.k0, a.ldk0, a.vt0, a.ldvt0 = k0.data_ptr(), k0.stride(0), vt0.data_ptr(), vt0.stride(0)
+    a.n0 = n0
+    a.kv0_batches = batch if kv0_batches is None else kv0_batches
+    a.ldv0_batch = n0 if ldv0_batch is None else ldv0_batch
+    if n1 > 0:
+        _chk(k1, torch.float16, "k1")
+        _chk(vt1, torch.float16, "vt1")
+        a.k1, a.ldk1, a.vt1, a.ldvt1 = k1.data_ptr(), k1.stride(0), vt1.data_ptr(), vt1.stride(0)
+        a.n1, a.kv1_batches = n1, kv1_batches
+        a.ldv1_batch = n1 if ldv1_batch is None else ldv1_batch
+        a.bank_batches = bank_batches
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    a.batch, a.heads, a.d, a.nq = batch, heads, d, nq
+    a.scale = float(d) ** -0.5 if scale is None else scale
+    _lib.check(lib.mdb_attention_f16(C.byref(a), _stream()), "attention_f16")
+    return out
+
+
+def groupnorm(x1, gamma, beta, *, batch, hw, eps, silu, x2=None, out=None):
+    lib = _lib.load()
+    _chk(x1, torch.float16, "x1")
+    c1 = x1.shape[-1]
+    c2 = 0 if x2 is None else x2.shape[-1]
+    assert x1.is_contiguous() and (x2 is None or x2.is_contiguous())
+    if out is None:
+        out = torch.empty((batch * hw, c1 + c2), dtype=torch.float16, device=x1.device)
+    stats = _workspace("gnstats", batch * 64, torch.float32, x1.device)
+    _lib.check(lib.mdb_groupnorm_f16(x1.data_ptr(), c1, _ptr(x2), c2, gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                     stats.data_ptr(), batch, hw, eps, int(silu), _stream()), "groupnorm_f16")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    lib = _lib.load()
+    _chk(x, torch.float16, "x")
+    assert x.is_contiguous()
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(lib.mdb_layernorm_f16(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows, c, eps,
+                                     _stream()), "layernorm_f16")
+    return out
+
+
+def conv3x3_direct(x, wt, bias, *, batch, h, w, cin, cout, stride=1, silu=False, residual=None, out=None):
+    lib = _lib.load()
+    _chk(x, torch.float16, "x")
+    ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+    if out is None:
+        out = torch.empty((batch * ho * wo, cout), dtype=torch.float16, device=x.device)
+    _lib.check(lib.mdb_conv3x3_direct_f16(x.data_ptr(), wt.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(), batch,
+                                          h, w, cin, cout, stride, int(silu), _stream()), "conv3x3_direct_f16")
+    return out
+
+
+def im2col3x3s2(x, *, batch, h, w, c):
+    lib = _lib.load()
+    _chk(x, torch.float16, "x")
+    col = torch.empty((batch * (h // 2) * (w // 2), 9 * c), dtype=torch.float16, device=x.device)
+    _lib.check(lib.mdb_im2col3x3s2_f16(x.data_ptr(), col.data_ptr(), batch, h, w, c, _stream()), "im2col3x3s2_f16")
+    return col
+
+
+def upsample2x(x, *, batch, h, w, c):
+    lib = _lib.load()
+    _chk(x, torch.float16, "x")
+    y = torch.empty((batch * 4 * h * w, c), dtype=torch.float16, device=x.device)
+    _lib.check(lib.mdb_upsample2x_f16(x.data_ptr(), y.data_ptr(), batch, h, w, c, _stream()), "upsample2x_f16")
+    return y
+
+
+def add(a, b, *, batch, b_batches=None, out=None):
+    lib = _lib.load()
+    _chk(a, torch.float16, "a")
+    _chk(b, torch.float16, "b")
+    if out is None:
+        out = torch.empty_like(a)
+    n_per = a.numel() // batch
+    bb = batch if b_batches is None else b_batches
+    assert b.numel() == n_per * bb
+    _lib.check(lib.mdb_add_f16(a.data_ptr(), b.data_ptr(), out.data_ptr(), n_per, batch, bb, _stream()), "add_f16")
+    return out
+
+
+def timestep_embedding(t, dim):
+    lib = _lib.load()
+    _chk(t, torch.int64, "t")
+    out = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
+    _lib.check(lib.mdb_timestep_embedding_f32(t.data_ptr(), out.data_ptr(), t.shape[0], dim, _stream()),
+               "timestep_embedding_f32")
+    return out
+
+
+def skinny_linear(x, w, bias, *, silu_in=False, silu_out=False):
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    _chk(w, torch.float16, "w")
+    rows, k = x.shape
+    n = w.shape[0]
+    assert w.shape[1] == k and x.is_contiguous() and w.is_contiguous()
+    out = torch.empty((rows, n), dtype=torch.float32, device=x.device)
+    _lib.check(lib.mdb_skinny_linear_f32(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), rows, n, k,
+                                         int(silu_in), int(silu_out), _stream()), "skinny_linear_f32")
+    return out
+
+
+def nchw_f32_to_nhwc_f16(x):
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    x = x.contiguous()
+    b, c, h, w = x.shape
+    y = torch.empty((b * h * w, c), dtype=torch.float16, device=x.device)
+    _lib.check(lib.mdb_nchw_f32_to_nhwc_f16(x.data_ptr(), y.data_ptr(), b, c, h, w, _stream()), "nchw_f32_to_nhwc_f16")
+    return y
+
+
+def nhwc_f16_to_nchw_f32(x, *, batch, c, h, w, out=None):
+    lib = _lib.load()
+    _chk(x, torch.float16, "x")
+    if out is None:
+        out = torch.empty((batch, c, h, w), dtype=torch.float32, device=x.device)
+    _lib.check(lib.mdb_nhwc_f16_to_nchw_f32(x.data_ptr(), out.data_ptr(), batch, c, h, w, _stream()),
+               "nhwc_f16_to_nchw_f32")
+    return out
+
+
+def cfg_ddim_update(x, eps_c, eps_u, coef, noise=None, x_prev=None, pred_x0=None):
+    """coef: device fp32[6] = {scale, sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma, sqrt(1-a_t)}"""
+    lib = _lib.load()
+    for t, nm in ((x, "x"), (eps_c, "eps_c"), (eps_u, "eps_u"), (coef, "coef")):
+        _chk(t, torch.float32, nm)
+    if x_prev is None:
+        x_prev = torch.empty_like(x)
+    if pred_x0 is None:
+        pred_x0 = torch.empty_like(x)
+    _lib.check(lib.mdb_cfg_ddim_update_f32(x.data_ptr(), eps_c.data_ptr(), eps_u.data_ptr(), _ptr(noise),
+                                           x_prev.data_ptr(), pred_x0.data_ptr(), x.numel(), coef.data_ptr(), _stream()),
+               "cfg_ddim_update_f32")
+    return x_prev, pred_x0
