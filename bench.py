@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the MagicPose DDIM denoising hot path on B200 (contract: see the task statement).
+
+    python bench.py --gpus 1 --steps 50 --warmup 3            # ours, one frame, full 50-step chain
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     # frames sharded over N GPUs
+    python bench.py --impl reference --steps K --warmup W     # the reference's path on the host CPUs
+
+A "step" is one p_sample_ddim (ddim.py:518-645) for the per-GPU batch of frames: the pose
+ControlNet, the UNet in 'read' mode with the appearance bank, the unconditional UNet, CFG combine
+and DDIM update.  The appearance ('write') pass runs once per timestep per SEQUENCE: the timesteps
+are dealt over the ranks and exchanged with one all-gather before the steps; that
+work and the exchange are inside the timed region.  At N=1 and one frame this is exactly
+BASELINE.json configs[1].
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "denoise-steps/sec @512x512 50-step DDIM"
+UNIT = "frame-steps/s"
+# algorithmic FLOPs (SURVEY §8d / BASELINE.md §2, torch FlopCounterMode on the reference modules)
+GF_FRAME_STEP = 2037.9   # pose ControlNet + UNet-read + UNet-uncond, per frame per step
+GF_REF_STEP = 803.18     # appearance 'write' pass, per reference per timestep
+GF_REF_AS_EXECUTED = 3124.4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("MDB_BENCH_BATCH", "1")), help="frames per GPU")
+    ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_step_seconds(sd, latent, steps, warmup, torch):
+    """Times the oracle port of p_sample_ddim (oracle/restatement.py) on the host cores."""
+    from oracle import restatement as R  # the ONE place bench.py executes oracle/: the CPU baseline
+    from magicdance_b200 import synth
+    import numpy as np
+    inp = synth.synth_inputs(1, latent, seed=0, shared_reference=True)
+    sched = R.ddim_schedule(R.make_schedule()["alphas_cumprod"].astype(np.float32).astype(np.float64))
+    x = inp["x"]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            index = 49 - (i % 50)
+            t = torch.full((1,), int(sched["timesteps"][index]), dtype=torch.long)
+            t0 = time.perf_counter()
+            # as executed by the reference: appearance + pose + UNet-read, then pose (discarded) + UNet-uc
+            x_prev, _, _, _ = R.p_sample_ddim(sd, x, t, index, inp["context"], inp["pose"], inp["ref"], sched, scale=7.0)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            x = x_prev
+    return sum(times) / len(times)
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from magicdance_b200 import synth
+    torch.set_grad_enabled(False)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.synth_state_dict(seed=0)
+    steps = max(1, min(args.steps, int(os.environ.get("MDB_REF_MAX_STEPS", "2"))))
+    warm = 1 if args.warmup > 0 else 0
+    sec = cpu_port_step_seconds(sd, args.latent, steps, warm, torch)
+    val = 1.0 / sec
+    sample = (f"{steps} timed p_sample_ddim step(s) of the 50-step chain (+{warm} warm-up), B=1, fp32, latent "
+              f"{args.latent}x{args.latent}; per-step time extrapolates linearly to the chain")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "512x512, 50-step DDIM, batch 1, appearance-control + OpenPose ControlNet (CPU)",
+                   "latent": args.latent, "frames_per_gpu": 1, "cfg_scale": 7.0},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def roofline_probe(torch, ops, trace, peaks):
+    """Replays every distinct tensor-core GEMM/conv launch of one step standalone, L2 flushed before
+    each launch, CUDA-event timed; achieved = sum(2MNK) / sum(avg duration x count)."""
+    from collections import Counter
+    cnt = Counter(trace)
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device="cuda")
+    tot_fl, tot_t, rows = 0.0, 0.0, []
+    for (m, n, k, conv, epi, splits, k2), c in cnt.items():
+        w = torch.randn(n, k, device="cuda", dtype=torch.float16) * k ** -0.5
+        if conv is not None:
+            a = torch.randn(m, conv[3], device="cuda", dtype=torch.float16)
+            kw = dict(conv=conv)
+        elif k2:
+            a = torch.randn(m, k - k2, device="cuda", dtype=torch.float16)
+            kw = dict(a2=torch.randn(m, k2, device="cuda", dtype=torch.float16))
+        else:
+            a = torch.randn(m, k, device="cuda", dtype=torch.float16)
+            kw = {}
+        reps, ts = 5, []
+        for r in range(reps + 1):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.gemm(a, w, epilogue=epi, splits=splits, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            if r:
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+        t = sum(ts) / len(ts)
+        fl = 2.0 * m * n * k
+        tot_fl += fl * c
+        tot_t += t * c
+        rows.append((fl * c, t * c, (m, n, k, conv is not None, splits), c))
+    rows.sort(key=lambda r: -r[1])
+    peak = peaks.get("bf16_tflops", 1590.0)
+    ach = tot_fl / tot_t / 1e12
+    top = [{"shape_mnk_conv_splits": list(map(int, r[2][:3])) + [bool(r[2][3]), int(r[2][4])], "count": r[3],
+            "ms_total": r[1] * 1e3, "tflops": r[0] / r[1] / 1e12} for r in rows[:6]]
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + 3x3 implicit-GEMM conv)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1590",
+            "traffic": None, "gemm_gflop_per_step": tot_fl / 1e9, "gemm_ms_per_step_isolated": tot_t * 1e3,
+            "launches_per_step": int(sum(cnt.values())), "top_by_time": top}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from magicdance_b200 import ops, synth, parallel
+    from magicdance_b200.engine import DenoiseEngine
+    from magicdance_b200.pipeline import DenoisePipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    torch.set_grad_enabled(False)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = {}
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+
+    sd = synth.synth_state_dict(seed=0)
+    eng = DenoiseEngine(sd, device=f"cuda:{local}")
+    if args.no_cpu_baseline or rank != 0 or world > 1:
+        del sd
+        sd = None
+    pipe = DenoisePipeline(eng, ddim_steps=50, scale=7.0, eta=0.0)
+    B, L, K, W = args.batch, args.latent, args.steps, args.warmup
+    inp = synth.synth_inputs(B, L, seed=100 + rank, shared_reference=True)
+    x_T = inp["x"][:1].expand(B, -1, -1, -1).contiguous()           # same x_T for every frame (test_tiktok.py:225)
+    ref_host, ctx_host = inp["ref"][:1].contiguous(), inp["context"][:1].contiguous()
+    pin = lambda t: t.pin_memory()
+    x_host, pose_host, ref_host, ctx_host = pin(x_T), pin(inp["pose"]), pin(ref_host), pin(ctx_host)
+    out_host = torch.empty_like(x_host).pin_memory()
+    ref = ref_host.cuda(non_blocking=True)
+    ctx = ctx_host.cuda(non_blocking=True)
+    geo = eng.attn_geometry(L, L)
+    layout = parallel.BankLayout([(n, c) for n, c in geo])
+    tokens = [n for n, _ in geo]
+
+    def build_fn(index, flat):
+        t = pipe.t_dev[index].expand(1).contiguous()
+        bank = eng.appearance_write(ref, t, ctx)
+        eng.project_bank(bank, 1, out=layout.views(flat, tokens, 1))
+
+    def run(n_steps, first_step, host_io):
+        """bank build (sharded) -> one all-gather -> n_steps DDIM steps for this rank's B frames"""
+        idxs = [49 - ((first_step + i) % 50) for i in range(n_steps)]
+        uniq = list(dict.fromkeys(idxs))
+        flats = parallel.build_and_gather_bank(uniq, layout, build_fn, eng.device, world, rank)
+        banks = {ix: layout.views(fl, tokens, 1) for ix, fl in flats.items()}
+        x = x_host.cuda(non_blocking=True)
+        pose = pose_host.cuda(non_blocking=True)
+        hint = pipe.hint(pose, frame_key=None)
+        for ix in idxs:
+            if host_io:
+                x = x_host.cuda(non_blocking=True) if ix == idxs[0] else out_host.cuda(non_blocking=True)
+                pose = pose_host.cuda(non_blocking=True)
+            x, _, _, _ = pipe.step(x, ix, ctx, hint, banks[ix])
+            if host_io:
+                out_host.copy_(x, non_blocking=True)
+                torch.cuda.synchronize()
+        return x
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (untimed) ----
+    run(max(W, 1), 0, host_io=False)
+    barrier()
+    # ---- timed: device-resident inputs ----
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    x_final = run(K, 0, host_io=False)
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    clk = clocks.stop()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    sec = float(ms.item()) * 1e-3
+    finite = bool(torch.isfinite(x_final).all())
+    value = world * B * K / sec
+
+    # ---- timed: end to end through host buffers (H2D of x_t + pose, D2H of x_prev every step) ----
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        run(K, 0, host_io=True)
+        barrier()
+        t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * K / float(t_e2e.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(x_host.numel() * 4 + pose_host.numel() * 4),
+               "d2h_bytes_per_step": int(out_host.numel() * 4), "timing": "host wall clock, max over ranks"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    uniq_ts = min(K, 50)
+    gflop = GF_FRAME_STEP * B * K * world + GF_REF_STEP * uniq_ts
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 1),
+        "ms_per_step": sec * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "512x512, 50-step DDIM, batch %d/GPU, appearance-control + OpenPose ControlNet, "
+                               "CFG 7 (BASELINE.json configs[%d])" % (B, 1 if B == 1 else 2),
+                   "latent": L, "frames_per_gpu": B, "cfg_scale": 7.0, "ddim_steps": 50,
+                   "bank": "appearance pass once per timestep per sequence, timesteps sharded over ranks + one "
+                           "all-gather, inside the timed region",
+                   "l2": "no flush needed: each step streams >4 GB of fp16 weights (L2 is 126 MB)",
+                   "weights": "random init (seeded), fp16 storage, fp32 accumulate"},
+        "gpu_launches": int(launches), "clocks": clk, "finite": finite,
+        "step_roofline": {"algorithmic_gflop": gflop, "achieved_tflops": gflop / sec / 1e3,
+                          "peak_tflops_per_gpu": peaks.get("bf16_tflops_sustained", 1400.0),
+                          "frac": gflop / sec / 1e3 / (world * peaks.get("bf16_tflops_sustained", 1400.0))},
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_roofline:
+        ops.TRACE = []
+        run(1, 0, host_io=False)
+        torch.cuda.synchronize()
+        trace, ops.TRACE = ops.TRACE, None
+        line["roofline"] = roofline_probe(torch, ops, trace, peaks)
+    if sd is not None:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        csec = cpu_port_step_seconds(sd, L, 1, 0, torch)
+        line["cpu_baseline"] = {"value": 1.0 / csec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "1 p_sample_ddim step (index 49) of the same chain, B=1, fp32, as executed "
+                                          "by the reference (incl. its discarded 2nd pose pass), no warm-up"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -425,18 +425,39 @@ class DenoiseEngine:
             x = self._run_block(net, f"output_blocks.{i}.", blk, x, hs.pop(), emb_all, ctx_kvs, state)
         return state["bank"]
 
-    def project_bank(self, bank, batches):
+    def attn_geometry(self, h, w):
+        """(tokens, channels) of every attention layer of the UNet, in bank order, for an h x w latent."""
+        net = self.unet
+        geo = []
+        for blk in net.inp:
+            for kind, _, _, cout in blk:
+                if kind == "attn":
+                    geo.append((h * w, cout))
+                elif kind == "down":
+                    h, w = h // 2, w // 2
+        geo.append((h * w, net.mid[1][3]))
+        for blk in net.out:
+            for kind, _, _, cout in blk:
+                if kind == "attn":
+                    geo.append((h * w, cout))
+                elif kind == "up":
+                    h, w = 2 * h, 2 * w
+        return geo
+
+    def project_bank(self, bank, batches, out=None):
         """K/V of the bank under the DENOISING UNet's attn1.to_k/to_v (attention.py:289,307):
         algebraically identical to projecting cat([x_norm1] + bank) (SURVEY §8a semantics 1).
-        Returns per layer (K [batches*N, C], V^T [C, batches*N], N, batches)."""
+        Returns per layer (K [batches*N, C], V^T [C, batches*N], N, batches); with `out` (a list of
+        such tuples aliasing preallocated storage, see parallel.BankLayout) the GEMMs write in place."""
         res = []
         layers = self.unet.attn_layers()
         assert len(layers) == len(bank)
-        for a, n1 in zip(layers, bank):
+        for i, (a, n1) in enumerate(zip(layers, bank)):
             c = a.c
             rows = n1.shape[0]
-            k1 = ops.gemm(n1, a.wqk[c:], splits=_auto_splits(rows, c, c))
-            vt1 = ops.gemm(a.wv, n1, splits=_auto_splits(c, rows, c))
+            ko, vo = (out[i][0], out[i][1]) if out is not None else (None, None)
+            k1 = ops.gemm(n1, a.wqk[c:], out=ko, splits=_auto_splits(rows, c, c))
+            vt1 = ops.gemm(a.wv, n1, out=vo, splits=_auto_splits(c, rows, c))
             res.append((k1, vt1, rows // batches, batches))
         return res
 

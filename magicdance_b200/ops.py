@@ -12,6 +12,7 @@ import torch
 from . import _lib
 
 EPI_NONE, EPI_GEGLU = 0, 1
+TRACE = None  # set to a list to record (m, n, k, conv, epilogue, splits, k2) of every gemm() call (bench.py)
 
 
 def _stream() -> int:
@@ -94,6 +95,9 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
         assert residual.dim() == 2 and residual.stride(1) == 1
         g.residual, g.ldr = residual.data_ptr(), residual.stride(0)
     g.m, g.n, g.k, g.epilogue = m, n, k, epilogue
+    if TRACE is not None:
+        TRACE.append((m, n, k, tuple(conv) if conv is not None else None, epilogue, splits,
+                      a2.shape[1] if a2 is not None else 0))
     if splits > 1:
         ws = _workspace("splitk", m * n, torch.float32, a.device)
         g.splits, g.splitk_ws = splits, ws.data_ptr()

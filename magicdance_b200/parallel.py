@@ -1,0 +1,75 @@
+"""Multi-GPU partition of the denoising path: frames are independent 50-step chains
+from the same x_T (test_tiktok.py:225,232-268), so they are sharded across ranks with no
+collective inside a step.  The ONE exchange is the appearance bank: with wonoise it depends on
+(reference latent, timestep) only, so the timesteps are dealt round-robin over the ranks, each
+rank runs the appearance 'write' pass + K/V projection for its share, and a single NCCL
+all-gather at sequence start gives every rank every timestep's bank K/V.
+
+One process per GPU (torchrun); torch.distributed is plumbing (NCCL on GPUs, gloo in CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_frames(n_frames: int, world: int, rank: int) -> range:
+    """Contiguous block of frames of this rank (64 frames / 8 ranks -> 8 each; remainders to low ranks)."""
+    base, rem = divmod(n_frames, world)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+def shard_timesteps(indices: Sequence[int], world: int, rank: int) -> List[int]:
+    """Round-robin deal of DDIM indices (50 steps / 8 ranks -> 7,7,6,6,6,6,6,6)."""
+    return [ix for j, ix in enumerate(indices) if j % world == rank]
+
+
+def owner_slot(indices: Sequence[int], world: int) -> Dict[int, Tuple[int, int]]:
+    """ddim index -> (owning rank, slot in that rank's local buffer)."""
+    out = {}
+    for j, ix in enumerate(indices):
+        out[ix] = (j % world, j // world)
+    return out
+
+
+class BankLayout:
+    """Flat fp16 layout of one timestep's bank K/V: per attention layer K [rows, C] then V^T [C, rows]."""
+
+    def __init__(self, layer_shapes: Sequence[Tuple[int, int]]):
+        self.layer_shapes = list(layer_shapes)  # (rows = ref_batches * N_l, C_l)
+        self.offsets = []
+        off = 0
+        for rows, c in self.layer_shapes:
+            self.offsets.append(off)
+            off += 2 * rows * c
+        self.numel = (off + 127) // 128 * 128
+
+    def views(self, flat: torch.Tensor, tokens_per_batch: Sequence[int], batches: int):
+        """flat [numel] -> list of (K, V^T, N_l, batches) tuples aliasing the buffer."""
+        res = []
+        for (rows, c), off, n in zip(self.layer_shapes, self.offsets, tokens_per_batch):
+            k = flat[off:off + rows * c].view(rows, c)
+            vt = flat[off + rows * c:off + 2 * rows * c].view(c, rows)
+            res.append((k, vt, n, batches))
+        return res
+
+
+def build_and_gather_bank(indices: Sequence[int], layout: BankLayout, build_fn: Callable[[int, torch.Tensor], None],
+                          device, world: int = 1, rank: int = 0, group=None) -> Dict[int, torch.Tensor]:
+    """Each rank calls build_fn(ddim_index, flat_slot) for its share of `indices` (build_fn fills the
+    flat fp16 slot in place), then ONE all_gather_into_tensor exchanges all slots.  Returns
+    ddim index -> flat buffer (a view into the gathered storage)."""
+    mine = shard_timesteps(indices, world, rank)
+    slots = (len(indices) + world - 1) // world
+    local = torch.zeros((slots, layout.numel), dtype=torch.float16, device=device)
+    for s, ix in enumerate(mine):
+        build_fn(ix, local[s])
+    if world == 1:
+        return {ix: local[s] for s, ix in enumerate(mine)}
+    gathered = torch.empty((world, slots, layout.numel), dtype=torch.float16, device=device)
+    dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=group)
+    table = owner_slot(indices, world)
+    return {ix: gathered[r, s] for ix, (r, s) in table.items()}

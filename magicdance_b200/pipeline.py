@@ -1,0 +1,126 @@
+"""DDIM step scheduler over the DenoiseEngine: the B200-side counterpart of
+DDIMSampler_ReferenceOnly (model_lib/ControlNet/ldm/models/diffusion/ddim.py:346-730), restricted
+to the path MagicPose's inference script drives (test_tiktok.py:261-268): eps-parameterisation,
+'controlnet is more important' CFG branch (ddim.py:598-605), wonoise=True (ddim.py:532-533).
+
+What is cached, and why it is legal:
+  * text K/V of every attn2            — depends only on the prompt            (per sequence)
+  * hint-encoder features              — depend only on the pose map           (per frame)
+  * appearance bank K/V per timestep   — with wonoise the appearance net sees (reference latent, t)
+                                         only, so it is identical for every frame of a sequence
+  * the unconditional call skips the pose ControlNet whose output the reference discards.
+Host code here is scheduling only; all tensor math goes through magicdance_b200.ops.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .engine import DenoiseEngine
+
+
+def linear_beta_schedule(n_timestep=1000, linear_start=0.00085, linear_end=0.0120):
+    """make_beta_schedule('linear') (ldm/modules/diffusionmodules/util.py:21-28) -> float64 numpy."""
+    return np.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=np.float64) ** 2
+
+
+def alphas_cumprod_f32(n_timestep=1000, linear_start=0.00085, linear_end=0.0120):
+    """DDPM.register_schedule (ddpm.py:120-133): cumprod in float64, stored as a float32 buffer."""
+    return np.cumprod(1.0 - linear_beta_schedule(n_timestep, linear_start, linear_end), axis=0).astype(np.float32)
+
+
+def ddim_timesteps_uniform(num_ddim, num_ddpm=1000):
+    """make_ddim_timesteps('uniform') (util.py:45-59): range(0, T, T//S) + 1."""
+    return np.asarray(list(range(0, num_ddpm, num_ddpm // num_ddim))) + 1
+
+
+def ddim_parameters(alphacums, ddim_timesteps, eta):
+    """make_ddim_sampling_parameters (util.py:62-73)."""
+    alphas = alphacums[ddim_timesteps]
+    alphas_prev = np.asarray([alphacums[0]] + alphacums[ddim_timesteps[:-1]].tolist())
+    sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
+    return sigmas, alphas, alphas_prev
+
+
+class DenoisePipeline:
+    def __init__(self, engine: DenoiseEngine, ddim_steps=50, scale=7.0, eta=0.0, num_ddpm=1000,
+                 linear_start=0.00085, linear_end=0.0120, alphas_cumprod=None):
+        self.engine = engine
+        self.device = engine.device
+        self.scale = float(scale)
+        acp = alphas_cumprod_f32(num_ddpm, linear_start, linear_end) if alphas_cumprod is None else \
+            np.asarray(alphas_cumprod, dtype=np.float32)
+        self.alphas_cumprod = acp
+        self.make_schedule(ddim_steps, eta)
+        self._bank_cache = {}
+        self._hint_cache = {}
+
+    def make_schedule(self, ddim_steps, eta=0.0):
+        self.ddim_steps = ddim_steps
+        self.timesteps = ddim_timesteps_uniform(ddim_steps, self.alphas_cumprod.shape[0])
+        sig, a, a_prev = ddim_parameters(self.alphas_cumprod, self.timesteps, eta)
+        self.sigmas, self.alphas, self.alphas_prev = sig, a, a_prev
+        coef = np.zeros((len(self.timesteps), 8), dtype=np.float32)
+        for i in range(len(self.timesteps)):
+            coef[i, :6] = [self.scale, math.sqrt(a[i]), math.sqrt(a_prev[i]),
+                           math.sqrt(max(1.0 - a_prev[i] - sig[i] ** 2, 0.0)), sig[i], math.sqrt(1.0 - a[i])]
+        self.coef = torch.from_numpy(coef).to(self.device)  # row i = coefficients of ddim index i
+        self.t_dev = torch.from_numpy(self.timesteps.astype(np.int64)).to(self.device)
+
+    # ---- per-sequence / per-frame preparation --------------------------------------------------
+    def reference_bank(self, ref_latent, context, index):
+        """Bank K/V for ddim index `index` (appearance 'write' pass + projection), cached."""
+        key = (ref_latent.data_ptr(), ref_latent._version, int(index))
+        hit = self._bank_cache.get(key)
+        if hit is None:
+            rb = ref_latent.shape[0]
+            t = self.t_dev[index].expand(rb).contiguous()
+            bank = self.engine.appearance_write(ref_latent, t, context[:rb])
+            hit = self.engine.project_bank(bank, rb)
+            self._bank_cache[key] = hit
+        return hit
+
+    def clear_caches(self):
+        self._bank_cache.clear()
+        self._hint_cache.clear()
+
+    def hint(self, pose_map, frame_key=None):
+        if frame_key is None:
+            return self.engine.hint_features(pose_map)
+        hit = self._hint_cache.get(frame_key)
+        if hit is None:
+            hit = self.engine.hint_features(pose_map)
+            self._hint_cache[frame_key] = hit
+        return hit
+
+    # ---- one DDIM step ---------------------------------------------------------------------------
+    def step(self, x, index, context, hint_feat, bank_kv, noise=None):
+        """p_sample_ddim (ddim.py:518-645): eps_c = apply_model(x,t,c,ref), eps_u = apply_model(x,t,c,None,uc),
+        CFG combine, DDIM update.  x: fp32 NCHW on the device.  Returns (x_prev, pred_x0, eps_c, eps_u)."""
+        eng = self.engine
+        b = x.shape[0]
+        t = self.t_dev[index].expand(b).contiguous()
+        pose = eng.controlnet(x, hint_feat, t, context)
+        eps_c = eng.unet_forward(x, t, context, bank_kv=bank_kv, pose=pose, uc=False)
+        eps_u = eng.unet_forward(x, t, context, uc=True)
+        x_prev, pred_x0 = ops.cfg_ddim_update(x.contiguous(), eps_c, eps_u, self.coef[index], noise=noise)
+        return x_prev, pred_x0, eps_c, eps_u
+
+    @torch.no_grad()
+    def sample(self, x_T, context, pose_map, ref_latent, frame_key=None, callback=None):
+        """ddim_sampling (ddim.py:460-516) for a batch of frames sharing one reference latent."""
+        x = x_T.to(device=self.device, dtype=torch.float32).contiguous()
+        context = context.to(self.device)
+        ref_latent = ref_latent.to(self.device)
+        hint_feat = self.hint(pose_map.to(self.device), frame_key)
+        pred_x0 = x
+        for i in range(self.ddim_steps):
+            index = self.ddim_steps - 1 - i
+            bank_kv = self.reference_bank(ref_latent, context, index)
+            x, pred_x0, _, _ = self.step(x, index, context, hint_feat, bank_kv)
+            if callback:
+                callback(i)
+        return x, pred_x0

@@ -5,7 +5,7 @@ Run in the build container only (needs /root/reference):
     cd /tmp && python /root/repo/oracle/make_golden.py
 
 Writes
-  tests/golden/state_manifest.json   key -> shape of the reference LDM's state_dict
+  magicdance_b200/state_manifest.json key -> shape of the reference LDM's state_dict
   tests/golden/small32.npz           apply_model cond+uncond, latent 32x32, B=2, per-sample t
                                      and per-sample reference latents
   tests/golden/full64.npz            one full p_sample_ddim (index 49, t=981, CFG 7) at the
@@ -125,7 +125,7 @@ def main():
     print(f"reference LDM built in {time.time() - t0:.1f}s", flush=True)
     sd = model.state_dict()
     manifest = {k: list(v.shape) for k, v in sd.items()}
-    with open(os.path.join(GOLDEN, "state_manifest.json"), "w") as f:
+    with open(synth.MANIFEST, "w") as f:
         json.dump(manifest, f, indent=0, sort_keys=True)
     weights = synth.synth_state_dict(manifest, seed=SEED)
     missing, unexpected = model.load_state_dict(weights, strict=False)

@@ -1,0 +1,108 @@
+"""CPU-only checks of the host logic and of the C-ABI library's exported surface."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from magicdance_b200 import build, _lib
+    path = build.build()
+    lib = _lib.load()
+    header = open(os.path.join(REPO, "include", "magicdance_b200.h")).read()
+    declared = set(re.findall(r"\b(mdb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    nm = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (mdb_[a-z0-9_]+)", nm))
+    assert declared <= exported, declared - exported
+    assert lib.mdb_abi_version() == 1 and lib.mdb_launch_count() == 0
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions():
+    from magicdance_b200 import build
+    path = build.build()
+    sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+    for mnem in ("UTCHMMA", "LDTM", "STTM", "UTMALDG"):
+        assert mnem in sass, f"{mnem} (tcgen05 / TMA) missing from the compiled kernels"
+    assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync path must not be present"
+
+
+def test_no_cuda_means_loud_failure():
+    from magicdance_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        ops.ensure_device()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.layernorm(torch.zeros(2, 320).half(), torch.ones(320), torch.zeros(320))
+
+
+def test_block_plan_and_packing_consume_the_reference_state_dict():
+    """Every key of the reference state dict (manifest recorded from the unmodified reference) is
+    consumed by the weight packer, except the appearance twin's dead hint block; shapes line up."""
+    from magicdance_b200 import synth
+    from magicdance_b200.engine import NetConfig, PackedNet, UNET, APPEARANCE, POSE
+    manifest = synth.load_manifest()
+    seen = set()
+
+    class Rec(dict):
+        def __getitem__(self, k):
+            seen.add(k)
+            return torch.empty(manifest[k], device="meta")
+
+        def __contains__(self, k):
+            return k in manifest
+
+    sd = Rec()
+    for prefix, kind in ((UNET, "unet"), (APPEARANCE, "appearance"), (POSE, "controlnet")):
+        PackedNet(sd, prefix, NetConfig(), kind, "meta")
+    nets = [k for k in manifest if k.startswith((UNET, APPEARANCE, POSE))]
+    unused = sorted(set(nets) - seen)
+    assert all(k.startswith(APPEARANCE + "input_hint_block.") for k in unused), unused[:5]
+    assert len(unused) == 16
+
+
+def test_geglu_packing_interleaves_value_and_gate_rows():
+    from magicdance_b200.engine import pack_geglu
+    c = 64
+    w = torch.arange(8 * c, dtype=torch.float32)[:, None].expand(8 * c, 4).contiguous()
+    b = torch.arange(8 * c, dtype=torch.float32)
+    wp, bp = pack_geglu(w, b, "cpu")
+    assert bp[:32].tolist() == list(range(32)) and bp[32:64].tolist() == list(range(4 * c, 4 * c + 32))
+    assert bp[64:96].tolist() == list(range(32, 64))
+    assert torch.equal(wp[:, 0].float(), bp.half().float())
+
+
+def test_schedule_matches_reference_buffers():
+    from magicdance_b200 import pipeline as P
+    from tests import golden_util as G
+    g = G.load("full64")
+    acp = P.alphas_cumprod_f32()
+    np.testing.assert_allclose(acp, g["full64/alphas_cumprod"], rtol=2e-6)
+    ts = P.ddim_timesteps_uniform(50)
+    assert list(ts) == list(g["full64/ddim_timesteps"]) and ts[0] == 1 and ts[-1] == 981
+    sig, a, ap = P.ddim_parameters(acp, ts, 0.0)
+    np.testing.assert_allclose(a, g["full64/ddim_alphas"], rtol=1e-6)
+    np.testing.assert_allclose(ap, g["full64/ddim_alphas_prev"], rtol=1e-6)
+    assert float(np.abs(sig).max()) == 0.0
+
+
+def test_sharding_helpers():
+    from magicdance_b200 import parallel as P
+    assert [len(P.shard_frames(64, 8, r)) for r in range(8)] == [8] * 8
+    assert [len(P.shard_frames(10, 4, r)) for r in range(4)] == [3, 3, 2, 2]
+    covered = sorted(i for r in range(4) for i in P.shard_frames(10, 4, r))
+    assert covered == list(range(10))
+    idx = list(range(49, -1, -1))
+    shares = [P.shard_timesteps(idx, 8, r) for r in range(8)]
+    assert [len(s) for s in shares] == [7, 7, 6, 6, 6, 6, 6, 6]
+    assert sorted(sum(shares, [])) == list(range(50))
+    table = P.owner_slot(idx, 8)
+    for r, sh in enumerate(shares):
+        for s, ix in enumerate(sh):
+            assert table[ix] == (r, s)

@@ -1,0 +1,63 @@
+"""world_size-2 test of the ONE exchange step of the multi-GPU path: timesteps dealt
+round-robin, each rank builds its share of the bank, a single all-gather distributes it.  Runs on
+CPU with the gloo backend; the same code path runs over NCCL in bench.py."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    from magicdance_b200 import parallel as P
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    layout = P.BankLayout([(16, 8), (4, 16)])  # two fake attention layers
+    built = []
+
+    def build_fn(index, flat):
+        built.append(index)
+        views = layout.views(flat, [16, 4], 1)
+        for li, (k, vt, n, b) in enumerate(views):
+            k.fill_(index + 0.25 * li)
+            vt.fill_(-(index + 0.25 * li))
+
+    indices = list(range(9, -1, -1))  # 10 timesteps over 2 ranks
+    table = P.build_and_gather_bank(indices, layout, build_fn, "cpu", world, rank)
+    ok = sorted(table) == list(range(10)) and built == P.shard_timesteps(indices, world, rank)
+    for ix, flat in table.items():
+        for li, (k, vt, n, b) in enumerate(layout.views(flat, [16, 4], 1)):
+            ok &= bool((k == ix + 0.25 * li).all()) and bool((vt == -(ix + 0.25 * li)).all())
+            ok &= k.shape == (layout.layer_shapes[li][0], layout.layer_shapes[li][1])
+    # frames: each rank gets a disjoint contiguous block
+    mine = list(P.shard_frames(7, world, rank))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    ok &= sorted(sum(gathered, [])) == list(range(7))
+    q.put((rank, ok, len(built)))
+    dist.destroy_process_group()
+
+
+def test_bank_allgather_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [True, True]
+    assert [r[2] for r in res] == [5, 5]  # each rank built exactly its half of the timesteps
