@@ -124,3 +124,95 @@ class DenoisePipeline:
             if callback:
                 callback(i)
         return x, pred_x0
+
+
+class GraphedDenoiser:
+    """The whole DDIM step (and the per-timestep appearance-bank build) captured once as CUDA graphs
+    and replayed for all 50 steps: at batch 1 the step is ~2000 small kernels, so launch latency and
+    Python would otherwise dominate.  Everything timestep-dependent is read from
+    device memory that is refreshed by tiny copies before each replay (the timestep, the DDIM
+    coefficient row, the bank K/V of that timestep), so ONE graph serves every step."""
+
+    def __init__(self, pipe: DenoisePipeline, batch: int, latent_hw, context: torch.Tensor, ref_batches: int = 1):
+        from . import parallel
+        self.pipe, self.eng = pipe, pipe.engine
+        eng, dev = self.eng, pipe.device
+        h, w = latent_hw
+        self.batch = batch
+        self.ctx = context.to(dev).contiguous()
+        self.x = torch.zeros((batch, 4, h, w), dtype=torch.float32, device=dev)
+        self.x_prev = torch.zeros_like(self.x)
+        self.pred_x0 = torch.zeros_like(self.x)
+        self.ref = torch.zeros((ref_batches, 4, h, w), dtype=torch.float32, device=dev)
+        self.t_cur = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.coef_cur = torch.zeros((8,), dtype=torch.float32, device=dev)
+        self.hint = torch.zeros((batch * h * w, eng.cfg.model_channels), dtype=torch.float16, device=dev)
+        geo = eng.attn_geometry(h, w)
+        self.tokens = [n for n, _ in geo]
+        self.layout = parallel.BankLayout([(ref_batches * n, c) for n, c in geo])
+        self.ref_batches = ref_batches
+        self.bank_cur = torch.zeros((self.layout.numel,), dtype=torch.float16, device=dev)
+        self.bank_built = torch.zeros((self.layout.numel,), dtype=torch.float16, device=dev)
+        self.g_step = self.g_bank = None
+
+    # the two bodies, written against the static buffers only
+    def _step_body(self):
+        eng, b = self.eng, self.batch
+        t = self.t_cur.expand(b).contiguous()
+        bank_kv = self.layout.views(self.bank_cur, self.tokens, self.ref_batches)
+        pose = eng.controlnet(self.x, self.hint, t, self.ctx)
+        eps_c = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, uc=False)
+        eps_u = eng.unet_forward(self.x, t, self.ctx, uc=True)
+        ops.cfg_ddim_update(self.x, eps_c, eps_u, self.coef_cur, x_prev=self.x_prev, pred_x0=self.pred_x0)
+        self.x.copy_(self.x_prev)
+
+    def _bank_body(self):
+        eng = self.eng
+        t = self.t_cur.expand(self.ref_batches).contiguous()
+        bank = eng.appearance_write(self.ref, t, self.ctx[:self.ref_batches] if self.ctx.shape[0] > 1 else self.ctx)
+        eng.project_bank(bank, self.ref_batches, out=self.layout.views(self.bank_built, self.tokens, self.ref_batches))
+
+    def capture(self):
+        """Warm up eagerly (fills every cache and workspace), then capture both graphs."""
+        s = torch.cuda.Stream(device=self.pipe.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._bank_body()
+                self._step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        n0 = ops.launch_count()
+        self.g_bank = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_bank):
+            self._bank_body()
+        n1 = ops.launch_count()
+        self.g_step = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_step, pool=self.g_bank.pool()):
+            self._step_body()
+        torch.cuda.synchronize()
+        # kernels of OUR library inside each graph (the C ABI counts launches at capture time only)
+        self.bank_launches, self.step_launches = n1 - n0, ops.launch_count() - n1
+        self.replayed_launches = 0
+        return self
+
+    # ---- replay helpers ---------------------------------------------------------------------------
+    def set_index(self, index):
+        self.t_cur.copy_(self.pipe.t_dev[index:index + 1])
+        self.coef_cur.copy_(self.pipe.coef[index])
+
+    def build_bank(self, index, ref_latent, out_flat):
+        """appearance 'write' pass + K/V projection for ddim index -> out_flat (fp16 [layout.numel])"""
+        self.ref.copy_(ref_latent)
+        self.set_index(index)
+        self.g_bank.replay()
+        self.replayed_launches += self.bank_launches
+        out_flat.copy_(self.bank_built)
+
+    def step(self, index, bank_flat):
+        """one DDIM step on self.x in place (result also in self.x_prev / self.pred_x0)"""
+        self.set_index(index)
+        self.bank_cur.copy_(bank_flat)
+        self.g_step.replay()
+        self.replayed_launches += self.step_launches
+        return self.x_prev
