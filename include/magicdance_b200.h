@@ -74,7 +74,7 @@ typedef struct mdb_gemm_desc {
   int64_t ldr;
   int32_t m, n, k;
   int32_t splits;             /* >1: split-K over gridDim.z through splitk_ws                     */
-  float* splitk_ws;           /* fp32 [M][N] scratch (only read/written when splits > 1)          */
+  float* splitk_ws;           /* fp32 [splits][M][N] scratch for the per-split partials (splits > 1 only) */
 } mdb_gemm_desc;
 
 int mdb_gemm_f16(const mdb_gemm_desc* desc, mdb_stream_t stream);

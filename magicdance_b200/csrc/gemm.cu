@@ -213,9 +213,17 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         const int ncols = min(32, p.n - col0);
         if (p.splits > 1) {
+          // split-K: this split's fp32 partial goes to its own workspace slab (plain vector stores);
+          // splitk_finalize_kernel sums the slabs in a fixed order (deterministic, no atomics).
           if (row_ok) {
-            float* wp = p.ws + row * p.n + col0;
-            for (int j = 0; j < ncols; ++j) atomicAdd(wp + j, v[j]);
+            float* wp = p.ws + (static_cast<long long>(split) * p.m + row) * p.n + col0;
+            if (ncols == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(wp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              for (int j = 0; j < ncols; ++j) wp[j] = v[j];
+            }
           }
         } else if (row_ok) {
           epi_store_chunk(p, row, col0, ncols, v);
@@ -269,14 +277,44 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
   }
 }
 
-// split-K second pass: ws (fp32 [M][N]) -> bias/residual -> fp16 D
+// split-K second pass: sum of the fp32 partial slabs ws[splits][M][N] -> bias/residual -> fp16 D
 __global__ void splitk_finalize_kernel(GemmKParams p) {
-  const long long total = static_cast<long long>(p.m) * p.n;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+  const long long slab = static_cast<long long>(p.m) * p.n;
+  if ((p.n & 3) == 0) {
+    const long long total4 = slab >> 2;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long e = i << 2;
+      const long long row = e / p.n;
+      const int col = static_cast<int>(e - row * p.n);
+      float4 a = *reinterpret_cast<const float4*>(p.ws + e);
+      for (int s = 1; s < p.splits; ++s) {
+        const float4 b = *reinterpret_cast<const float4*>(p.ws + s * slab + e);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      if (p.bias != nullptr) {
+        const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
+        const float* bp = p.bias + brow * p.bias_batch_stride + col;
+        a.x += bp[0]; a.y += bp[1]; a.z += bp[2]; a.w += bp[3];
+      }
+      if (p.residual != nullptr) {
+        const __half2* rp = reinterpret_cast<const __half2*>(p.residual + row * p.ldr + col);
+        const float2 r0 = __half22float2(rp[0]), r1 = __half22float2(rp[1]);
+        a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
+      }
+      uint2 o;
+      o.x = pack_half2(a.x, a.y);
+      o.y = pack_half2(a.z, a.w);
+      *reinterpret_cast<uint2*>(p.d + row * p.ldd + col) = o;
+    }
+    return;
+  }
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < slab;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long row = i / p.n;
     const int col = static_cast<int>(i - row * p.n);
-    float v = p.ws[i];
+    float v = 0.f;
+    for (int s = 0; s < p.splits; ++s) v += p.ws[s * slab + i];
     if (p.bias != nullptr) {
       const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
       v += p.bias[brow * p.bias_batch_stride + col];
@@ -447,7 +485,6 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   kp.ws = g->splitk_ws;
   if (splits > 1) {
     MDB_REQUIRE(g->splitk_ws != nullptr, "mdb_gemm_f16: splits > 1 needs splitk_ws");
-    MDB_CHECK_CUDA(cudaMemsetAsync(g->splitk_ws, 0, sizeof(float) * (size_t)g->m * g->n, st));
   }
 
   dim3 grid((g->m + kBM - 1) / kBM, (g->n + bn - 1) / bn, splits);
@@ -456,7 +493,7 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   else rc = launch_gemm<128, false>(kp, grid, st);
   if (rc) return rc;
   if (splits > 1) {
-    const long long total = (long long)g->m * g->n;
+    const long long total = ((long long)g->m * g->n + 3) / 4;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     splitk_finalize_kernel<<<blocks, 256, 0, st>>>(kp);

@@ -99,6 +99,125 @@ __global__ void __launch_bounds__(256) direct_conv3x3_kernel(const __half* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// 3x3 stride-1 conv with a tiny input-channel count (the 4->320 input conv): K = 9*cin <= 72.
+// CTA = 8 pixels x (cout/8) channel groups; weights live in shared memory as fp32.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCiPix = 8;
+__global__ void conv3x3_smallcin_kernel(const __half* __restrict__ x, const __half* __restrict__ wt,
+                                        const float* __restrict__ bias, const __half* __restrict__ residual,
+                                        __half* __restrict__ y, int batch, int h, int w, int cin, int cout, int silu) {
+  extern __shared__ float s_wt[];  // [cout][9*cin]
+  const int kk = 9 * cin;
+  for (int i = threadIdx.x; i < cout * kk; i += blockDim.x) s_wt[i] = __half2float(wt[i]);
+  __syncthreads();
+  const int groups = cout / 8;
+  const int g = threadIdx.x % groups;
+  const int pl = threadIdx.x / groups;
+  const long long pix = static_cast<long long>(blockIdx.x) * kCiPix + pl;
+  const long long npix = static_cast<long long>(batch) * h * w;
+  if (pl >= kCiPix || pix >= npix) return;
+  const int xx = static_cast<int>(pix % w), yy = static_cast<int>((pix / w) % h);
+  const long long b = pix / (static_cast<long long>(w) * h);
+  float in[72];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int iy = yy + t / 3 - 1, ix = xx + t % 3 - 1;
+    const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
+    for (int ci = 0; ci < cin; ++ci)
+      in[t * 8 + ci] = ok ? __half2float(x[((b * h + iy) * w + ix) * cin + ci]) : 0.f;
+  }
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int co = g * 8 + j;
+    float a = bias ? bias[co] : 0.f;
+    const float* wr = &s_wt[co * kk];
+    for (int t = 0; t < 9; ++t)
+      for (int ci = 0; ci < cin; ++ci) a += in[t * 8 + ci] * wr[t * cin + ci];
+    if (silu) a = silu_f(a);
+    acc[j] = a;
+  }
+  const long long o = pix * cout + g * 8;
+  if (residual) {
+    uint4 r4 = *reinterpret_cast<const uint4*>(residual + o);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __half22float2(h2[e]);
+      acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+    }
+  }
+  uint4 o4;
+  o4.x = pack_half2(acc[0], acc[1]); o4.y = pack_half2(acc[2], acc[3]);
+  o4.z = pack_half2(acc[4], acc[5]); o4.w = pack_half2(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(y + o) = o4;
+}
+
+// 3x3 stride-1 conv with a tiny output-channel count (the 320->4 output conv): one warp per pixel,
+// lanes split the K = 9*cin reduction in 16-byte vectors, weights in shared memory.
+template <int COUT>
+__global__ void conv3x3_smallcout_kernel(const __half* __restrict__ x, const __half* __restrict__ wt,
+                                         const float* __restrict__ bias, __half* __restrict__ y, int batch, int h,
+                                         int w, int cin, int silu) {
+  extern __shared__ __half s_wh[];  // [COUT][9*cin]
+  const int kk = 9 * cin;
+  for (int i = threadIdx.x * 8; i < COUT * kk; i += blockDim.x * 8)
+    *reinterpret_cast<uint4*>(&s_wh[i]) = *reinterpret_cast<const uint4*>(&wt[i]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const long long npix = static_cast<long long>(batch) * h * w;
+  const int vecs = cin / 8;
+  for (long long pix = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); pix < npix;
+       pix += static_cast<long long>(gridDim.x) * warps) {
+    const int xx = static_cast<int>(pix % w), yy = static_cast<int>((pix / w) % h);
+    const long long b = pix / (static_cast<long long>(w) * h);
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+    for (int t = 0; t < 9; ++t) {
+      const int iy = yy + t / 3 - 1, ix = xx + t % 3 - 1;
+      if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;  // warp-uniform
+      const __half* xp = x + ((b * h + iy) * w + ix) * cin;
+      for (int v = lane; v < vecs; v += 32) {
+        uint4 u = *reinterpret_cast<const uint4*>(xp + v * 8);
+        const __half2* xh = reinterpret_cast<const __half2*>(&u);
+        float xf[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f2 = __half22float2(xh[e]);
+          xf[2 * e] = f2.x; xf[2 * e + 1] = f2.y;
+        }
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) {
+          uint4 wu = *reinterpret_cast<const uint4*>(&s_wh[j * kk + t * cin + v * 8]);
+          const __half2* wh = reinterpret_cast<const __half2*>(&wu);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 f2 = __half22float2(wh[e]);
+            acc[j] += xf[2 * e] * f2.x + xf[2 * e + 1] * f2.y;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if (lane < COUT) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < COUT; ++j)
+        if (j == lane) v = acc[j];
+      v += bias ? bias[lane] : 0.f;
+      if (silu) v = silu_f(v);
+      y[pix * COUT + lane] = __float2half_rn(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 __global__ void im2col3x3s2_kernel(const __half* __restrict__ x, __half* __restrict__ col, int batch, int h, int w,
                                    int c) {
   const int ho = h / 2, wo = w / 2, vecs = c / 8;
@@ -300,6 +419,39 @@ extern "C" int mdb_conv3x3_direct_f16(const void* x, const void* wt, const float
   const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
   dim3 grid(((wo + kDcTile - 1) / kDcTile) * ((ho + kDcTile - 1) / kDcTile), (cout + kDcCout - 1) / kDcCout, batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long npix = static_cast<long long>(batch) * h * w;
+  if (stride == 1 && cin <= 8 && cout % 8 == 0 && cout * 9 * cin * 4 <= 96 * 1024 && kCiPix * (cout / 8) <= 1024) {
+    // tiny-cin path (input conv)
+    static bool attr_set = false;
+    const int smem = cout * 9 * cin * 4;
+    if (!attr_set) {
+      MDB_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_smallcin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set = true;
+    }
+    const int threads = ((kCiPix * (cout / 8) + 31) / 32) * 32;
+    conv3x3_smallcin_kernel<<<static_cast<int>((npix + kCiPix - 1) / kCiPix), threads, smem, st>>>(
+        static_cast<const __half*>(x), static_cast<const __half*>(wt), bias, static_cast<const __half*>(residual),
+        static_cast<__half*>(y), batch, h, w, cin, cout, silu);
+    MDB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MDB_OK;
+  }
+  if (stride == 1 && cout == 4 && cin % 8 == 0 && residual == nullptr && cout * 9 * cin * 2 <= 96 * 1024) {
+    // tiny-cout path (output conv)
+    static bool attr_set = false;
+    const int smem = cout * 9 * cin * 2;
+    if (!attr_set) {
+      MDB_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_smallcout_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set = true;
+    }
+    int blocks = static_cast<int>((npix + 7) / 8);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    conv3x3_smallcout_kernel<4><<<blocks, 256, smem, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(wt),
+                                                          bias, static_cast<__half*>(y), batch, h, w, cin, silu);
+    MDB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MDB_OK;
+  }
   if (stride == 1)
     direct_conv3x3_kernel<1><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(wt), bias,
                                                    static_cast<const __half*>(residual), static_cast<__half*>(y), h, w,

@@ -13,8 +13,6 @@ namespace mdb {
 
 void count_launch(int n = 1);
 
-constexpr int kGnRowsPerCta = 64;
-
 __device__ __forceinline__ const uint4* gn_src(const __half* x1, int c1, const __half* x2, int c2, long long row,
                                                 int ch) {
   // channel ch (multiple of 8) of concatenated row -> address of its 16-byte vector
@@ -22,36 +20,38 @@ __device__ __forceinline__ const uint4* gn_src(const __half* x1, int c1, const _
                    : reinterpret_cast<const uint4*>(x2 + row * c2 + (ch - c1));
 }
 
+// rows_per_cta is chosen by the launcher so that ~2 waves of CTAs cover the tensor and every thread
+// owns at most a handful of rows (loads of one thread are independent and unrolled).
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
-                                float* __restrict__ stats, int hw) {
+                                float* __restrict__ stats, int hw, int rows_per_cta) {
   extern __shared__ float sh[];  // [2][32] group sums
   const int c = c1 + c2;
   const int cg = c / 32;
   const int b = blockIdx.y;
-  const int row0 = blockIdx.x * kGnRowsPerCta;
-  const int rows = min(kGnRowsPerCta, hw - row0);
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int rows = min(rows_per_cta, hw - row0);
   const int vecs = c / 8;
   if (threadIdx.x < 64) sh[threadIdx.x] = 0.f;
   __syncthreads();
-  // thread -> (vector index v, row phase); blockDim.x >= vecs is guaranteed by the launcher
   const int v = threadIdx.x % vecs;
   const int rphase = threadIdx.x / vecs;
   const int rstride = blockDim.x / vecs;
-  if (rphase < rstride) {
-    float s[8], q[8];
+  float s[8], q[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-    for (int r = rphase; r < rows; r += rstride) {
-      const long long row = static_cast<long long>(b) * hw + row0 + r;
-      uint4 u = *gn_src(x1, c1, x2, c2, row, v * 8);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+#pragma unroll 4
+  for (int r = rphase; r < rows; r += rstride) {
+    const long long row = static_cast<long long>(b) * hw + row0 + r;
+    uint4 u = *gn_src(x1, c1, x2, c2, row, v * 8);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = __half22float2(h2[e]);
-        s[2 * e] += f.x; q[2 * e] += f.x * f.x;
-        s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
-      }
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __half22float2(h2[e]);
+      s[2 * e] += f.x; q[2 * e] += f.x * f.x;
+      s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
     }
+  }
+  if (rphase < rows) {
     // fold the 8 channels into (at most two) groups
     const int g_first = (v * 8) / cg;
     float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
@@ -62,7 +62,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __h
     }
     atomicAdd(&sh[g_first], sa);
     atomicAdd(&sh[32 + g_first], qa);
-    if ((v * 8 + 7) / cg != g_first) {  // cg >= 10 so a vector spans at most two groups
+    if ((v * 8 + 7) / cg != g_first) {  // cg >= 8 so a vector spans at most two groups
       atomicAdd(&sh[g_first + 1], sb);
       atomicAdd(&sh[32 + g_first + 1], qb);
     }
@@ -170,9 +170,16 @@ extern "C" int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int
   const int vecs = c / 8;
   int threads = ((512 / vecs) * vecs);  // whole number of row phases
   if (threads < vecs) threads = vecs;
-  dim3 grid((hw + kGnRowsPerCta - 1) / kGnRowsPerCta, batch);
+  const int rstride = threads / vecs;
+  // ~296 CTAs (2 per SM) in total, whole multiples of the row-phase count, at most 8 rows per thread
+  int per = (batch * hw + 295) / 296;
+  int rows_per_cta = ((per + rstride - 1) / rstride) * rstride;
+  if (rows_per_cta > 8 * rstride) rows_per_cta = 8 * rstride;
+  if (rows_per_cta < rstride) rows_per_cta = rstride;
+  dim3 grid((hw + rows_per_cta - 1) / rows_per_cta, batch);
   gn_stats_kernel<<<grid, threads, 64 * sizeof(float), st>>>(static_cast<const __half*>(x1), c1,
-                                                             static_cast<const __half*>(x2), c2, stats_ws, hw);
+                                                             static_cast<const __half*>(x2), c2, stats_ws, hw,
+                                                             rows_per_cta);
   MDB_CHECK_CUDA(cudaGetLastError());
   const long long total = static_cast<long long>(batch) * hw * vecs;
   int blocks = static_cast<int>((total + 255) / 256);

@@ -495,19 +495,44 @@ class DenoiseEngine:
         outs.append(ops.gemm(x.data, zw, bias=zb, splits=_auto_splits(x.b * x.hw, x.c, x.c)))
         return outs
 
-    def unet_forward(self, x_noisy, t, context, bank_kv=None, pose=None, uc=False, bank_batches=None, taps=None):
+    def unet_forward(self, x_noisy, t, context, bank_kv=None, pose=None, uc=False, taps=None, cfg_pair=False):
         """ControlledUnetModelAttnPose.forward (cldm.py:59-112).  uc=True: plain SD UNet without bank
-        or pose residuals (cldm.py:70-84).  bank_kv: project_bank() output.  Returns eps as NCHW fp32."""
+        or pose residuals (cldm.py:70-84); otherwise 'read' mode.  bank_kv: project_bank() output.
+        Returns eps as NCHW fp32.
+
+        cfg_pair=True runs the conditional AND the unconditional evaluation of p_sample_ddim
+        (ddim.py:598-604: same x, t and text for both) as ONE batch of 2B samples: every shared-weight
+        layer streams its weights once and sees twice the rows; samples [0,B) read the bank and take the
+        pose residuals, samples [B,2B) do neither.  Returns (eps_cond, eps_uncond)."""
         net = self.unet
         x, ctx16, key = self._prep(x_noisy, context)
         b = x.b
+        if cfg_pair:
+            assert not uc and 2 * b <= 16, "cfg_pair needs 2*B <= 16 (timestep MLP kernel limit)"
+            both = torch.empty((2 * b * x.hw, x.c), dtype=torch.float16, device=self.device)
+            both[:b * x.hw].copy_(x.data)
+            both[b * x.hw:].copy_(x.data)
+            x = Act(both, 2 * b, x.h, x.w)
+            t = torch.cat([t, t])
+            if ctx16.shape[0] > 1:
+                ctx16 = torch.cat([ctx16, ctx16])
+                key = key + ("pair",)
         ctx_kvs = self.context_kv(net, ctx16, key)
         emb_all = self.time_bias(net, t)
         state = {"mode": "plain" if uc else "read", "attn_i": 0}
         pose = None if (uc or pose is None) else list(pose)
         state["bank_kv"] = None if uc else bank_kv
-        state["bank_batches"] = b if bank_batches is None else bank_batches
+        state["bank_batches"] = b
         hs = []
+
+        def add_pose(act):
+            p = pose.pop()
+            if cfg_pair:  # in place on the conditional half only
+                first = act.data[:b * act.hw]
+                ops.add(first, p, batch=b, out=first)
+                return act
+            return Act(ops.add(act.data, p, batch=b), act.b, act.h, act.w)
+
         for i, blk in enumerate(net.inp):
             x = self._run_block(net, f"input_blocks.{i}.", blk, x, None, emb_all, ctx_kvs, state)
             hs.append(x)
@@ -517,17 +542,20 @@ class DenoiseEngine:
         if taps is not None:
             taps.append(x)
         if pose is not None:
-            x = Act(ops.add(x.data, pose.pop(), batch=b), x.b, x.h, x.w)
+            x = add_pose(x)
         for i, blk in enumerate(net.out):
             skip = hs.pop()
             if pose is not None:
-                skip = Act(ops.add(skip.data, pose.pop(), batch=b), skip.b, skip.h, skip.w)
+                skip = add_pose(skip)
             x = self._run_block(net, f"output_blocks.{i}.", blk, x, skip, emb_all, ctx_kvs, state)
             if taps is not None:
                 taps.append(x)
-        hn = ops.groupnorm(x.data, *net.out_gn, batch=b, hw=x.hw, eps=1e-5, silu=True)
-        y = self._conv3(Act(hn, b, x.h, x.w), net.out_w, net.out_b, cout=self.cfg.out_channels)
-        return ops.nhwc_f16_to_nchw_f32(y.data, batch=b, c=self.cfg.out_channels, h=x.h, w=x.w)
+        hn = ops.groupnorm(x.data, *net.out_gn, batch=x.b, hw=x.hw, eps=1e-5, silu=True)
+        y = self._conv3(Act(hn, x.b, x.h, x.w), net.out_w, net.out_b, cout=self.cfg.out_channels)
+        eps = ops.nhwc_f16_to_nchw_f32(y.data, batch=x.b, c=self.cfg.out_channels, h=x.h, w=x.w)
+        if cfg_pair:
+            return eps[:b], eps[b:]
+        return eps
 
     # ---- glue ---------------------------------------------------------------------------------
     def apply_model(self, x_noisy, t, context, pose_map, reference_image_noisy, uc=False, hint_feat=None,

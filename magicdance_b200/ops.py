@@ -99,7 +99,7 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
         TRACE.append((m, n, k, tuple(conv) if conv is not None else None, epilogue, splits,
                       a2.shape[1] if a2 is not None else 0))
     if splits > 1:
-        ws = _workspace("splitk", m * n, torch.float32, a.device)
+        ws = _workspace("splitk", splits * m * n, torch.float32, a.device)
         g.splits, g.splitk_ws = splits, ws.data_ptr()
     else:
         g.splits = 1
@@ -190,9 +190,11 @@ def upsample2x(x, *, batch, h, w, c):
 
 
 def add(a, b, *, batch, b_batches=None, out=None):
+    """out = a + b (out may alias a)."""
     lib = _lib.load()
     _chk(a, torch.float16, "a")
     _chk(b, torch.float16, "b")
+    assert a.is_contiguous() and b.is_contiguous()
     if out is None:
         out = torch.empty_like(a)
     n_per = a.numel() // batch
@@ -224,12 +226,12 @@ def skinny_linear(x, w, bias, *, silu_in=False, silu_out=False):
     return out
 
 
-def nchw_f32_to_nhwc_f16(x):
+def nchw_f32_to_nhwc_f16(x, out=None):
     lib = _lib.load()
     _chk(x, torch.float32, "x")
     x = x.contiguous()
     b, c, h, w = x.shape
-    y = torch.empty((b * h * w, c), dtype=torch.float16, device=x.device)
+    y = torch.empty((b * h * w, c), dtype=torch.float16, device=x.device) if out is None else out
     _lib.check(lib.mdb_nchw_f32_to_nhwc_f16(x.data_ptr(), y.data_ptr(), b, c, h, w, _stream()), "nchw_f32_to_nhwc_f16")
     return y
 

@@ -57,16 +57,19 @@ class BankLayout:
         return res
 
 
-def build_and_gather_bank(indices: Sequence[int], layout: BankLayout, build_fn: Callable[[int, torch.Tensor], None],
-                          device, world: int = 1, rank: int = 0, group=None) -> Dict[int, torch.Tensor]:
-    """Each rank calls build_fn(ddim_index, flat_slot) for its share of `indices` (build_fn fills the
-    flat fp16 slot in place), then ONE all_gather_into_tensor exchanges all slots.  Returns
+def build_and_gather_bank(indices: Sequence[int], layout: BankLayout,
+                          build_fn: Callable[[List[int], torch.Tensor], None], device, world: int = 1, rank: int = 0,
+                          group=None, chunk: int = 10) -> Dict[int, torch.Tensor]:
+    """Each rank calls build_fn(ddim_indices_chunk, slots[len(chunk), numel]) for its share of `indices`
+    (build_fn fills the flat fp16 slots in place; chunks of up to `chunk` timesteps are built as ONE
+    batched appearance pass), then ONE all_gather_into_tensor exchanges all slots.  Returns
     ddim index -> flat buffer (a view into the gathered storage)."""
     mine = shard_timesteps(indices, world, rank)
     slots = (len(indices) + world - 1) // world
     local = torch.zeros((slots, layout.numel), dtype=torch.float16, device=device)
-    for s, ix in enumerate(mine):
-        build_fn(ix, local[s])
+    for s0 in range(0, len(mine), chunk):
+        part = mine[s0:s0 + chunk]
+        build_fn(part, local[s0:s0 + len(part)])
     if world == 1:
         return {ix: local[s] for s, ix in enumerate(mine)}
     gathered = torch.empty((world, slots, layout.numel), dtype=torch.float16, device=device)

@@ -104,9 +104,13 @@ class DenoisePipeline:
         b = x.shape[0]
         t = self.t_dev[index].expand(b).contiguous()
         pose = eng.controlnet(x, hint_feat, t, context)
-        eps_c = eng.unet_forward(x, t, context, bank_kv=bank_kv, pose=pose, uc=False)
-        eps_u = eng.unet_forward(x, t, context, uc=True)
-        x_prev, pred_x0 = ops.cfg_ddim_update(x.contiguous(), eps_c, eps_u, self.coef[index], noise=noise)
+        if 2 * b <= 16:
+            eps_c, eps_u = eng.unet_forward(x, t, context, bank_kv=bank_kv, pose=pose, cfg_pair=True)
+        else:
+            eps_c = eng.unet_forward(x, t, context, bank_kv=bank_kv, pose=pose, uc=False)
+            eps_u = eng.unet_forward(x, t, context, uc=True)
+        x_prev, pred_x0 = ops.cfg_ddim_update(x.contiguous(), eps_c.contiguous(), eps_u.contiguous(), self.coef[index],
+                                              noise=noise)
         return x_prev, pred_x0, eps_c, eps_u
 
     @torch.no_grad()
@@ -126,51 +130,67 @@ class DenoisePipeline:
         return x, pred_x0
 
 
-class GraphedDenoiser:
-    """The whole DDIM step (and the per-timestep appearance-bank build) captured once as CUDA graphs
-    and replayed for all 50 steps: at batch 1 the step is ~2000 small kernels, so launch latency and
-    Python would otherwise dominate.  Everything timestep-dependent is read from
-    device memory that is refreshed by tiny copies before each replay (the timestep, the DDIM
-    coefficient row, the bank K/V of that timestep), so ONE graph serves every step."""
+def build_bank_slots(eng: DenoiseEngine, ref_latent, t_vec, context, layout, tokens, out_slots):
+    """Appearance 'write' pass for a BATCH of timesteps of one reference latent (the appearance net
+    takes per-sample t, cldm.py:469-472) + K/V projection, re-laid out as one contiguous flat slot
+    per timestep (parallel.BankLayout with ref_batches=1): out_slots [len(t_vec), layout.numel]."""
+    tb = t_vec.shape[0]
+    ref = ref_latent[:1].expand(tb, -1, -1, -1).contiguous()
+    bank = eng.appearance_write(ref, t_vec, context[:1])
+    kv = eng.project_bank(bank, tb)
+    for (k, vt, n, _), (rows, c), off in zip(kv, layout.layer_shapes, layout.offsets):
+        # K [tb*n, c] -> slot j rows; V^T [c, tb*n] -> slot j [c, n]
+        out_slots[:, off:off + n * c].view(tb, n, c).copy_(k.view(tb, n, c))
+        out_slots[:, off + n * c:off + 2 * n * c].view(tb, c, n).copy_(vt.view(c, tb, n).permute(1, 0, 2))
 
-    def __init__(self, pipe: DenoisePipeline, batch: int, latent_hw, context: torch.Tensor, ref_batches: int = 1):
+
+class GraphedDenoiser:
+    """The whole DDIM step and the (timestep-batched) appearance-bank build captured once as CUDA
+    graphs and replayed: at batch 1 the step is ~1400 small kernels, so launch latency and Python
+    would otherwise dominate.  Everything timestep-dependent is read from device
+    memory refreshed by tiny copies before each replay (the timestep, the DDIM coefficient row, the
+    bank K/V of that timestep), so ONE graph serves every step."""
+
+    def __init__(self, pipe: DenoisePipeline, batch: int, latent_hw, context: torch.Tensor, bank_chunk: int = 10):
         from . import parallel
         self.pipe, self.eng = pipe, pipe.engine
         eng, dev = self.eng, pipe.device
         h, w = latent_hw
-        self.batch = batch
+        self.batch, self.bank_chunk = batch, bank_chunk
         self.ctx = context.to(dev).contiguous()
         self.x = torch.zeros((batch, 4, h, w), dtype=torch.float32, device=dev)
         self.x_prev = torch.zeros_like(self.x)
         self.pred_x0 = torch.zeros_like(self.x)
-        self.ref = torch.zeros((ref_batches, 4, h, w), dtype=torch.float32, device=dev)
+        self.ref = torch.zeros((1, 4, h, w), dtype=torch.float32, device=dev)
         self.t_cur = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.t_vec = torch.zeros((bank_chunk,), dtype=torch.int64, device=dev)
         self.coef_cur = torch.zeros((8,), dtype=torch.float32, device=dev)
         self.hint = torch.zeros((batch * h * w, eng.cfg.model_channels), dtype=torch.float16, device=dev)
         geo = eng.attn_geometry(h, w)
         self.tokens = [n for n, _ in geo]
-        self.layout = parallel.BankLayout([(ref_batches * n, c) for n, c in geo])
-        self.ref_batches = ref_batches
+        self.layout = parallel.BankLayout([(n, c) for n, c in geo])
         self.bank_cur = torch.zeros((self.layout.numel,), dtype=torch.float16, device=dev)
-        self.bank_built = torch.zeros((self.layout.numel,), dtype=torch.float16, device=dev)
+        self.bank_built = torch.zeros((bank_chunk, self.layout.numel), dtype=torch.float16, device=dev)
         self.g_step = self.g_bank = None
+        self.replayed_launches = 0
 
     # the two bodies, written against the static buffers only
     def _step_body(self):
         eng, b = self.eng, self.batch
         t = self.t_cur.expand(b).contiguous()
-        bank_kv = self.layout.views(self.bank_cur, self.tokens, self.ref_batches)
+        bank_kv = self.layout.views(self.bank_cur, self.tokens, 1)
         pose = eng.controlnet(self.x, self.hint, t, self.ctx)
-        eps_c = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, uc=False)
-        eps_u = eng.unet_forward(self.x, t, self.ctx, uc=True)
-        ops.cfg_ddim_update(self.x, eps_c, eps_u, self.coef_cur, x_prev=self.x_prev, pred_x0=self.pred_x0)
+        if 2 * b <= 16:
+            eps_c, eps_u = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, cfg_pair=True)
+        else:
+            eps_c = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, uc=False)
+            eps_u = eng.unet_forward(self.x, t, self.ctx, uc=True)
+        ops.cfg_ddim_update(self.x, eps_c.contiguous(), eps_u.contiguous(), self.coef_cur, x_prev=self.x_prev,
+                            pred_x0=self.pred_x0)
         self.x.copy_(self.x_prev)
 
     def _bank_body(self):
-        eng = self.eng
-        t = self.t_cur.expand(self.ref_batches).contiguous()
-        bank = eng.appearance_write(self.ref, t, self.ctx[:self.ref_batches] if self.ctx.shape[0] > 1 else self.ctx)
-        eng.project_bank(bank, self.ref_batches, out=self.layout.views(self.bank_built, self.tokens, self.ref_batches))
+        build_bank_slots(self.eng, self.ref, self.t_vec, self.ctx, self.layout, self.tokens, self.bank_built)
 
     def capture(self):
         """Warm up eagerly (fills every cache and workspace), then capture both graphs."""
@@ -193,25 +213,24 @@ class GraphedDenoiser:
         torch.cuda.synchronize()
         # kernels of OUR library inside each graph (the C ABI counts launches at capture time only)
         self.bank_launches, self.step_launches = n1 - n0, ops.launch_count() - n1
-        self.replayed_launches = 0
         return self
 
     # ---- replay helpers ---------------------------------------------------------------------------
-    def set_index(self, index):
-        self.t_cur.copy_(self.pipe.t_dev[index:index + 1])
-        self.coef_cur.copy_(self.pipe.coef[index])
-
-    def build_bank(self, index, ref_latent, out_flat):
-        """appearance 'write' pass + K/V projection for ddim index -> out_flat (fp16 [layout.numel])"""
-        self.ref.copy_(ref_latent)
-        self.set_index(index)
+    def build_bank(self, indices, ref_latent, out_slots):
+        """bank K/V of the given ddim indices (<= bank_chunk of them) -> out_slots [len(indices), numel]"""
+        n = len(indices)
+        assert 0 < n <= self.bank_chunk
+        self.ref.copy_(ref_latent[:1])
+        idx = torch.as_tensor(list(indices) + [indices[-1]] * (self.bank_chunk - n), device=self.pipe.device)
+        self.t_vec.copy_(self.pipe.t_dev[idx])
         self.g_bank.replay()
         self.replayed_launches += self.bank_launches
-        out_flat.copy_(self.bank_built)
+        out_slots.copy_(self.bank_built[:n])
 
     def step(self, index, bank_flat):
         """one DDIM step on self.x in place (result also in self.x_prev / self.pred_x0)"""
-        self.set_index(index)
+        self.t_cur.copy_(self.pipe.t_dev[index:index + 1])
+        self.coef_cur.copy_(self.pipe.coef[index])
         self.bank_cur.copy_(bank_flat)
         self.g_step.replay()
         self.replayed_launches += self.step_launches

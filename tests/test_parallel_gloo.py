@@ -25,15 +25,17 @@ def _worker(rank, world, port, q):
     layout = P.BankLayout([(16, 8), (4, 16)])  # two fake attention layers
     built = []
 
-    def build_fn(index, flat):
-        built.append(index)
-        views = layout.views(flat, [16, 4], 1)
-        for li, (k, vt, n, b) in enumerate(views):
-            k.fill_(index + 0.25 * li)
-            vt.fill_(-(index + 0.25 * li))
+    def build_fn(chunk, slots):
+        assert slots.shape == (len(chunk), layout.numel) and len(chunk) <= 3
+        for index, flat in zip(chunk, slots):
+            built.append(index)
+            views = layout.views(flat, [16, 4], 1)
+            for li, (k, vt, n, b) in enumerate(views):
+                k.fill_(index + 0.25 * li)
+                vt.fill_(-(index + 0.25 * li))
 
     indices = list(range(9, -1, -1))  # 10 timesteps over 2 ranks
-    table = P.build_and_gather_bank(indices, layout, build_fn, "cpu", world, rank)
+    table = P.build_and_gather_bank(indices, layout, build_fn, "cpu", world, rank, chunk=3)
     ok = sorted(table) == list(range(10)) and built == P.shard_timesteps(indices, world, rank)
     for ix, flat in table.items():
         for li, (k, vt, n, b) in enumerate(layout.views(flat, [16, 4], 1)):
