@@ -50,7 +50,7 @@ struct AttnKParams {
 };
 
 template <int D, int BKV>
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_constant__ AttnKParams p) {
+__global__ void __launch_bounds__(kAttnThreads, (D <= 80) ? 2 : 1) attn_tc_kernel(const __grid_constant__ AttnKParams p) {
   using C = AttnCfg<D, BKV>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_bar, s_full, p_full, o_done;
@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
   const int t1 = (b < p.bank_batches && p.n1 > 0) ? (p.n1 + BKV - 1) / BKV : 0;
   const int n_tiles = t0 + t1;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK0);
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -171,36 +173,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
       const int valid = min(BKV, (src1 ? p.n1 : p.n0) - key0);
       mbar_wait(&s_full, j & 1);
       tc_fence_after_sync();
-      float sv[BKV];
+      // pass 1 over S (TMEM reads are cheap): row max in the log2 domain
+      float mt = -INFINITY;
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) {
         uint32_t rr[32];
         tmem_ld_x32(t_s + c * 32, rr);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sv[c * 32 + i] = __uint_as_float(rr[i]) * p.scale_log2;
-      }
-      float mt = -INFINITY;
-      if (valid == BKV) {
-#pragma unroll
-        for (int i = 0; i < BKV; ++i) mt = fmaxf(mt, sv[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < BKV; ++i) {
-          if (i >= valid) sv[i] = -INFINITY;
-          mt = fmaxf(mt, sv[i]);
+        for (int i = 0; i < 32; ++i) {
+          const float sc = (c * 32 + i < valid) ? __uint_as_float(rr[i]) * p.scale_log2 : -INFINITY;
+          mt = fmaxf(mt, sc);
         }
       }
       float m_new = m_run;
       if (mt - m_run > 8.0f) m_new = mt;  // lazy: tolerate p <= 2^8 before paying for a rescale
       const float alpha = exp2f(m_run - m_new);  // m_run = -inf on the first tile -> 0
-      float lsum = 0.f;
-#pragma unroll
-      for (int i = 0; i < BKV; ++i) {
-        sv[i] = exp2f(sv[i] - m_new);
-        lsum += sv[i];
-      }
-      l_run = l_run * alpha + lsum;
       m_run = m_new;
 
       if (j > 0) {
@@ -220,17 +208,36 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
           tmem_wait_st();
         }
       }
-      // P -> smem, K-major 128B-swizzled: 16-byte unit u of row r lands at unit (u ^ (r & 7))
+      // pass 2: p = exp2(s - m), row sum, P -> smem (K-major 128B-swizzled: 16-byte unit u of row r
+      // lands at unit u ^ (r & 7)).  32 columns at a time keeps the live register set small enough for
+      // two CTAs per SM, which is what overlaps one CTA's softmax with the other's MMAs.
+      float lsum = 0.f;
+      const float neg_m = -m_new;
 #pragma unroll
-      for (int u = 0; u < BKV / 8; ++u) {
-        uint4 pk;
-        pk.x = pack_half2(sv[u * 8 + 0], sv[u * 8 + 1]);
-        pk.y = pack_half2(sv[u * 8 + 2], sv[u * 8 + 3]);
-        pk.z = pack_half2(sv[u * 8 + 4], sv[u * 8 + 5]);
-        pk.w = pack_half2(sv[u * 8 + 6], sv[u * 8 + 7]);
-        const int kc = u >> 3, uu = u & 7;
-        *reinterpret_cast<uint4*>(p_row + kc * (kBQ * 128) + ((uu ^ sw) << 4)) = pk;
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t rr[32];
+        tmem_ld_x32(t_s + c * 32, rr);
+        tmem_wait_ld();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = (c * 32 + i < valid) ? exp2f(fmaf(__uint_as_float(rr[i]), p.scale_log2, neg_m)) : 0.f;
+          pv[i] = e;
+          lsum += e;
+        }
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) {
+          uint4 pk;
+          pk.x = pack_half2(pv[u4 * 8 + 0], pv[u4 * 8 + 1]);
+          pk.y = pack_half2(pv[u4 * 8 + 2], pv[u4 * 8 + 3]);
+          pk.z = pack_half2(pv[u4 * 8 + 4], pv[u4 * 8 + 5]);
+          pk.w = pack_half2(pv[u4 * 8 + 6], pv[u4 * 8 + 7]);
+          const int u = c * 4 + u4;
+          const int kc = u >> 3, uu = u & 7;
+          *reinterpret_cast<uint4*>(p_row + kc * (kBQ * 128) + ((uu ^ sw) << 4)) = pk;
+        }
       }
+      l_run = l_run * alpha + lsum;
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(&p_full);
@@ -282,8 +289,7 @@ static int launch_attn(const AttnKParams& kp, dim3 grid, cudaStream_t st) {
     MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     attr_set = true;
   }
-  kern<<<grid, kAttnThreads, C::kSmem, st>>>(kp);
-  MDB_CHECK_CUDA(cudaGetLastError());
+  MDB_CHECK_CUDA(launch_pdl(kern, grid, dim3(kAttnThreads), C::kSmem, st, kp));
   count_launch();
   return MDB_OK;
 }

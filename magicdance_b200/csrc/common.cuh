@@ -49,6 +49,26 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 // ----------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
+// launch helper: cudaLaunchKernelEx with the programmatic-stream-serialization attribute (PDL);
+// MDB_PDL=0 in the environment turns the attribute off (then griddepcontrol.* are no-ops).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -62,6 +82,14 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Every kernel of this library starts with pdl_launch_dependents() (the NEXT kernel in the stream may
+// begin its prologue: barrier init, TMEM alloc, descriptor prefetch, index math) and calls pdl_wait()
+// before it touches global memory (waits until the PREVIOUS kernel has completed and flushed).  With
+// ~900 small kernels per denoise step this hides most of the launch-to-launch latency.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- mbarrier --------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -57,51 +57,51 @@ struct GemmSmem {
 
 __device__ __forceinline__ void epi_store_chunk(const GemmKParams& p, long long row, int col0, int ncols,
                                                 float (&v)[32]) {
-  // v holds columns col0 .. col0+31 of `row` (fp32 accumulators); bias + residual, then fp16 store
+  // v holds columns col0 .. col0+31 of `row` (fp32 accumulators); bias + residual, then fp16 store.
+  // Whole groups of 8 columns go through 16-byte accesses, a ragged tail (N = 77) is scalar.
   const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
-  if (p.bias != nullptr) {
-    const float* bp = p.bias + brow * p.bias_batch_stride + col0;
-    if (ncols == 32) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 b4 = *reinterpret_cast<const float4*>(bp + j);
-        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-      }
-    } else {
-      for (int j = 0; j < ncols; ++j) v[j] += bp[j];
-    }
-  }
+  const float* bp = (p.bias != nullptr) ? p.bias + brow * p.bias_batch_stride + col0 : nullptr;
+  const __half* rp = (p.residual != nullptr) ? p.residual + row * p.ldr + col0 : nullptr;
   __half* dp = p.d + row * p.ldd + col0;
-  if (ncols == 32) {
-    if (p.residual != nullptr) {
-      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 r4 = rp[q];
+  for (int q = 0; q < 4; ++q) {
+    if (q * 8 + 8 <= ncols) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = v[q * 8 + e];
+      if (bp != nullptr) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bp + q * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bp + q * 8 + 4);
+        o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+        o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+      }
+      if (rp != nullptr) {
+        const uint4 r4 = *reinterpret_cast<const uint4*>(rp + q * 8);
         const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float2 f = __half22float2(h2[e]);
-          v[q * 8 + e * 2] += f.x;
-          v[q * 8 + e * 2 + 1] += f.y;
+          const float2 f = __half22float2(h2[e]);
+          o[2 * e] += f.x;
+          o[2 * e + 1] += f.y;
         }
       }
-    }
-    uint4* d4 = reinterpret_cast<uint4*>(dp);
+      uint4 o4;
+      o4.x = pack_half2(o[0], o[1]);
+      o4.y = pack_half2(o[2], o[3]);
+      o4.z = pack_half2(o[4], o[5]);
+      o4.w = pack_half2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dp + q * 8) = o4;
+    } else if (q * 8 < ncols) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 o;
-      o.x = pack_half2(v[q * 8 + 0], v[q * 8 + 1]);
-      o.y = pack_half2(v[q * 8 + 2], v[q * 8 + 3]);
-      o.z = pack_half2(v[q * 8 + 4], v[q * 8 + 5]);
-      o.w = pack_half2(v[q * 8 + 6], v[q * 8 + 7]);
-      d4[q] = o;
-    }
-  } else {
-    for (int j = 0; j < ncols; ++j) {
-      float x = v[j];
-      if (p.residual != nullptr) x += __half2float(p.residual[row * p.ldr + col0 + j]);
-      dp[j] = __float2half_rn(x);
+      for (int e = 0; e < 8; ++e) {
+        const int j = q * 8 + e;
+        if (j < ncols) {
+          float x = v[j];
+          if (bp != nullptr) x += bp[j];
+          if (rp != nullptr) x += __half2float(rp[j]);
+          dp[j] = __float2half_rn(x);
+        }
+      }
     }
   }
 }
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
   const int n_iter = kc_end - kc_begin;
   constexpr uint32_t kTmemCols = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
     if (lane == 0 && n_iter > 0) {
@@ -202,27 +204,39 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
     if constexpr (!GEGLU) {
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = 0; ch < (BN + 31) / 32; ++ch) {
         const int col0 = n0 + ch * 32;
         if (col0 >= p.n) break;  // warp-uniform
         uint32_t r[32];
-        tmem_ld_x32(taddr + ch * 32, r);
+        if (BN % 32 != 0 && ch == BN / 32) {  // 16-column tail of an 80-wide tile
+          uint32_t r16[16];
+          tmem_ld_x16(taddr + ch * 32, r16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = r16[j];
+#pragma unroll
+          for (int j = 16; j < 32; ++j) r[j] = 0u;
+        } else {
+          tmem_ld_x32(taddr + ch * 32, r);
+        }
         tmem_wait_ld();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const int ncols = min(32, p.n - col0);
+        const int ncols = min(min(32, BN - ch * 32), p.n - col0);
         if (p.splits > 1) {
           // split-K: this split's fp32 partial goes to its own workspace slab (plain vector stores);
           // splitk_finalize_kernel sums the slabs in a fixed order (deterministic, no atomics).
           if (row_ok) {
             float* wp = p.ws + (static_cast<long long>(split) * p.m + row) * p.n + col0;
-            if (ncols == 32) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
+            for (int j = 0; j < 32; j += 4) {
+              if (j + 4 <= ncols && (p.n & 3) == 0) {
                 *reinterpret_cast<float4*>(wp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              for (int j = 0; j < ncols; ++j) wp[j] = v[j];
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (j + e < ncols) wp[j + e] = v[j + e];
+              }
             }
           }
         } else if (row_ok) {
@@ -279,6 +293,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
 
 // split-K second pass: sum of the fp32 partial slabs ws[splits][M][N] -> bias/residual -> fp16 D
 __global__ void splitk_finalize_kernel(GemmKParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long slab = static_cast<long long>(p.m) * p.n;
   if ((p.n & 3) == 0) {
     const long long total4 = slab >> 2;
@@ -382,8 +398,7 @@ static int launch_gemm(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
     MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
     attr_set = true;
   }
-  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(kp);
-  MDB_CHECK_CUDA(cudaGetLastError());
+  MDB_CHECK_CUDA(launch_pdl(kern, grid, dim3(kGemmThreads), GemmSmem<BN>::kTotal, st, kp));
   count_launch();
   return MDB_OK;
 }
@@ -414,6 +429,10 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   kp.conv = g->conv;
   MDB_REQUIRE(g->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(g->d) & 15) == 0,
               "mdb_gemm_f16: D must be 16B aligned with ldd %% 8 == 0 (ldd=%lld)", (long long)g->ldd);
+  if (g->bias) {
+    MDB_REQUIRE((reinterpret_cast<uintptr_t>(g->bias) & 15) == 0 && g->bias_batch_stride % 4 == 0,
+                "mdb_gemm_f16: bias must be 16B aligned with bias_batch_stride %% 4 == 0");
+  }
   if (g->residual) {
     MDB_REQUIRE(g->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0,
                 "mdb_gemm_f16: residual must be 16B aligned with ldr %% 8 == 0");
@@ -465,8 +484,12 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   if (geglu) {
     MDB_REQUIRE(g->n % 128 == 0, "mdb_gemm_f16: GEGLU needs N %% 128 == 0 (N=%d)", g->n);
     bn = 128;
+  } else if (g->n % 160 == 0) {
+    // 160-wide tiles unless that leaves most of the 148 SMs idle; then halve the tile width
+    const long long tiles160 = (long long)((g->m + kBM - 1) / kBM) * (g->n / 160) * (g->splits > 1 ? g->splits : 1);
+    bn = (tiles160 < 100) ? 80 : 160;
   } else {
-    bn = (g->n % 160 == 0) ? 160 : 128;
+    bn = 128;
   }
   {
     uint32_t box[2] = {kBK, (uint32_t)bn};
@@ -490,14 +513,14 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   dim3 grid((g->m + kBM - 1) / kBM, (g->n + bn - 1) / bn, splits);
   if (geglu) rc = launch_gemm<128, true>(kp, grid, st);
   else if (bn == 160) rc = launch_gemm<160, false>(kp, grid, st);
+  else if (bn == 80) rc = launch_gemm<80, false>(kp, grid, st);
   else rc = launch_gemm<128, false>(kp, grid, st);
   if (rc) return rc;
   if (splits > 1) {
     const long long total = ((long long)g->m * g->n + 3) / 4;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_finalize_kernel<<<blocks, 256, 0, st>>>(kp);
-    MDB_CHECK_CUDA(cudaGetLastError());
+    MDB_CHECK_CUDA(launch_pdl(splitk_finalize_kernel, dim3(blocks), dim3(256), 0, st, kp));
     count_launch();
   }
   return MDB_OK;

@@ -2,6 +2,7 @@
 // im2col (stride-2 downsample), nearest x2 upsample, residual add, timestep embedding, skinny
 // Linear for the timestep MLPs, NCHW fp32 <-> NHWC fp16 boundary converts, fused CFG + DDIM update.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -23,6 +24,14 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n = 1);
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MDB_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // direct 3x3 conv, pad 1, stride 1|2, NHWC fp16, fp32 accumulate.
@@ -39,6 +48,8 @@ __global__ void __launch_bounds__(256) direct_conv3x3_kernel(const __half* __res
                                                              const __half* __restrict__ residual, __half* __restrict__ y,
                                                              int h, int w, int cin, int cout, int ho, int wo, int silu) {
   constexpr int PH = (kDcTile - 1) * STRIDE + 3;  // patch height/width
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_in[PH * PH * kDcCin];
   __shared__ float s_w[kDcCout * 9 * kDcCin];
   const int tiles_x = (wo + kDcTile - 1) / kDcTile;
@@ -99,58 +110,74 @@ __global__ void __launch_bounds__(256) direct_conv3x3_kernel(const __half* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// 3x3 stride-1 conv with a tiny input-channel count (the 4->320 input conv): K = 9*cin <= 72.
-// CTA = 8 pixels x (cout/8) channel groups; weights live in shared memory as fp32.
+// 3x3 stride-1 conv with a tiny input-channel count (the 4->320 input conv): K = 9*CIN.
+// CTA = 8 pixel slots x (cout/8) channel groups, each thread walks 4 pixels; the weights sit in shared
+// memory as fp32 laid out [k][j][group] so that a warp's reads are conflict-free; they are constants,
+// so they are staged BEFORE the PDL wait and overlap the previous kernel's tail.
 // ---------------------------------------------------------------------------------------------
-constexpr int kCiPix = 8;
+constexpr int kCiSlots = 8;
+constexpr int kCiPixPerThread = 4;
+template <int CIN>
 __global__ void conv3x3_smallcin_kernel(const __half* __restrict__ x, const __half* __restrict__ wt,
                                         const float* __restrict__ bias, const __half* __restrict__ residual,
-                                        __half* __restrict__ y, int batch, int h, int w, int cin, int cout, int silu) {
-  extern __shared__ float s_wt[];  // [cout][9*cin]
-  const int kk = 9 * cin;
-  for (int i = threadIdx.x; i < cout * kk; i += blockDim.x) s_wt[i] = __half2float(wt[i]);
-  __syncthreads();
+                                        __half* __restrict__ y, int batch, int h, int w, int cout, int silu) {
+  extern __shared__ float s_wt[];  // [9*CIN][8][groups]
+  constexpr int KK = 9 * CIN;
   const int groups = cout / 8;
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < cout * KK; i += blockDim.x) {
+    const int co = i / KK, k = i - co * KK;
+    s_wt[(k * 8 + (co & 7)) * groups + (co >> 3)] = __half2float(wt[i]);
+  }
+  __syncthreads();
+  pdl_wait();
   const int g = threadIdx.x % groups;
-  const int pl = threadIdx.x / groups;
-  const long long pix = static_cast<long long>(blockIdx.x) * kCiPix + pl;
+  const int slot = threadIdx.x / groups;
+  if (slot >= kCiSlots) return;
   const long long npix = static_cast<long long>(batch) * h * w;
-  if (pl >= kCiPix || pix >= npix) return;
-  const int xx = static_cast<int>(pix % w), yy = static_cast<int>((pix / w) % h);
-  const long long b = pix / (static_cast<long long>(w) * h);
-  float in[72];
+  float bj[8];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int iy = yy + t / 3 - 1, ix = xx + t % 3 - 1;
-    const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
-    for (int ci = 0; ci < cin; ++ci)
-      in[t * 8 + ci] = ok ? __half2float(x[((b * h + iy) * w + ix) * cin + ci]) : 0.f;
-  }
-  float acc[8];
+  for (int j = 0; j < 8; ++j) bj[j] = bias ? bias[g * 8 + j] : 0.f;
+  for (int pp = 0; pp < kCiPixPerThread; ++pp) {
+    const long long pix = (static_cast<long long>(blockIdx.x) * kCiPixPerThread + pp) * kCiSlots + slot;
+    if (pix >= npix) break;
+    const int xx = static_cast<int>(pix % w), yy = static_cast<int>((pix / w) % h);
+    const long long b = pix / (static_cast<long long>(w) * h);
+    float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int co = g * 8 + j;
-    float a = bias ? bias[co] : 0.f;
-    const float* wr = &s_wt[co * kk];
-    for (int t = 0; t < 9; ++t)
-      for (int ci = 0; ci < cin; ++ci) a += in[t * 8 + ci] * wr[t * cin + ci];
-    if (silu) a = silu_f(a);
-    acc[j] = a;
-  }
-  const long long o = pix * cout + g * 8;
-  if (residual) {
-    uint4 r4 = *reinterpret_cast<const uint4*>(residual + o);
-    const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
+    for (int j = 0; j < 8; ++j) acc[j] = bj[j];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 f = __half22float2(h2[e]);
-      acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+    for (int t = 0; t < 9; ++t) {
+      const int iy = yy + t / 3 - 1, ix = xx + t % 3 - 1;
+      if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
+      const __half* xp = x + ((b * h + iy) * w + ix) * CIN;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float xv = __half2float(xp[ci]);
+        const float* wr = &s_wt[((t * CIN + ci) * 8) * groups + g];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += xv * wr[j * groups];
+      }
     }
+    if (silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = silu_f(acc[j]);
+    }
+    const long long o = pix * cout + g * 8;
+    if (residual) {
+      uint4 r4 = *reinterpret_cast<const uint4*>(residual + o);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h2[e]);
+        acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+      }
+    }
+    uint4 o4;
+    o4.x = pack_half2(acc[0], acc[1]); o4.y = pack_half2(acc[2], acc[3]);
+    o4.z = pack_half2(acc[4], acc[5]); o4.w = pack_half2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(y + o) = o4;
   }
-  uint4 o4;
-  o4.x = pack_half2(acc[0], acc[1]); o4.y = pack_half2(acc[2], acc[3]);
-  o4.z = pack_half2(acc[4], acc[5]); o4.w = pack_half2(acc[6], acc[7]);
-  *reinterpret_cast<uint4*>(y + o) = o4;
 }
 
 // 3x3 stride-1 conv with a tiny output-channel count (the 320->4 output conv): one warp per pixel,
@@ -161,9 +188,11 @@ __global__ void conv3x3_smallcout_kernel(const __half* __restrict__ x, const __h
                                          int w, int cin, int silu) {
   extern __shared__ __half s_wh[];  // [COUT][9*cin]
   const int kk = 9 * cin;
+  pdl_launch_dependents();
   for (int i = threadIdx.x * 8; i < COUT * kk; i += blockDim.x * 8)
     *reinterpret_cast<uint4*>(&s_wh[i]) = *reinterpret_cast<const uint4*>(&wt[i]);
   __syncthreads();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
   const long long npix = static_cast<long long>(batch) * h * w;
@@ -220,6 +249,8 @@ __global__ void conv3x3_smallcout_kernel(const __half* __restrict__ x, const __h
 // ---------------------------------------------------------------------------------------------
 __global__ void im2col3x3s2_kernel(const __half* __restrict__ x, __half* __restrict__ col, int batch, int h, int w,
                                    int c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ho = h / 2, wo = w / 2, vecs = c / 8;
   const long long total = static_cast<long long>(batch) * ho * wo * 9 * vecs;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -240,6 +271,8 @@ __global__ void im2col3x3s2_kernel(const __half* __restrict__ x, __half* __restr
 }
 
 __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ y, int batch, int h, int w, int c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vecs = c / 8;
   const long long total = static_cast<long long>(batch) * (2 * h) * (2 * w) * vecs;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -256,6 +289,8 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restri
 
 __global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ y,
                            long long n_per_batch, int batch, int b_batches) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long vec_per = n_per_batch / 8;
   const long long total = vec_per * batch;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -275,6 +310,8 @@ __global__ void add_kernel(const __half* __restrict__ a, const __half* __restric
 }
 
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int batch, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * half) return;
@@ -290,6 +327,8 @@ template <int ROWS>
 __global__ void skinny_linear_kernel(const float* __restrict__ x, const __half* __restrict__ w,
                                      const float* __restrict__ bias, float* __restrict__ out, int rows, int n, int k,
                                      int silu_in, int silu_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n) return;
@@ -335,6 +374,8 @@ __global__ void skinny_linear_kernel(const float* __restrict__ x, const __half* 
 
 __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int batch, int c, int h,
                                             int w) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(batch) * c * h * w;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -350,6 +391,8 @@ __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half*
 
 __global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, int batch, int c, int h,
                                             int w) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(batch) * c * h * w;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -368,6 +411,8 @@ __global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float*
                                        const float* __restrict__ eu, const float* __restrict__ noise,
                                        float* __restrict__ x_prev, float* __restrict__ pred_x0, long long n,
                                        const float* __restrict__ coef) {
+  pdl_launch_dependents();
+  pdl_wait();
   // coef (device, so one captured CUDA graph serves all 50 steps):
   //   {cfg scale, sqrt(a_t), sqrt(a_prev), sqrt(1 - a_prev - sigma^2), sigma, sqrt(1 - a_t)}
   const float scale = coef[0], sqrt_at = coef[1], sqrt_aprev = coef[2], dir_coef = coef[3], sigma = coef[4],
@@ -420,19 +465,20 @@ extern "C" int mdb_conv3x3_direct_f16(const void* x, const void* wt, const float
   dim3 grid(((wo + kDcTile - 1) / kDcTile) * ((ho + kDcTile - 1) / kDcTile), (cout + kDcCout - 1) / kDcCout, batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long npix = static_cast<long long>(batch) * h * w;
-  if (stride == 1 && cin <= 8 && cout % 8 == 0 && cout * 9 * cin * 4 <= 96 * 1024 && kCiPix * (cout / 8) <= 1024) {
+  if (stride == 1 && cin == 4 && cout % 8 == 0 && cout * 36 * 4 <= 96 * 1024 && kCiSlots * (cout / 8) <= 1024) {
     // tiny-cin path (input conv)
     static bool attr_set = false;
-    const int smem = cout * 9 * cin * 4;
+    const int smem = cout * 36 * 4;
     if (!attr_set) {
-      MDB_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_smallcin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      MDB_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_smallcin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       attr_set = true;
     }
-    const int threads = ((kCiPix * (cout / 8) + 31) / 32) * 32;
-    conv3x3_smallcin_kernel<<<static_cast<int>((npix + kCiPix - 1) / kCiPix), threads, smem, st>>>(
-        static_cast<const __half*>(x), static_cast<const __half*>(wt), bias, static_cast<const __half*>(residual),
-        static_cast<__half*>(y), batch, h, w, cin, cout, silu);
-    MDB_CHECK_CUDA(cudaGetLastError());
+    const int threads = ((kCiSlots * (cout / 8) + 31) / 32) * 32;
+    const int per_block = kCiSlots * kCiPixPerThread;
+    MDB_CHECK_CUDA(launch_pdl(conv3x3_smallcin_kernel<4>, dim3(static_cast<unsigned>((npix + per_block - 1) / per_block)),
+                              dim3(threads), smem, st, static_cast<const __half*>(x), static_cast<const __half*>(wt),
+                              bias, static_cast<const __half*>(residual), static_cast<__half*>(y), batch, h, w, cout,
+                              silu));
     count_launch();
     return MDB_OK;
   }
@@ -446,21 +492,20 @@ extern "C" int mdb_conv3x3_direct_f16(const void* x, const void* wt, const float
     }
     int blocks = static_cast<int>((npix + 7) / 8);
     if (blocks > 148 * 4) blocks = 148 * 4;
-    conv3x3_smallcout_kernel<4><<<blocks, 256, smem, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(wt),
-                                                          bias, static_cast<__half*>(y), batch, h, w, cin, silu);
-    MDB_CHECK_CUDA(cudaGetLastError());
+    MDB_CHECK_CUDA(launch_pdl(conv3x3_smallcout_kernel<4>, dim3(blocks), dim3(256), smem, st,
+                              static_cast<const __half*>(x), static_cast<const __half*>(wt), bias,
+                              static_cast<__half*>(y), batch, h, w, cin, silu));
     count_launch();
     return MDB_OK;
   }
   if (stride == 1)
-    direct_conv3x3_kernel<1><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(wt), bias,
-                                                   static_cast<const __half*>(residual), static_cast<__half*>(y), h, w,
-                                                   cin, cout, ho, wo, silu);
+    MDB_CHECK_CUDA(launch_pdl(direct_conv3x3_kernel<1>, grid, dim3(256), 0, st, static_cast<const __half*>(x),
+                              static_cast<const __half*>(wt), bias, static_cast<const __half*>(residual),
+                              static_cast<__half*>(y), h, w, cin, cout, ho, wo, silu));
   else
-    direct_conv3x3_kernel<2><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(wt), bias,
-                                                   static_cast<const __half*>(residual), static_cast<__half*>(y), h, w,
-                                                   cin, cout, ho, wo, silu);
-  MDB_CHECK_CUDA(cudaGetLastError());
+    MDB_CHECK_CUDA(launch_pdl(direct_conv3x3_kernel<2>, grid, dim3(256), 0, st, static_cast<const __half*>(x),
+                              static_cast<const __half*>(wt), bias, static_cast<const __half*>(residual),
+                              static_cast<__half*>(y), h, w, cin, cout, ho, wo, silu));
   count_launch();
   return MDB_OK;
 }
@@ -470,9 +515,8 @@ extern "C" int mdb_im2col3x3s2_f16(const void* x, void* col, int32_t batch, int3
   MDB_REQUIRE(x && col, "mdb_im2col3x3s2_f16: null pointer");
   MDB_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "mdb_im2col3x3s2_f16: need c %% 8 == 0 and even h, w");
   const long long total = static_cast<long long>(batch) * (h / 2) * (w / 2) * 9 * (c / 8);
-  im2col3x3s2_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), static_cast<__half*>(col), batch, h, w, c);
-  MDB_CHECK_CUDA(cudaGetLastError());
+  MDB_CHECK_CUDA(launch_pdl(im2col3x3s2_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                            static_cast<const __half*>(x), static_cast<__half*>(col), batch, h, w, c));
   count_launch();
   return MDB_OK;
 }
@@ -481,9 +525,8 @@ extern "C" int mdb_upsample2x_f16(const void* x, void* y, int32_t batch, int32_t
                                   mdb_stream_t stream) {
   MDB_REQUIRE(x && y && c % 8 == 0, "mdb_upsample2x_f16: bad arguments");
   const long long total = static_cast<long long>(batch) * 4 * h * w * (c / 8);
-  upsample2x_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), static_cast<__half*>(y), batch, h, w, c);
-  MDB_CHECK_CUDA(cudaGetLastError());
+  MDB_CHECK_CUDA(launch_pdl(upsample2x_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                            static_cast<const __half*>(x), static_cast<__half*>(y), batch, h, w, c));
   count_launch();
   return MDB_OK;
 }
@@ -492,10 +535,10 @@ extern "C" int mdb_add_f16(const void* a, const void* b, void* y, int64_t n_per_
                            mdb_stream_t stream) {
   MDB_REQUIRE(a && b && y && n_per_batch % 8 == 0, "mdb_add_f16: bad arguments");
   MDB_REQUIRE(b_batches == 1 || b_batches == batch, "mdb_add_f16: b_batches must be 1 or batch");
-  add_kernel<<<grid_for(n_per_batch / 8 * batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<__half*>(y), n_per_batch, batch,
-      b_batches);
-  MDB_CHECK_CUDA(cudaGetLastError());
+  MDB_CHECK_CUDA(launch_pdl(add_kernel, dim3(grid_for(n_per_batch / 8 * batch)), dim3(256), 0,
+                            static_cast<cudaStream_t>(stream), static_cast<const __half*>(a),
+                            static_cast<const __half*>(b), static_cast<__half*>(y), static_cast<long long>(n_per_batch),
+                            batch, b_batches));
   count_launch();
   return MDB_OK;
 }
@@ -503,8 +546,8 @@ extern "C" int mdb_add_f16(const void* a, const void* b, void* y, int64_t n_per_
 extern "C" int mdb_timestep_embedding_f32(const int64_t* t, float* out, int32_t batch, int32_t dim, mdb_stream_t stream) {
   MDB_REQUIRE(t && out && dim % 2 == 0, "mdb_timestep_embedding_f32: bad arguments");
   const int total = batch * dim / 2;
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, out, batch, dim);
-  MDB_CHECK_CUDA(cudaGetLastError());
+  MDB_CHECK_CUDA(launch_pdl(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0,
+                            static_cast<cudaStream_t>(stream), t, out, batch, dim));
   count_launch();
   return MDB_OK;
 }
@@ -518,12 +561,14 @@ extern "C" int mdb_skinny_linear_f32(const float* x, const void* w, const float*
   const int blocks = (n * 32 + threads - 1) / threads;
   const __half* wp = static_cast<const __half*>(w);
   if (rows <= 2)
-    skinny_linear_kernel<2><<<blocks, threads, 0, st>>>(x, wp, bias, out, rows, n, k, silu_in, silu_out);
+    MDB_CHECK_CUDA(launch_pdl(skinny_linear_kernel<2>, dim3(blocks), dim3(threads), 0, st, x, wp, bias, out, rows, n, k,
+                              silu_in, silu_out));
   else if (rows <= 8)
-    skinny_linear_kernel<8><<<blocks, threads, 0, st>>>(x, wp, bias, out, rows, n, k, silu_in, silu_out);
+    MDB_CHECK_CUDA(launch_pdl(skinny_linear_kernel<8>, dim3(blocks), dim3(threads), 0, st, x, wp, bias, out, rows, n, k,
+                              silu_in, silu_out));
   else
-    skinny_linear_kernel<16><<<blocks, threads, 0, st>>>(x, wp, bias, out, rows, n, k, silu_in, silu_out);
-  MDB_CHECK_CUDA(cudaGetLastError());
+    MDB_CHECK_CUDA(launch_pdl(skinny_linear_kernel<16>, dim3(blocks), dim3(threads), 0, st, x, wp, bias, out, rows, n, k,
+                              silu_in, silu_out));
   count_launch();
   return MDB_OK;
 }
@@ -532,9 +577,8 @@ extern "C" int mdb_nchw_f32_to_nhwc_f16(const float* x, void* y, int32_t batch, 
                                         mdb_stream_t stream) {
   MDB_REQUIRE(x && y, "mdb_nchw_f32_to_nhwc_f16: null pointer");
   const long long total = static_cast<long long>(batch) * c * h * w;
-  nchw_f32_to_nhwc_f16_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<__half*>(y), batch, c, h, w);
-  MDB_CHECK_CUDA(cudaGetLastError());
+  MDB_CHECK_CUDA(launch_pdl(nchw_f32_to_nhwc_f16_kernel, dim3(grid_for(total)), dim3(256), 0,
+                            static_cast<cudaStream_t>(stream), x, static_cast<__half*>(y), batch, c, h, w));
   count_launch();
   return MDB_OK;
 }
@@ -543,9 +587,8 @@ extern "C" int mdb_nhwc_f16_to_nchw_f32(const void* x, float* y, int32_t batch, 
                                         mdb_stream_t stream) {
   MDB_REQUIRE(x && y, "mdb_nhwc_f16_to_nchw_f32: null pointer");
   const long long total = static_cast<long long>(batch) * c * h * w;
-  nhwc_f16_to_nchw_f32_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), y, batch, c, h, w);
-  MDB_CHECK_CUDA(cudaGetLastError());
+  MDB_CHECK_CUDA(launch_pdl(nhwc_f16_to_nchw_f32_kernel, dim3(grid_for(total)), dim3(256), 0,
+                            static_cast<cudaStream_t>(stream), static_cast<const __half*>(x), y, batch, c, h, w));
   count_launch();
   return MDB_OK;
 }
@@ -554,9 +597,8 @@ extern "C" int mdb_cfg_ddim_update_f32(const float* x, const float* eps_c, const
                                        float* x_prev, float* pred_x0, int64_t n, const float* coef,
                                        mdb_stream_t stream) {
   MDB_REQUIRE(x && eps_c && eps_u && x_prev && pred_x0 && coef && n > 0, "mdb_cfg_ddim_update_f32: bad arguments");
-  cfg_ddim_update_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, eps_c, eps_u, noise, x_prev,
-                                                                                     pred_x0, n, coef);
-  MDB_CHECK_CUDA(cudaGetLastError());
+  MDB_CHECK_CUDA(launch_pdl(cfg_ddim_update_kernel, dim3(grid_for(n)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                            x, eps_c, eps_u, noise, x_prev, pred_x0, static_cast<long long>(n), coef));
   count_launch();
   return MDB_OK;
 }

@@ -25,6 +25,7 @@ __device__ __forceinline__ const uint4* gn_src(const __half* x1, int c1, const _
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
                                 float* __restrict__ stats, int hw, int rows_per_cta) {
   extern __shared__ float sh[];  // [2][32] group sums
+  pdl_launch_dependents();
   const int c = c1 + c2;
   const int cg = c / 32;
   const int b = blockIdx.y;
@@ -33,6 +34,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __h
   const int vecs = c / 8;
   if (threadIdx.x < 64) sh[threadIdx.x] = 0.f;
   __syncthreads();
+  pdl_wait();
   const int v = threadIdx.x % vecs;
   const int rphase = threadIdx.x / vecs;
   const int rstride = blockDim.x / vecs;
@@ -78,6 +80,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __h
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ stats, __half* __restrict__ y, int batch, int hw, float eps,
                                 int silu) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = c1 + c2;
   const int cg = c / 32;
   const int vecs = c / 8;
@@ -119,6 +123,8 @@ template <int VPL>  // half2 pairs per lane
 __global__ void layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, __half* __restrict__ y, long long rows, int c,
                                  float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -177,16 +183,15 @@ extern "C" int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int
   if (rows_per_cta > 8 * rstride) rows_per_cta = 8 * rstride;
   if (rows_per_cta < rstride) rows_per_cta = rstride;
   dim3 grid((hw + rows_per_cta - 1) / rows_per_cta, batch);
-  gn_stats_kernel<<<grid, threads, 64 * sizeof(float), st>>>(static_cast<const __half*>(x1), c1,
-                                                             static_cast<const __half*>(x2), c2, stats_ws, hw,
-                                                             rows_per_cta);
-  MDB_CHECK_CUDA(cudaGetLastError());
+  MDB_CHECK_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), 64 * sizeof(float), st,
+                            static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2, stats_ws, hw,
+                            rows_per_cta));
   const long long total = static_cast<long long>(batch) * hw * vecs;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_apply_kernel<<<blocks, 256, 0, st>>>(static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2,
-                                          gamma, beta, stats_ws, static_cast<__half*>(y), batch, hw, eps, silu);
-  MDB_CHECK_CUDA(cudaGetLastError());
+  MDB_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3(blocks), dim3(256), 0, st, static_cast<const __half*>(x1), c1,
+                            static_cast<const __half*>(x2), c2, gamma, beta, static_cast<const float*>(stats_ws),
+                            static_cast<__half*>(y), batch, hw, eps, silu));
   count_launch(2);
   return MDB_OK;
 }
@@ -201,9 +206,10 @@ extern "C" int mdb_layernorm_f16(const void* x, const float* gamma, const float*
   const int blocks = static_cast<int>((rows * 32 + threads - 1) / threads);
   const __half* xp = static_cast<const __half*>(x);
   __half* yp = static_cast<__half*>(y);
-#define MDB_LN_CASE(V)                                                                       \
-  case V:                                                                                    \
-    layernorm_kernel<V><<<blocks, threads, 0, st>>>(xp, gamma, beta, yp, rows, c, eps);      \
+#define MDB_LN_CASE(V)                                                                                       \
+  case V:                                                                                                    \
+    MDB_CHECK_CUDA(launch_pdl(layernorm_kernel<V>, dim3(blocks), dim3(threads), 0, st, xp, gamma, beta, yp,  \
+                              static_cast<long long>(rows), c, eps));                                        \
     break;
   switch (vpl) {
     MDB_LN_CASE(5)
@@ -214,7 +220,6 @@ extern "C" int mdb_layernorm_f16(const void* x, const float* gamma, const float*
       return MDB_ERR_UNSUPPORTED;
   }
 #undef MDB_LN_CASE
-  MDB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return MDB_OK;
 }

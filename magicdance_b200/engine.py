@@ -256,16 +256,21 @@ def _igemm_ok(h, w, c):
 
 def _auto_splits(m, n, k):
     """Split-K factor: small-M layers (8x8 / 16x16 latents) would otherwise run on a handful of SMs and
-    stream their weights at a fraction of HBM bandwidth."""
+    stream their weights at a fraction of HBM bandwidth.  Mirrors the tile choice of mdb_gemm_f16:
+    160-wide tiles, 80-wide when that leaves most SMs idle; split K only if still under ~100 CTAs."""
     if os.environ.get("MDB_SPLITK", "1") == "0":
         return 1
-    bn = 160 if n % 160 == 0 else 128
-    tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
+    mt = (m + 127) // 128
+    if n % 160 == 0:
+        tiles = mt * (n // 160)
+        if tiles < 100:
+            tiles *= 2  # the kernel switches to 80-wide tiles
+    else:
+        tiles = mt * ((n + 127) // 128)
     chunks = k // 64
-    if tiles >= 96 or chunks < 8:
+    if tiles >= 100 or chunks < 8:
         return 1
-    s = min(16, max(1, 148 // tiles), chunks // 4)
-    return max(1, s)
+    return max(1, min(16, 148 // tiles, chunks // 4))
 
 
 class DenoiseEngine:
