@@ -173,22 +173,33 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 80) ? 2 : 1) attn_tc_kerne
       const int valid = min(BKV, (src1 ? p.n1 : p.n0) - key0);
       mbar_wait(&s_full, j & 1);
       tc_fence_after_sync();
-      // pass 1 over S (TMEM reads are cheap): row max in the log2 domain
+      // pass 1 over S (TMEM reads are cheap): raw row max; the softmax scale is positive, so it is applied
+      // to the max afterwards.  The unmasked path costs half an instruction per element (3-input max).
       float mt = -INFINITY;
+      if (valid == BKV) {
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t rr[32];
-        tmem_ld_x32(t_s + c * 32, rr);
-        tmem_wait_ld();
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t rr[32];
+          tmem_ld_x32(t_s + c * 32, rr);
+          tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sc = (c * 32 + i < valid) ? __uint_as_float(rr[i]) * p.scale_log2 : -INFINITY;
-          mt = fmaxf(mt, sc);
+          for (int i = 0; i < 32; i += 2) mt = fmax3(mt, __uint_as_float(rr[i]), __uint_as_float(rr[i + 1]));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t rr[32];
+          tmem_ld_x32(t_s + c * 32, rr);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mt = fmaxf(mt, __uint_as_float(rr[i]));
         }
       }
+      mt *= p.scale_log2;
       float m_new = m_run;
       if (mt - m_run > 8.0f) m_new = mt;  // lazy: tolerate p <= 2^8 before paying for a rescale
-      const float alpha = exp2f(m_run - m_new);  // m_run = -inf on the first tile -> 0
+      const float alpha = ex2_approx(m_run - m_new);  // m_run = -inf on the first tile -> 0
       m_run = m_new;
 
       if (j > 0) {
@@ -211,7 +222,7 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 80) ? 2 : 1) attn_tc_kerne
       // pass 2: p = exp2(s - m), row sum, P -> smem (K-major 128B-swizzled: 16-byte unit u of row r
       // lands at unit u ^ (r & 7)).  32 columns at a time keeps the live register set small enough for
       // two CTAs per SM, which is what overlaps one CTA's softmax with the other's MMAs.
-      float lsum = 0.f;
+      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
       const float neg_m = -m_new;
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) {
@@ -219,11 +230,17 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 80) ? 2 : 1) attn_tc_kerne
         tmem_ld_x32(t_s + c * 32, rr);
         tmem_wait_ld();
         float pv[32];
+        if (valid == BKV) {  // one FFMA + one MUFU.EX2 + one FADD per element
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = (c * 32 + i < valid) ? exp2f(fmaf(__uint_as_float(rr[i]), p.scale_log2, neg_m)) : 0.f;
-          pv[i] = e;
-          lsum += e;
+          for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(rr[i]), p.scale_log2, neg_m));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            pv[i] = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(rr[i]), p.scale_log2, neg_m)) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          ls0 += pv[i]; ls1 += pv[i + 1]; ls2 += pv[i + 2]; ls3 += pv[i + 3];
         }
 #pragma unroll
         for (int u4 = 0; u4 < 4; ++u4) {
@@ -237,6 +254,7 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 80) ? 2 : 1) attn_tc_kerne
           *reinterpret_cast<uint4*>(p_row + kc * (kBQ * 128) + ((uu ^ sw) << 4)) = pk;
         }
       }
+      const float lsum = (ls0 + ls1) + (ls2 + ls3);
       l_run = l_run * alpha + lsum;
       fence_proxy_async_smem();
       tc_fence_before_sync();

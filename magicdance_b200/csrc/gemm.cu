@@ -21,7 +21,6 @@ namespace mdb {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 halves = 128 B = one swizzle row
-constexpr int kStages = 3;
 constexpr int kGemmThreads = 192;
 
 struct GemmKParams {
@@ -47,12 +46,15 @@ struct GemmKParams {
   int y_box;           // rows of the image covered by one M tile (hw >= 128) or h (hw < 128)
 };
 
-template <int BN>
+// STAGES = 3: <=108 KB, two CTAs per SM (large grids: the co-resident CTA hides the TMA round trip).
+// STAGES = 6 (8 for 80-wide tiles): one CTA per SM with a ring deep enough to cover the TMA latency on
+// its own — used when the grid has at most one CTA per SM anyway and the K loop is long.
+template <int BN, int STAGES>
 struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTotal = kStages * kStageBytes + 1024;  // + alignment slack
+  static constexpr int kTotal = STAGES * kStageBytes + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ void epi_store_chunk(const GemmKParams& p, long long row, int col0, int ncols,
@@ -106,9 +108,10 @@ __device__ __forceinline__ void epi_store_chunk(const GemmKParams& p, long long 
   }
 }
 
-template <int BN, bool GEGLU>
-__global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
-  using S = GemmSmem<BN>;
+template <int BN, bool GEGLU, int kStages>
+__global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
+    gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
+  using S = GemmSmem<BN, kStages>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
@@ -390,15 +393,16 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 
 void count_launch(int n = 1);
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, int STAGES>
 static int launch_gemm(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, GEGLU>;
+  auto kern = gemm_tc_kernel<BN, GEGLU, STAGES>;
   if (!attr_set) {
-    MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
+    MDB_CHECK_CUDA(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, STAGES>::kTotal));
     attr_set = true;
   }
-  MDB_CHECK_CUDA(launch_pdl(kern, grid, dim3(kGemmThreads), GemmSmem<BN>::kTotal, st, kp));
+  MDB_CHECK_CUDA(launch_pdl(kern, grid, dim3(kGemmThreads), GemmSmem<BN, STAGES>::kTotal, st, kp));
   count_launch();
   return MDB_OK;
 }
@@ -511,10 +515,11 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   }
 
   dim3 grid((g->m + kBM - 1) / kBM, (g->n + bn - 1) / bn, splits);
-  if (geglu) rc = launch_gemm<128, true>(kp, grid, st);
-  else if (bn == 160) rc = launch_gemm<160, false>(kp, grid, st);
-  else if (bn == 80) rc = launch_gemm<80, false>(kp, grid, st);
-  else rc = launch_gemm<128, false>(kp, grid, st);
+  const bool deep = (long long)grid.x * grid.y * grid.z <= 148 && kp.chunks_per_split >= 12;
+  if (geglu) rc = launch_gemm<128, true, 3>(kp, grid, st);
+  else if (bn == 160) rc = deep ? launch_gemm<160, false, 6>(kp, grid, st) : launch_gemm<160, false, 3>(kp, grid, st);
+  else if (bn == 80) rc = deep ? launch_gemm<80, false, 8>(kp, grid, st) : launch_gemm<80, false, 3>(kp, grid, st);
+  else rc = deep ? launch_gemm<128, false, 6>(kp, grid, st) : launch_gemm<128, false, 3>(kp, grid, st);
   if (rc) return rc;
   if (splits > 1) {
     const long long total = ((long long)g->m * g->n + 3) / 4;
