@@ -500,7 +500,8 @@ class DenoiseEngine:
         outs.append(ops.gemm(x.data, zw, bias=zb, splits=_auto_splits(x.b * x.hw, x.c, x.c)))
         return outs
 
-    def unet_forward(self, x_noisy, t, context, bank_kv=None, pose=None, uc=False, taps=None, cfg_pair=False):
+    def unet_forward(self, x_noisy, t, context, bank_kv=None, pose=None, uc=False, taps=None, cfg_pair=False,
+                     before_pose=None):
         """ControlledUnetModelAttnPose.forward (cldm.py:59-112).  uc=True: plain SD UNet without bank
         or pose residuals (cldm.py:70-84); otherwise 'read' mode.  bank_kv: project_bank() output.
         Returns eps as NCHW fp32.
@@ -546,6 +547,8 @@ class DenoiseEngine:
         x = self._run_block(net, "middle_block.", net.mid, x, None, emb_all, ctx_kvs, state)
         if taps is not None:
             taps.append(x)
+        if before_pose is not None:
+            before_pose()  # join point for a pose ControlNet running on another stream
         if pose is not None:
             x = add_pose(x)
         for i, blk in enumerate(net.out):

@@ -45,11 +45,31 @@ def launch_count() -> int:
 _ws_cache = {}
 
 
+_ws_tag = 0  # scratch buffers are per "lane": concurrent streams must not share split-K / GroupNorm scratch
+
+
+class workspace_lane:
+    """`with ops.workspace_lane(1):` — kernels issued inside use their own scratch buffers, so a second
+    CUDA stream can run another branch of the step concurrently (pipeline.GraphedDenoiser)."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        global _ws_tag
+        self.prev, _ws_tag = _ws_tag, self.tag
+
+    def __exit__(self, *a):
+        global _ws_tag
+        _ws_tag = self.prev
+
+
 def _workspace(key, numel, dtype, device):
-    t = _ws_cache.get((key, device))
+    k = (key, device, _ws_tag)
+    t = _ws_cache.get(k)
     if t is None or t.numel() < numel or t.dtype != dtype:
         t = torch.empty(max(numel, 1), dtype=dtype, device=device)
-        _ws_cache[(key, device)] = t
+        _ws_cache[k] = t
     return t
 
 

@@ -173,16 +173,33 @@ class GraphedDenoiser:
         self.bank_built = torch.zeros((bank_chunk, self.layout.numel), dtype=torch.float16, device=dev)
         self.g_step = self.g_bank = None
         self.replayed_launches = 0
+        import os
+        self.side = torch.cuda.Stream(device=dev) if os.environ.get("MDB_DUAL_STREAM", "1") != "0" else None
 
     # the two bodies, written against the static buffers only
     def _step_body(self):
+        """One DDIM step.  The pose ControlNet and the UNet's encoder half are independent (the pose
+        residuals enter at the middle block, cldm.py:93-104), and at one frame per GPU each of their
+        kernels fills only part of the 148 SMs, so the ControlNet runs on a second stream (forked and
+        joined with events, captured into the same graph) with its own scratch buffers."""
         eng, b = self.eng, self.batch
         t = self.t_cur.expand(b).contiguous()
         bank_kv = self.layout.views(self.bank_cur, self.tokens, 1)
-        pose = eng.controlnet(self.x, self.hint, t, self.ctx)
-        if 2 * b <= 16:
-            eps_c, eps_u = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, cfg_pair=True)
+        main = torch.cuda.current_stream()
+        if self.side is not None:
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side), ops.workspace_lane(1):
+                pose = eng.controlnet(self.x, self.hint, t, self.ctx)
+            join = lambda: main.wait_stream(self.side)
         else:
+            pose = eng.controlnet(self.x, self.hint, t, self.ctx)
+            join = None
+        if 2 * b <= 16:
+            eps_c, eps_u = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, cfg_pair=True,
+                                            before_pose=join)
+        else:
+            if join:
+                join()
             eps_c = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, uc=False)
             eps_u = eng.unet_forward(self.x, t, self.ctx, uc=True)
         ops.cfg_ddim_update(self.x, eps_c.contiguous(), eps_u.contiguous(), self.coef_cur, x_prev=self.x_prev,
