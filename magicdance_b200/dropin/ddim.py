@@ -1,0 +1,145 @@
+"""Drop-in for DDIMSampler_ReferenceOnly (model_lib/ControlNet/ldm/models/diffusion/ddim.py:346-730):
+same constructor, make_schedule / sample / ddim_sampling / p_sample_ddim signatures and return values,
+for the configuration the MagicPose scripts drive (test_tiktok.py:261-268): eps-prediction, DDIM,
+classifier-free guidance through the 'controlnet is more important' branch (ddim.py:598-605).
+
+Host code only: the step itself (pose ControlNet, paired conditional/unconditional UNet, fused
+CFG + DDIM update) runs on the sm_100a kernels via magicdance_b200.pipeline.DenoisePipeline, which also
+keeps the per-sequence caches (text K/V, per-timestep appearance bank, per-frame hint features) across
+the frames of a video — the reference recomputes all of them for every frame and step.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ..pipeline import DenoisePipeline, ddim_parameters, ddim_timesteps_uniform
+
+
+class DDIMSampler_ReferenceOnly(object):
+    def __init__(self, model, schedule="linear", **kwargs):
+        super().__init__()
+        self.model = model
+        self.ddpm_num_timesteps = model.num_timesteps
+        self.schedule = schedule
+
+    def register_buffer(self, name, attr):
+        setattr(self, name, attr)
+
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
+        """ddim.py:359-388 (uniform discretisation)."""
+        assert ddim_discretize == "uniform"
+        acp = self.model.alphas_cumprod.detach().cpu().numpy().astype(np.float32)
+        self.ddim_timesteps = ddim_timesteps_uniform(ddim_num_steps, self.ddpm_num_timesteps)
+        sig, a, a_prev = ddim_parameters(acp, self.ddim_timesteps, ddim_eta)
+        self.ddim_sigmas, self.ddim_alphas, self.ddim_alphas_prev = sig, a, a_prev
+        self.ddim_sqrt_one_minus_alphas = np.sqrt(1.0 - a)
+        self.ddim_eta = ddim_eta
+        self.alphas_cumprod = acp
+
+    def _pipeline(self, scale) -> DenoisePipeline:
+        """One pipeline (and its caches) per (steps, eta, scale), kept on the model so that successive
+        sample_log() calls for the frames of one video share the appearance bank and the text K/V."""
+        cache = self.model.__dict__.setdefault("_mdb_pipelines", {})
+        key = (len(self.ddim_timesteps), float(self.ddim_eta), float(scale))
+        eng = self.model.engine()
+        pipe = cache.get(key)
+        if pipe is None or pipe.engine is not eng:
+            cache.clear()
+            pipe = DenoisePipeline(eng, ddim_steps=key[0], scale=scale, eta=self.ddim_eta,
+                                   alphas_cumprod=self.alphas_cumprod)
+            cache[key] = pipe
+        return pipe
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None, img_callback=None,
+               quantize_x0=False, eta=0., mask=None, x0=None, temperature=1., noise_dropout=0., score_corrector=None,
+               corrector_kwargs=None, verbose=True, x_T=None, log_every_t=100, unconditional_guidance_scale=1.,
+               unconditional_conditioning=None, dynamic_threshold=None, ucg_schedule=None, inpaint=None, **kwargs):
+        """ddim.py:390-458"""
+        self.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=verbose)
+        C, H, W = shape
+        return self.ddim_sampling(conditioning, (batch_size, C, H, W), callback=callback, img_callback=img_callback,
+                                  quantize_denoised=quantize_x0, mask=mask, x0=x0, x_T=x_T, log_every_t=log_every_t,
+                                  temperature=temperature, noise_dropout=noise_dropout, score_corrector=score_corrector,
+                                  corrector_kwargs=corrector_kwargs,
+                                  unconditional_guidance_scale=unconditional_guidance_scale,
+                                  unconditional_conditioning=unconditional_conditioning,
+                                  dynamic_threshold=dynamic_threshold, ucg_schedule=ucg_schedule, inpaint=inpaint)
+
+    @torch.no_grad()
+    def ddim_sampling(self, cond, shape, x_T=None, ddim_use_original_steps=False, callback=None, timesteps=None,
+                      quantize_denoised=False, mask=None, x0=None, img_callback=None, log_every_t=100, temperature=1.,
+                      noise_dropout=0., score_corrector=None, corrector_kwargs=None, unconditional_guidance_scale=1.,
+                      unconditional_conditioning=None, dynamic_threshold=None, ucg_schedule=None, inpaint=None):
+        """ddim.py:460-516"""
+        assert not ddim_use_original_steps and timesteps is None and mask is None and ucg_schedule is None
+        device = self.model.betas.device
+        b = shape[0]
+        img = torch.randn(shape, device=device) if x_T is None else x_T.to(device)
+        intermediates = {"x_inter": [img], "pred_x0": [img]}
+        total = self.ddim_timesteps.shape[0]
+        for i, step in enumerate(np.flip(self.ddim_timesteps)):
+            index = total - i - 1
+            ts = torch.full((b,), int(step), device=device, dtype=torch.long)
+            img, pred_x0 = self.p_sample_ddim(img, cond, ts, index=index, quantize_denoised=quantize_denoised,
+                                              temperature=temperature, noise_dropout=noise_dropout,
+                                              score_corrector=score_corrector, corrector_kwargs=corrector_kwargs,
+                                              unconditional_guidance_scale=unconditional_guidance_scale,
+                                              unconditional_conditioning=unconditional_conditioning,
+                                              dynamic_threshold=dynamic_threshold, inpaint=inpaint)
+            if callback:
+                callback(i)
+            if img_callback:
+                img_callback(pred_x0, i)
+            if index % log_every_t == 0 or index == total - 1:
+                intermediates["x_inter"].append(img)
+                intermediates["pred_x0"].append(pred_x0)
+        return img, intermediates
+
+    @torch.no_grad()
+    def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
+                      temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
+                      unconditional_guidance_scale=1., unconditional_conditioning=None, dynamic_threshold=None,
+                      inpaint=None):
+        """ddim.py:518-645 for the branch MagicPose takes: c carries image_control (+wonoise), the
+        unconditional conditioning does not ('controlnet is more important', ddim.py:598-605), so
+        eps = eps_u + s (eps_c - eps_u) with eps_u = apply_model(x, t, c, None, uc=True)."""
+        if (inpaint is not None or use_original_steps or quantize_denoised or score_corrector is not None
+                or dynamic_threshold is not None or noise_dropout != 0.0 or temperature != 1.0):
+            raise NotImplementedError("option not used by the MagicPose inference scripts")
+        if not (isinstance(c, dict) and c.get("image_control") is not None):
+            raise NotImplementedError("p_sample_ddim needs cond['image_control'] (the reference image latent)")
+        if unconditional_conditioning is None or unconditional_guidance_scale == 1.0:
+            raise NotImplementedError("only the classifier-free-guidance path of the scripts is accelerated")
+        if unconditional_conditioning.get("image_control") is not None:
+            raise NotImplementedError("only control_mode='controlnet_important' (test_tiktok.py:237-240) is accelerated")
+        if c.get("overlap_sampling"):
+            raise NotImplementedError("overlap_sampling is off in every released script (test_tiktok.py:247)")
+        pipe = self._pipeline(unconditional_guidance_scale)
+        dev = pipe.device
+        x = x.to(device=dev, dtype=torch.float32)
+        ref = torch.cat(c["image_control"], 1)
+        ctx = torch.cat(c["c_crossattn"], 1)
+        pose_map = torch.cat(c["c_concat"], 1)
+        if c["wonoise"]:
+            # the clean reference latent feeds the appearance net (ddim.py:532-533): the bank depends on
+            # (reference, t) only.  One reference for the whole batch (the scripts repeat it per sample) is
+            # computed once and broadcast in-kernel; the result is cached per timestep for the next frames.
+            src = c["image_control"][0] if len(c["image_control"]) == 1 else ref
+            shared = src.shape[0] == 1 or bool((src[1:] == src[:1]).all())
+            if shared:
+                bank_kv = pipe.reference_bank(src, ctx, index, first_only=True)
+            else:
+                tt = pipe.t_dev[index].expand(ref.shape[0]).contiguous()
+                bank_kv = pipe.engine.project_bank(pipe.engine.appearance_write(ref, tt, ctx), ref.shape[0])
+        else:  # noised reference (ddim.py:535): depends on fresh noise, cannot be cached
+            ref_n = self.model.q_sample(ref, t.to(ref.device))
+            tt = pipe.t_dev[index].expand(ref.shape[0]).contiguous()
+            bank_kv = pipe.engine.project_bank(pipe.engine.appearance_write(ref_n, tt, ctx), ref.shape[0])
+        hint = pipe.hint(pose_map.to(dev), frame_key=(pose_map.data_ptr(), pose_map._version, tuple(pose_map.shape)))
+        noise = None
+        if float(self.ddim_sigmas[index]) != 0.0:
+            noise = torch.randn_like(x)
+        x_prev, pred_x0, _, _ = pipe.step(x, index, ctx.to(dev), hint, bank_kv, noise=noise)
+        return x_prev, pred_x0

@@ -285,6 +285,17 @@ class DenoiseEngine:
         self.pose = PackedNet(state_dict, POSE, self.cfg, "controlnet", self.device)
         self._ctx_cache = {}
 
+    @classmethod
+    def from_packed(cls, unet: "PackedNet", appearance: "PackedNet | None", pose: "PackedNet | None"):
+        """Engine over already-packed networks (the drop-in nn.Modules pack themselves lazily)."""
+        ops.ensure_device()
+        self = cls.__new__(cls)
+        first = unet or appearance or pose
+        self.cfg, self.device = first.cfg, first.device
+        self.unet, self.appearance, self.pose = unet, appearance, pose
+        self._ctx_cache = {}
+        return self
+
     # ---- small pieces -------------------------------------------------------------------------
     def time_bias(self, net: PackedNet, t: torch.Tensor):
         """timestep_embedding -> time_embed MLP -> all emb_layers of the net (util.py:189-209,

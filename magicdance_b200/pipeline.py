@@ -71,14 +71,20 @@ class DenoisePipeline:
         self.t_dev = torch.from_numpy(self.timesteps.astype(np.int64)).to(self.device)
 
     # ---- per-sequence / per-frame preparation --------------------------------------------------
-    def reference_bank(self, ref_latent, context, index):
-        """Bank K/V for ddim index `index` (appearance 'write' pass + projection), cached."""
+    def reference_bank(self, ref_latent, context, index, first_only=False):
+        """Bank K/V for ddim index `index` (appearance 'write' pass + projection), cached per
+        (reference tensor, index).  first_only: all rows of ref_latent are the same image; compute row 0."""
         key = (ref_latent.data_ptr(), ref_latent._version, int(index))
+        if self._bank_cache and next(iter(self._bank_cache))[:2] != key[:2]:
+            self._bank_cache.clear()  # a new reference image: drop the previous sequence's banks (2.3 GB)
+            self._bank_ref = None
+        self._bank_ref = ref_latent  # keep the tensor alive so its address cannot be recycled under the cache
         hit = self._bank_cache.get(key)
         if hit is None:
-            rb = ref_latent.shape[0]
+            src = ref_latent[:1].contiguous() if first_only else ref_latent
+            rb = src.shape[0]
             t = self.t_dev[index].expand(rb).contiguous()
-            bank = self.engine.appearance_write(ref_latent, t, context[:rb])
+            bank = self.engine.appearance_write(src, t, context[:rb])
             hit = self.engine.project_bank(bank, rb)
             self._bank_cache[key] = hit
         return hit

@@ -1,0 +1,1 @@
+"""Same dotted path as the reference (Boese0601/MagicDance) — see INTEGRATION.md."""

@@ -1,0 +1,76 @@
+"""The drop-in boundary: same dotted paths, constructor kwargs and state-dict keys as the
+reference; no CPU fallback."""
+import os
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+YAML = os.path.join(REPO, "model_lib", "ControlNet", "models", "cldm_v15_reference_only_pose.yaml")
+
+
+@pytest.fixture(scope="module")
+def model():
+    from model_lib.ControlNet.cldm.model import create_model
+    return create_model(YAML)
+
+
+def test_yaml_targets_resolve_to_dropin_classes(model):
+    import yaml
+    cfg = yaml.safe_load(open(YAML))["model"]
+    assert cfg["target"] == "model_lib.ControlNet.cldm.cldm.ControlLDMReferenceOnlyPose"
+    from model_lib.ControlNet.cldm import cldm
+    assert type(model) is cldm.ControlLDMReferenceOnlyPose
+    assert type(model.model.diffusion_model) is cldm.ControlledUnetModelAttnPose
+    assert type(model.appearance_control_model) is cldm.ControlNetReferenceOnly
+    assert type(model.pose_control_model) is cldm.ControlNet
+    # attributes the reference scripts set / read (test_tiktok.py:374-375,224; train_tiktok.py:798-822)
+    model.sd_locked, model.only_mid_control = True, False
+    assert model.channels == 4 and model.image_size == 64 and model.num_timesteps == 1000
+    for name in ("input_blocks", "middle_block", "output_blocks", "out"):
+        assert hasattr(model.model.diffusion_model, name)
+    for name in ("input_blocks", "middle_block", "input_hint_block", "middle_block_out", "zero_convs"):
+        assert hasattr(model.pose_control_model, name)
+
+
+def test_state_dict_keys_and_shapes_equal_the_reference(model):
+    from magicdance_b200 import synth
+    manifest = synth.load_manifest()  # recorded from the unmodified reference (oracle/make_golden.py)
+    ours = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert ours == manifest
+
+
+def test_schedule_buffers_match_reference(model):
+    import numpy as np
+    from tests import golden_util as G
+    g = G.load("full64")
+    np.testing.assert_allclose(model.alphas_cumprod.numpy(), g["full64/alphas_cumprod"], rtol=2e-6)
+    from model_lib.ControlNet.ldm.models.diffusion.ddim import DDIMSampler_ReferenceOnly
+    s = DDIMSampler_ReferenceOnly(model)
+    s.make_schedule(50, ddim_eta=0.0, verbose=False)
+    assert list(s.ddim_timesteps) == list(g["full64/ddim_timesteps"])
+    np.testing.assert_allclose(s.ddim_alphas, g["full64/ddim_alphas"], rtol=1e-6)
+
+
+def test_cpu_model_fails_loudly(model):
+    x = torch.zeros(1, 4, 64, 64)
+    cond = {"c_concat": [torch.zeros(1, 3, 512, 512)], "c_crossattn": [torch.zeros(1, 77, 768)]}
+    with pytest.raises(RuntimeError, match="no CPU|CUDA"):
+        model.apply_model(x, torch.zeros(1, dtype=torch.long), cond, x)
+
+
+def test_training_entry_refuses_to_fake_gradients(model):
+    x = torch.zeros(1, 4, 64, 64)
+    cond = {"c_concat": [torch.zeros(1, 3, 512, 512)], "c_crossattn": [torch.zeros(1, 77, 768)],
+            "image_control": [x], "wonoise": True}
+    with pytest.raises(NotImplementedError, match="forward"):
+        model(x, cond)
+
+
+def test_strict_load_of_a_reference_checkpoint_layout(model):
+    from magicdance_b200 import synth
+    manifest = synth.load_manifest()
+    sd = {k: torch.zeros(v) for k, v in manifest.items()}  # a checkpoint with exactly the reference's keys
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    assert model.model.diffusion_model._packed is None  # packed fp16 copies are invalidated by a load

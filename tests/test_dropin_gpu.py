@@ -1,0 +1,98 @@
+"""The reference-facing API on the GPU: create_model(yaml) -> load_state_dict -> apply_model /
+DDIMSampler_ReferenceOnly.p_sample_ddim / the three networks' own forward()s, against the golden
+vectors of the unmodified reference."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+YAML = os.path.join(REPO, "model_lib", "ControlNet", "models", "cldm_v15_reference_only_pose.yaml")
+TOL = 5e-3
+
+
+@pytest.fixture(scope="module")
+def model():
+    from magicdance_b200 import synth
+    from model_lib.ControlNet.cldm.model import create_model
+    torch.set_grad_enabled(False)
+    m = create_model(YAML)
+    missing, unexpected = m.load_state_dict(synth.synth_state_dict(seed=0), strict=False)
+    assert not unexpected and set(missing) <= set(synth.SCHEDULE_KEYS)
+    return m.cuda().eval()
+
+
+def test_apply_model_matches_reference_golden(model):
+    from tests import golden_util as G
+    g = G.load("small32")
+    inp = {k: v.cuda() for k, v in G.small32_inputs().items()}
+    cond = {"c_concat": [inp["pose"]], "c_crossattn": [inp["context"]]}
+    eps_c = model.apply_model(inp["x"], inp["t"], cond, inp["ref"])
+    eps_u = model.apply_model(inp["x"], inp["t"], cond, None, uc=True)
+    assert eps_c.dtype == torch.float32 and eps_c.shape == inp["x"].shape
+    assert G.rel_l2(eps_c, torch.from_numpy(g["small32/eps_c"])) <= TOL
+    assert G.rel_l2(eps_u, torch.from_numpy(g["small32/eps_u"])) <= TOL
+
+
+def test_network_forwards_keep_the_reference_interfaces(model):
+    """ControlNetReferenceOnly fills the bank list, ControlNet returns 13 NCHW residuals, and the UNet
+    consumes both (cldm.py:1108-1115) — the reference's own glue, run through the sub-module API."""
+    from tests import golden_util as G
+    g = G.load("small32")
+    inp = {k: v.cuda() for k, v in G.small32_inputs().items()}
+    bank = []
+    out = model.appearance_control_model(x=inp["ref"], hint=None, timesteps=inp["t"], context=inp["context"],
+                                         attention_bank=bank, attention_mode="write", uc=False)
+    assert out == [] and len(bank) == 16 and isinstance(bank[0], list)
+    G.check_summary(g, "small32/bank0", bank[0][0], TOL)
+    G.check_summary(g, "small32/bank15", bank[15][0], TOL)
+    pose = model.pose_control_model(x=inp["x"], hint=inp["pose"], timesteps=inp["t"], context=inp["context"])
+    assert len(pose) == 13
+    for i in (0, 6, 12):
+        G.check_summary(g, f"small32/pose{i}", pose[i], TOL)
+    eps = model.model.diffusion_model(x=inp["x"], timesteps=inp["t"], context=inp["context"], control=bank,
+                                      pose_control=pose, only_mid_control=False, attention_mode="read", uc=False)
+    assert pose == []  # consumed like the reference's .pop()
+    assert G.rel_l2(eps, torch.from_numpy(g["small32/eps_c"])) <= TOL
+
+
+def test_sampler_step_matches_reference_p_sample_ddim(model):
+    from tests import golden_util as G
+    from model_lib.ControlNet.ldm.models.diffusion.ddim import DDIMSampler_ReferenceOnly
+    g = G.load("full64")
+    inp = {k: v.cuda() for k, v in G.full64_inputs().items()}
+    sampler = DDIMSampler_ReferenceOnly(model)
+    sampler.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+    gen = torch.Generator().manual_seed(123)
+    uc_ctx = torch.randn(1, 77, 768, generator=gen).cuda()  # must be ignored (ddim.py:599-604)
+    c = {"c_concat": [inp["pose"]], "c_crossattn": [inp["context"]], "image_control": [inp["ref"]], "wonoise": True,
+         "overlap_sampling": False}
+    uc = {"c_concat": [inp["pose"]], "c_crossattn": [uc_ctx], "wonoise": True, "overlap_sampling": False}
+    ts = torch.full((1,), 981, dtype=torch.long, device="cuda")
+    x_prev, pred_x0 = sampler.p_sample_ddim(inp["x"], c, ts, index=49, unconditional_guidance_scale=7.0,
+                                            unconditional_conditioning=uc)
+    assert G.rel_l2(x_prev, torch.from_numpy(g["full64/x_prev"])) <= 2e-2
+    assert G.rel_l2(pred_x0, torch.from_numpy(g["full64/pred_x0"])) <= 2e-2
+
+
+def test_sample_log_runs_the_chain_and_reuses_the_bank(model):
+    """sample_log (ddpm.py:2401-2413) for two 'frames' of one reference at 256x256, 4 DDIM steps: the second
+    frame must hit the per-timestep bank cache (no appearance pass) and stay finite."""
+    from magicdance_b200 import ops, synth
+    inp = {k: v.cuda() for k, v in synth.synth_inputs(1, 32, seed=5, shared_reference=True).items()}
+    model.image_size = 32
+    c = {"c_concat": [inp["pose"]], "c_crossattn": [inp["context"]], "image_control": [inp["ref"]], "wonoise": True,
+         "overlap_sampling": False}
+    uc = {"c_concat": [inp["pose"]], "c_crossattn": [inp["context"]], "wonoise": True, "overlap_sampling": False}
+    n0 = ops.launch_count()
+    s1, inter = model.sample_log(cond=c, batch_size=1, ddim=True, ddim_steps=4, eta=0.0,
+                                 unconditional_guidance_scale=7.0, unconditional_conditioning=uc, x_T=inp["x"])
+    n1 = ops.launch_count()
+    s2, _ = model.sample_log(cond=c, batch_size=1, ddim=True, ddim_steps=4, eta=0.0,
+                             unconditional_guidance_scale=7.0, unconditional_conditioning=uc, x_T=inp["x"])
+    n2 = ops.launch_count()
+    model.image_size = 64
+    assert s1.shape == (1, 4, 32, 32) and torch.isfinite(s1).all() and "pred_x0" in inter
+    assert torch.equal(s1, s2) or float((s1 - s2).abs().max()) < 1e-3
+    assert (n2 - n1) < 0.8 * (n1 - n0)  # second frame skipped the 4 appearance passes + text K/V
