@@ -308,7 +308,7 @@ class DenoiseEngine:
     def context_kv(self, net: PackedNet, ctx16: torch.Tensor, key):
         """Text keys/values of every attn2 (CrossAttention.to_k/to_v on the CLIP context,
         attention.py:172-174); depends only on the context -> cached per (net, context)."""
-        ck = (net.prefix, key)
+        ck = (id(net), key)  # per PackedNet object: drop-in modules all have an empty key prefix
         hit = self._ctx_cache.get(ck)
         if hit is not None:
             return hit

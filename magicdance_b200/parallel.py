@@ -57,22 +57,32 @@ class BankLayout:
         return res
 
 
+def bank_storage(slots: int, layout: BankLayout, device, world: int = 1):
+    """(local [slots, numel], gathered [world, slots, numel] or None) fp16 buffers for build_and_gather_bank"""
+    local = torch.zeros((slots, layout.numel), dtype=torch.float16, device=device)
+    gathered = torch.empty((world, slots, layout.numel), dtype=torch.float16, device=device) if world > 1 else None
+    return local, gathered
+
+
 def build_and_gather_bank(indices: Sequence[int], layout: BankLayout,
                           build_fn: Callable[[List[int], torch.Tensor], None], device, world: int = 1, rank: int = 0,
-                          group=None, chunk: int = 10) -> Dict[int, torch.Tensor]:
+                          group=None, chunk: int = 10, storage=None) -> Dict[int, torch.Tensor]:
     """Each rank calls build_fn(ddim_indices_chunk, slots[len(chunk), numel]) for its share of `indices`
     (build_fn fills the flat fp16 slots in place; chunks of up to `chunk` timesteps are built as ONE
     batched appearance pass), then ONE all_gather_into_tensor exchanges all slots.  Returns
     ddim index -> flat buffer (a view into the gathered storage)."""
     mine = shard_timesteps(indices, world, rank)
     slots = (len(indices) + world - 1) // world
-    local = torch.zeros((slots, layout.numel), dtype=torch.float16, device=device)
+    if storage is not None:  # (local, gathered) preallocated by bank_storage(): keeps cudaMalloc out of timed regions
+        local, gathered = storage[0][:slots], (storage[1][:, :slots] if storage[1] is not None else None)
+        assert local.is_contiguous() or slots == storage[0].shape[0]
+    else:
+        local, gathered = bank_storage(slots, layout, device, world)
     for s0 in range(0, len(mine), chunk):
         part = mine[s0:s0 + chunk]
         build_fn(part, local[s0:s0 + len(part)])
     if world == 1:
         return {ix: local[s] for s, ix in enumerate(mine)}
-    gathered = torch.empty((world, slots, layout.numel), dtype=torch.float16, device=device)
     dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=group)
     table = owner_slot(indices, world)
     return {ix: gathered[r, s] for ix, (r, s) in table.items()}
