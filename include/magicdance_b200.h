@@ -112,10 +112,12 @@ int mdb_attention_f16(const mdb_attn_desc* desc, mdb_stream_t stream);
  * ResBlock.in_layers/out_layers and UNet.out (openaimodel.py:222-226,246-248,744-748), and
  * Normalize (attention.py:89-90, eps 1e-6) in SpatialTransformer.
  *   x1 [B][hw][c1], x2 [B][hw][c2] (x2 NULL => c2 = 0), y [B][hw][c1+c2];  stats: fp32 [B][32][2]
+ *   scratch; stats_prezeroed != 0 promises it is already zero (callers that hand every call its own slot
+ *   of a ring they clear once per network pass save one memset node per GroupNorm).
  * ---------------------------------------------------------------------------------------------- */
 int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* gamma, const float* beta,
                       void* y, float* stats_ws, int32_t batch, int32_t hw, float eps, int32_t silu,
-                      mdb_stream_t stream);
+                      int32_t stats_prezeroed, mdb_stream_t stream);
 
 /* LayerNorm over the last dim (eps 1e-5), fp16 [rows][c] -> fp16; replaces nn.LayerNorm norm1/2/3 of
  * BasicTransformerBlock (attention.py:270-272). */

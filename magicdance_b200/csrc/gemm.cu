@@ -15,6 +15,8 @@
 //                               per-batch bias (timestep embedding) / residual / GEGLU, store fp16.
 // Two CTAs fit per SM (3 stages, <=108 KB smem, <=256 TMEM columns each) so one CTA's epilogue
 // overlaps the other's main loop.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mdb {
@@ -43,7 +45,7 @@ struct GemmKParams {
   int conv;            // conv mode
   int chunks_per_tap;  // c / 64
   int w, hw;           // conv geometry
-  int y_box;           // rows of the image covered by one M tile (hw >= 128) or h (hw < 128)
+  int cluster_reduce;  // split-K partners form a cluster (1,1,splits) and reduce through distributed smem
 };
 
 // STAGES = 3: <=108 KB, two CTAs per SM (large grids: the co-resident CTA hides the TMA round trip).
@@ -128,6 +130,8 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
   const int kc_end = min(p.k_chunks, kc_begin + p.chunks_per_split);
   const int n_iter = kc_end - kc_begin;
   constexpr uint32_t kTmemCols = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
+  constexpr int kRedLd = BN + 4;  // fp32 row pitch of the split-K partial tile parked in shared memory
+  static_assert(kBM * kRedLd * 4 <= kStages * S::kStageBytes, "partial tile must fit in the operand ring");
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -226,9 +230,16 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         const int ncols = min(min(32, BN - ch * 32), p.n - col0);
-        if (p.splits > 1) {
-          // split-K: this split's fp32 partial goes to its own workspace slab (plain vector stores);
-          // splitk_finalize_kernel sums the slabs in a fixed order (deterministic, no atomics).
+        if (p.cluster_reduce) {
+          // split-K inside a cluster: park this CTA's fp32 partial tile in its own shared memory (the
+          // operand ring is idle by now); the cluster reduces it through DSMEM below.
+          float* rp = reinterpret_cast<float*>(smem) + (g * 32 + lane) * kRedLd + ch * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (j < ncols) *reinterpret_cast<float4*>(rp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else if (p.splits > 1) {
+          // split-K through global memory: this split's fp32 partial goes to its own workspace slab
+          // (plain vector stores); splitk_finalize_kernel sums the slabs in a fixed order.
           if (row_ok) {
             float* wp = p.ws + (static_cast<long long>(split) * p.m + row) * p.n + col0;
 #pragma unroll
@@ -283,6 +294,69 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
           }
         }
       }
+    }
+  }
+
+  if constexpr (!GEGLU) {
+    if (p.cluster_reduce) {
+      // ---- split-K reduction across the cluster through distributed shared memory ----
+      // cluster = the `splits` CTAs of this output tile.  CTA r owns rows [r*R, (r+1)*R) of the tile: it
+      // sums that slice over all partners' parked partials (ld.shared::cluster), applies the epilogue
+      // and stores fp16.  No global workspace, no second kernel.
+      cluster_sync_all();
+      const uint32_t crank = cluster_ctarank();
+      const int S_ = p.splits;
+      const int R = kBM / S_;
+      const int groups = BN / 8;
+      const uint32_t red_base = smem_u32(smem);
+      for (int item = threadIdx.x; item < R * groups; item += kGemmThreads) {
+        const int rl = item / groups, cgp = item - rl * groups;
+        const int rt = static_cast<int>(crank) * R + rl;  // row inside the tile
+        const long long row = static_cast<long long>(m0) + rt;
+        const int col0 = n0 + cgp * 8;
+        if (row >= p.m || col0 >= p.n) continue;
+        const uint32_t off = red_base + static_cast<uint32_t>((rt * kRedLd + cgp * 8) * 4);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+        for (int pr = 0; pr < S_; ++pr) {
+          const uint32_t ra = dsmem_map(off, static_cast<uint32_t>(pr));
+          const float4 a = dsmem_ld_f4(ra), b = dsmem_ld_f4(ra + 16);
+          o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+          o[4] += b.x; o[5] += b.y; o[6] += b.z; o[7] += b.w;
+        }
+        const int ncols = min(8, p.n - col0);
+        const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
+        if (p.bias != nullptr) {
+          const float* bp = p.bias + brow * p.bias_batch_stride + col0;
+          for (int e = 0; e < ncols; ++e) o[e] += bp[e];
+        }
+        if (ncols == 8) {
+          if (p.residual != nullptr) {
+            const uint4 r4 = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(h2[e]);
+              o[2 * e] += f.x;
+              o[2 * e + 1] += f.y;
+            }
+          }
+          uint4 o4;
+          o4.x = pack_half2(o[0], o[1]);
+          o4.y = pack_half2(o[2], o[3]);
+          o4.z = pack_half2(o[4], o[5]);
+          o4.w = pack_half2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(p.d + row * p.ldd + col0) = o4;
+        } else {
+          for (int e = 0; e < ncols; ++e) {
+            float x = o[e];
+            if (p.residual != nullptr) x += __half2float(p.residual[row * p.ldr + col0 + e]);
+            p.d[row * p.ldd + col0 + e] = __float2half_rn(x);
+          }
+        }
+      }
+      cluster_sync_all();  // nobody leaves while a partner may still read its shared memory
     }
   }
 
@@ -395,6 +469,7 @@ void count_launch(int n = 1);
 
 template <int BN, bool GEGLU, int STAGES>
 static int launch_gemm(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
+  const unsigned cluster_z = kp.cluster_reduce ? static_cast<unsigned>(kp.splits) : 1u;
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, GEGLU, STAGES>;
   if (!attr_set) {
@@ -402,7 +477,7 @@ static int launch_gemm(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, STAGES>::kTotal));
     attr_set = true;
   }
-  MDB_CHECK_CUDA(launch_pdl(kern, grid, dim3(kGemmThreads), GemmSmem<BN, STAGES>::kTotal, st, kp));
+  MDB_CHECK_CUDA(launch_pdl_cluster(kern, grid, dim3(kGemmThreads), GemmSmem<BN, STAGES>::kTotal, st, cluster_z, kp));
   count_launch();
   return MDB_OK;
 }
@@ -510,7 +585,11 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   splits = (kp.k_chunks + kp.chunks_per_split - 1) / kp.chunks_per_split;  // no empty splits
   kp.splits = splits;
   kp.ws = g->splitk_ws;
-  if (splits > 1) {
+  // 2, 4 or 8 splits: the partners form a thread-block cluster and reduce through DSMEM (one kernel);
+  // other counts go through the global fp32 workspace + finalize kernel.
+  static const bool cluster_ok = [] { const char* e = getenv("MDB_CLUSTER_SPLITK"); return !(e && e[0] == '0'); }();
+  kp.cluster_reduce = (cluster_ok && !geglu && (splits == 2 || splits == 4 || splits == 8)) ? 1 : 0;
+  if (splits > 1 && !kp.cluster_reduce) {
     MDB_REQUIRE(g->splitk_ws != nullptr, "mdb_gemm_f16: splits > 1 needs splitk_ws");
   }
 
@@ -521,7 +600,7 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   else if (bn == 80) rc = deep ? launch_gemm<80, false, 8>(kp, grid, st) : launch_gemm<80, false, 3>(kp, grid, st);
   else rc = deep ? launch_gemm<128, false, 6>(kp, grid, st) : launch_gemm<128, false, 3>(kp, grid, st);
   if (rc) return rc;
-  if (splits > 1) {
+  if (splits > 1 && !kp.cluster_reduce) {
     const long long total = ((long long)g->m * g->n + 3) / 4;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;

@@ -76,22 +76,37 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __h
   }
 }
 
+// apply: every CTA first turns the 32 group statistics of its batch element into per-channel
+// (scale, shift) pairs in shared memory — y = x * a_c + b_c with a_c = rstd_g * gamma_c and
+// b_c = beta_c - mean_g * a_c — and then streams its rows with one FMA (+ SiLU) per element.
 __global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ stats, __half* __restrict__ y, int batch, int hw, float eps,
-                                int silu) {
+                                const float* __restrict__ stats, __half* __restrict__ y, int hw, int rows_per_cta,
+                                float eps, int silu) {
+  extern __shared__ float s_ab[];  // [2][c]
   pdl_launch_dependents();
-  pdl_wait();
   const int c = c1 + c2;
   const int cg = c / 32;
   const int vecs = c / 8;
-  const long long total = static_cast<long long>(batch) * hw * vecs;
+  const int b = blockIdx.y;
   const float inv_n = 1.0f / (static_cast<float>(cg) * hw);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = i / vecs;
-    const int v = static_cast<int>(i - row * vecs);
-    const int b = static_cast<int>(row / hw);
+  pdl_wait();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const int g = ch / cg;
+    const float mean = stats[(b * 32 + g) * 2] * inv_n;
+    const float var = fmaxf(stats[(b * 32 + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+    const float a = rsqrtf(var + eps) * gamma[ch];
+    s_ab[ch] = a;
+    s_ab[c + ch] = beta[ch] - mean * a;
+  }
+  __syncthreads();
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int rows = min(rows_per_cta, hw - row0);
+  const int total = rows * vecs;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int r = i / vecs;
+    const int v = i - r * vecs;
+    const long long row = static_cast<long long>(b) * hw + row0 + r;
     uint4 u = *gn_src(x1, c1, x2, c2, row, v * 8);
     const __half2* h2 = reinterpret_cast<const __half2*>(&u);
     float f[8];
@@ -100,16 +115,15 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __h
       float2 t = __half22float2(h2[e]);
       f[2 * e] = t.x; f[2 * e + 1] = t.y;
     }
+    const float4 a0 = *reinterpret_cast<const float4*>(&s_ab[v * 8]);
+    const float4 a1 = *reinterpret_cast<const float4*>(&s_ab[v * 8 + 4]);
+    const float4 b0 = *reinterpret_cast<const float4*>(&s_ab[c + v * 8]);
+    const float4 b1 = *reinterpret_cast<const float4*>(&s_ab[c + v * 8 + 4]);
+    f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
+    f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
+    if (silu) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int ch = v * 8 + e;
-      const int g = ch / cg;
-      const float mean = stats[(b * 32 + g) * 2] * inv_n;
-      const float var = fmaxf(stats[(b * 32 + g) * 2 + 1] * inv_n - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + eps);
-      float o = (f[e] - mean) * rstd * gamma[ch] + beta[ch];
-      if (silu) o = silu_f(o);
-      f[e] = o;
+      for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
     }
     uint4 o4;
     o4.x = pack_half2(f[0], f[1]); o4.y = pack_half2(f[2], f[3]);
@@ -164,7 +178,7 @@ using namespace mdb;
 
 extern "C" int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* gamma,
                                  const float* beta, void* y, float* stats_ws, int32_t batch, int32_t hw, float eps,
-                                 int32_t silu, mdb_stream_t stream) {
+                                 int32_t silu, int32_t stats_prezeroed, mdb_stream_t stream) {
   const int c = c1 + (x2 ? c2 : 0);
   if (!x2) c2 = 0;
   MDB_REQUIRE(x1 && y && gamma && beta && stats_ws, "mdb_groupnorm_f16: null pointer");
@@ -172,7 +186,7 @@ extern "C" int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int
               "mdb_groupnorm_f16: channels must be multiples of 8, c %% 32 == 0 and c/32 >= 8 (c1=%d c2=%d)", c1, c2);
   MDB_REQUIRE(c / 8 <= 512, "mdb_groupnorm_f16: too many channels (%d)", c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  MDB_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * batch * 64, st));
+  if (!stats_prezeroed) MDB_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * batch * 64, st));
   const int vecs = c / 8;
   int threads = ((512 / vecs) * vecs);  // whole number of row phases
   if (threads < vecs) threads = vecs;
@@ -186,12 +200,17 @@ extern "C" int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int
   MDB_CHECK_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), 64 * sizeof(float), st,
                             static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2, stats_ws, hw,
                             rows_per_cta));
-  const long long total = static_cast<long long>(batch) * hw * vecs;
-  int blocks = static_cast<int>((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  MDB_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3(blocks), dim3(256), 0, st, static_cast<const __half*>(x1), c1,
-                            static_cast<const __half*>(x2), c2, gamma, beta, static_cast<const float*>(stats_ws),
-                            static_cast<__half*>(y), batch, hw, eps, silu));
+  {
+    // ~2-4 CTAs per SM; each CTA pays a c-element (scale, shift) setup, so rows per CTA grow with c
+    int rows_apply = (batch * hw + 443) / 444;
+    const int min_rows = (c >= 1280) ? 8 : 4;
+    if (rows_apply < min_rows) rows_apply = min_rows;
+    if (rows_apply > 64) rows_apply = 64;
+    dim3 agrid((hw + rows_apply - 1) / rows_apply, batch);
+    MDB_CHECK_CUDA(launch_pdl(gn_apply_kernel, agrid, dim3(256), 2 * c * sizeof(float), st,
+                              static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2, gamma, beta,
+                              static_cast<const float*>(stats_ws), static_cast<__half*>(y), hw, rows_apply, eps, silu));
+  }
   count_launch(2);
   return MDB_OK;
 }

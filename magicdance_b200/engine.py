@@ -270,7 +270,12 @@ def _auto_splits(m, n, k):
     chunks = k // 64
     if tiles >= 100 or chunks < 8:
         return 1
-    return max(1, min(16, 148 // tiles, chunks // 4))
+    want = max(1, min(16, 148 // tiles, chunks // 4))
+    # powers of two up to 8 run as a thread-block cluster with an in-kernel DSMEM reduction
+    for s_ in (8, 4, 2):
+        if want >= s_:
+            return s_
+    return 1
 
 
 class DenoiseEngine:
@@ -425,6 +430,7 @@ class DenoiseEngine:
         norm1(x) token matrices [B*N_l, C_l] fp16 (attention.py:287-298).  Layers after the last
         norm1 (dead compute in the reference) are skipped."""
         net = self.appearance
+        ops.gn_ring_reset(self.device)
         x, ctx16, key = self._prep(ref_latent, context)
         ctx_kvs = self.context_kv(net, ctx16, key)
         emb_all = self.time_bias(net, t)
@@ -496,6 +502,7 @@ class DenoiseEngine:
     def controlnet(self, x_noisy, hint_feat, t, context):
         """ControlNet.forward (cldm.py:736-757) -> 13 residuals as fp16 [B*H*W, C] matrices."""
         net = self.pose
+        ops.gn_ring_reset(self.device)
         x, ctx16, key = self._prep(x_noisy, context)
         ctx_kvs = self.context_kv(net, ctx16, key)
         emb_all = self.time_bias(net, t)
@@ -522,6 +529,7 @@ class DenoiseEngine:
         layer streams its weights once and sees twice the rows; samples [0,B) read the bank and take the
         pose residuals, samples [B,2B) do neither.  Returns (eps_cond, eps_uncond)."""
         net = self.unet
+        ops.gn_ring_reset(self.device)
         x, ctx16, key = self._prep(x_noisy, context)
         b = x.b
         if cfg_pair:

@@ -264,6 +264,10 @@ ALL_CASES = [
     (case_gemm, (320, 4096, 320)),
     (case_gemm, (64, 1280, 2560, True, True, 8)),
     (case_gemm, (256, 1280, 11520, True, False, 12)),
+    (case_gemm, (256, 1280, 1280, True, True, 4)),
+    (case_gemm, (1024, 640, 640, True, True, 2)),
+    (case_gemm, (2048, 320, 1280, True, True, 2)),
+    (case_gemm, (100, 1280, 2560, True, True, 8)),
     (case_gemm_batch_bias, (2, 1024, 640, 320)),
     (case_gemm_dual, (1024, 640, 640, 320)),
     (case_gemm_strided_out, (320, 77, 768)),
@@ -275,6 +279,8 @@ ALL_CASES = [
     (case_conv, (3, 8, 8, 1280, 1280, True, True)),
     (case_conv, (2, 4, 4, 1280, 1280)),
     (case_conv, (1, 8, 8, 2560, 1280, True, False, 8)),
+    (case_conv, (2, 16, 16, 1280, 1280, True, True, 4)),
+    (case_conv, (2, 32, 32, 640, 640, True, True, 2)),
     (case_conv_direct, (1, 64, 64, 4, 320, 1, False, True)),
     (case_conv_direct, (2, 64, 64, 320, 4, 1, False)),
     (case_conv_direct, (1, 256, 256, 3, 16, 1, True)),
