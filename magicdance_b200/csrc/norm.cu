@@ -203,7 +203,7 @@ extern "C" int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int
   {
     // ~2-4 CTAs per SM; each CTA pays a c-element (scale, shift) setup, so rows per CTA grow with c
     int rows_apply = (batch * hw + 443) / 444;
-    const int min_rows = (c >= 1280) ? 8 : 4;
+    const int min_rows = (c >= 1280) ? 2 : 4;  // few rows per CTA when hw is small: parallelism beats setup reuse
     if (rows_apply < min_rows) rows_apply = min_rows;
     if (rows_apply > 64) rows_apply = 64;
     dim3 agrid((hw + rows_apply - 1) / rows_apply, batch);
