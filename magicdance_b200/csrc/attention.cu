@@ -15,6 +15,8 @@
 //              (fp16, smem, 128B-swizzled K-major) O += P V (M=128, N=DV) into TMEM.
 //   warps 2-5  softmax: thread == query row.  tcgen05.ld S, running max / sum in the log2 domain,
 //              lazy O rescale (only when the max grows by > 2^8), write P, final O / l -> fp16.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mdb {
@@ -296,7 +298,323 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 80) ? 2 : 1) attn_tc_kerne
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2: two Q tiles (256 queries) per CTA, ping-pong.  One K/V tile feeds both Q tiles; each Q tile has
+// its own S and O accumulators in TMEM, its own P buffer and its own softmax warpgroup (warps 2-5 for
+// tile A, 6-9 for tile B).  The MMA thread interleaves the two tiles — PV_A(j), QK_A(j+1), PV_B(j),
+// QK_B(j+1) — so while warpgroup A runs its softmax the tensor core works for B and vice versa, and
+// the MUFU (exp2) pipe, which bounds d=40 attention, always has a warpgroup feeding it.
+// TMEM columns: S_A [0,BKV) S_B [BKV,2BKV) O_A [2BKV,2BKV+DV) O_B [2BKV+DV, 2BKV+2DV)  (<= 512).
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttn2Threads = 320;
+
+template <int D, int BKV>
+struct Attn2Cfg {
+  using C1 = AttnCfg<D, BKV>;
+  static constexpr int kDV = C1::kDV;
+  static constexpr int kQBytes = C1::kQBytes;   // per Q tile
+  static constexpr int kKBytes = C1::kKBytes;
+  static constexpr int kVBytes = C1::kVBytes;
+  static constexpr int kPBytes = C1::kPBytes;   // per Q tile
+  static constexpr int kStages = 2;
+  static constexpr int kSmem = 2 * kQBytes + kStages * (kKBytes + kVBytes) + 2 * kPBytes + 1024;
+  static constexpr int kCols = 2 * BKV + 2 * kDV;
+  static constexpr int kTmemCols = kCols <= 256 ? 256 : 512;
+  static_assert(kCols <= 512, "TMEM budget");
+};
+
+template <int D, int BKV>
+__global__ void __launch_bounds__(kAttn2Threads, 1) attn2_tc_kernel(const __grid_constant__ AttnKParams p) {
+  using C = Attn2Cfg<D, BKV>;
+  using C1 = AttnCfg<D, BKV>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t q_bar;
+  __shared__ __align__(8) uint64_t s_full[2], p_full[2], o_done[2];
+  __shared__ __align__(8) uint64_t kv_full[C::kStages], kv_empty[C::kStages];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2][kQBytes]
+  uint8_t* sKV = sQ + 2 * C::kQBytes;                   // [stages][K | V]
+  uint8_t* sP = sKV + C::kStages * (C::kKBytes + C::kVBytes);  // [2][kPBytes]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * kBQ);
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const bool tile_b_active = q0 + kBQ < p.nq;  // CTA-uniform
+
+  const int t0 = (p.n0 + BKV - 1) / BKV;
+  const int t1 = (b < p.bank_batches && p.n1 > 0) ? (p.n1 + BKV - 1) / BKV : 0;
+  const int n_tiles = t0 + t1;
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK0);
+    tma_prefetch_desc(&p.tmV0);
+    mbar_init(&q_bar, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&o_done[t], 1);
+    }
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, C::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&q_bar, 2 * C::kQBytes);
+      for (int t = 0; t < 2; ++t)
+        for (int dc = 0; dc < C1::kDkChunks; ++dc)
+          tma_load_3d(sQ + t * C::kQBytes + dc * (kBQ * 128), &p.tmQ, &q_bar, dc * 64, head, b * p.nq + q0 + t * kBQ);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % C::kStages;
+        const uint32_t ph = (j / C::kStages) & 1;
+        const bool src1 = j >= t0;
+        const int key0 = (src1 ? (j - t0) : j) * BKV;
+        const CUtensorMap* tk = src1 ? &p.tmK1 : &p.tmK0;
+        const CUtensorMap* tv = src1 ? &p.tmV1 : &p.tmV0;
+        const int nsrc = src1 ? p.n1 : p.n0;
+        const int kvb = src1 ? (p.kv1_batches > 1 ? b : 0) : (p.kv0_batches > 1 ? b : 0);
+        const int ldvb = src1 ? p.ldv1_batch : p.ldv0_batch;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_expect_tx(&kv_full[s], C::kKBytes + C::kVBytes);
+        uint8_t* sk = sKV + s * (C::kKBytes + C::kVBytes);
+        uint8_t* sv = sk + C::kKBytes;
+        for (int dc = 0; dc < C1::kDkChunks; ++dc)
+          tma_load_3d(sk + dc * (BKV * 128), tk, &kv_full[s], dc * 64, head, kvb * nsrc + key0);
+        for (int kc = 0; kc < C1::kKvChunks; ++kc)
+          tma_load_2d(sv + kc * (C::kDV * 128), tv, &kv_full[s], kvb * ldvb + key0 + kc * 64, head * D);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(kBQ, BKV);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(kBQ, C::kDV);
+      const int n_act = tile_b_active ? 2 : 1;
+      auto issue_qk = [&](int t, int stage) {
+        const uint32_t q_addr = smem_u32(sQ + t * C::kQBytes);
+        const uint32_t k_addr = smem_u32(sKV + stage * (C::kKBytes + C::kVBytes));
+#pragma unroll
+        for (int ks = 0; ks < C1::kKSteps; ++ks) {
+          const int dc = ks >> 2, kk = ks & 3;
+          const uint64_t da = umma_desc_k_sw128(q_addr + dc * (kBQ * 128)) + 2 * kk;
+          const uint64_t db = umma_desc_k_sw128(k_addr + dc * (BKV * 128)) + 2 * kk;
+          umma_f16_ss(tmem_base + t * BKV, da, db, idesc_qk, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[t]);
+      };
+      mbar_wait(&q_bar, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after_sync();
+      for (int t = 0; t < n_act; ++t) issue_qk(t, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % C::kStages;
+        const uint32_t v_addr = smem_u32(sKV + s * (C::kKBytes + C::kVBytes)) + C::kKBytes;
+        const bool more = j + 1 < n_tiles;
+        const int s_next = (j + 1) % C::kStages;
+        for (int t = 0; t < n_act; ++t) {
+          // P_t(j) (and the O_t rescale) published by warpgroup t
+          mbar_wait(&p_full[t], j & 1);
+          tc_fence_after_sync();
+          const uint32_t p_addr = smem_u32(sP + t * C::kPBytes);
+#pragma unroll
+          for (int ks = 0; ks < BKV / 16; ++ks) {
+            const int kc = ks >> 2, kk = ks & 3;
+            const uint64_t da = umma_desc_k_sw128(p_addr + kc * (kBQ * 128)) + 2 * kk;
+            const uint64_t db = umma_desc_k_sw128(v_addr + kc * (C::kDV * 128)) + 2 * kk;
+            umma_f16_ss(tmem_base + 2 * BKV + t * C::kDV, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&o_done[t]);
+          if (t == n_act - 1) umma_commit(&kv_empty[s]);  // every MMA that reads stage s has been issued
+          if (more) {
+            if (t == 0) {
+              mbar_wait(&kv_full[s_next], ((j + 1) / C::kStages) & 1);
+              tc_fence_after_sync();
+            }
+            issue_qk(t, s_next);  // S_t is free: warpgroup t finished reading it before arriving on p_full
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax warpgroups: warps 2-5 -> Q tile A, warps 6-9 -> Q tile B ----------------
+    const int t = (warp - 2) >> 2;
+    if (t == 0 || tile_b_active) {
+      const int g = warp & 3;
+      const int r = g * 32 + lane;  // query row inside the tile == TMEM lane
+      const uint32_t t_s = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + t * BKV;
+      const uint32_t t_o = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + 2 * BKV + t * C::kDV;
+      float m_run = -INFINITY;
+      float l_run = 0.f;
+      uint8_t* p_row = sP + t * C::kPBytes + (r >> 3) * 1024 + (r & 7) * 128;
+      const int sw = r & 7;
+
+      for (int j = 0; j < n_tiles; ++j) {
+        const bool src1 = j >= t0;
+        const int key0 = (src1 ? (j - t0) : j) * BKV;
+        const int valid = min(BKV, (src1 ? p.n1 : p.n0) - key0);
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after_sync();
+        // pass 1: raw row max; the next chunk's TMEM load is issued before the current chunk is reduced
+        float mt = -INFINITY;
+        {
+          uint32_t ra[32], rb[32];
+          tmem_ld_x32(t_s, ra);
+#pragma unroll
+          for (int c = 0; c < BKV / 32; ++c) {
+            uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+            uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
+            tmem_wait_ld();
+            if (c + 1 < BKV / 32) tmem_ld_x32(t_s + (c + 1) * 32, nxt);
+            if (valid == BKV) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) mt = fmax3(mt, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i < valid) mt = fmaxf(mt, __uint_as_float(cur[i]));
+            }
+          }
+        }
+        mt *= p.scale_log2;
+        float m_new = m_run;
+        if (mt - m_run > 8.0f) m_new = mt;
+        const float alpha = ex2_approx(m_run - m_new);
+        m_run = m_new;
+
+        if (j > 0) {
+          mbar_wait(&o_done[t], (j - 1) & 1);  // PV_t(j-1) done: P_t may be overwritten, O_t rescaled
+          tc_fence_after_sync();
+          if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+            for (int c = 0; c < C::kDV / 16; ++c) {
+              uint32_t oo[16];
+              tmem_ld_x16(t_o + c * 16, oo);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) oo[i] = __float_as_uint(__uint_as_float(oo[i]) * alpha);
+              tmem_st_x16(t_o + c * 16, oo);
+            }
+            tmem_wait_st();
+          }
+        }
+        // pass 2: p = exp2(s * scale - m), row sum, P -> smem (K-major, 128B swizzle)
+        float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+        const float neg_m = -m_new;
+        {
+          uint32_t ra[32], rb[32];
+          tmem_ld_x32(t_s, ra);
+#pragma unroll
+          for (int c = 0; c < BKV / 32; ++c) {
+            uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+            uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
+            tmem_wait_ld();
+            if (c + 1 < BKV / 32) tmem_ld_x32(t_s + (c + 1) * 32, nxt);
+            float pv[32];
+            if (valid == BKV) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                pv[i] = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m)) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              ls0 += pv[i]; ls1 += pv[i + 1]; ls2 += pv[i + 2]; ls3 += pv[i + 3];
+            }
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+              uint4 pk;
+              pk.x = pack_half2(pv[u4 * 8 + 0], pv[u4 * 8 + 1]);
+              pk.y = pack_half2(pv[u4 * 8 + 2], pv[u4 * 8 + 3]);
+              pk.z = pack_half2(pv[u4 * 8 + 4], pv[u4 * 8 + 5]);
+              pk.w = pack_half2(pv[u4 * 8 + 6], pv[u4 * 8 + 7]);
+              const int u = c * 4 + u4;
+              const int kc = u >> 3, uu = u & 7;
+              *reinterpret_cast<uint4*>(p_row + kc * (kBQ * 128) + ((uu ^ sw) << 4)) = pk;
+            }
+          }
+        }
+        l_run = l_run * alpha + ((ls0 + ls1) + (ls2 + ls3));
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        mbar_arrive(&p_full[t]);
+      }
+
+      // final: O / l -> fp16
+      mbar_wait(&o_done[t], (n_tiles - 1) & 1);
+      tc_fence_after_sync();
+      const float inv_l = 1.0f / l_run;
+      const int q = q0 + t * kBQ + r;
+      __half* op = p.out + (static_cast<long long>(b) * p.nq + q) * p.ldo + head * D;
+#pragma unroll
+      for (int c = 0; c < C::kDV / 16; ++c) {
+        uint32_t oo[16];
+        tmem_ld_x16(t_o + c * 16, oo);
+        tmem_wait_ld();
+        if (q < p.nq) {
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            if (c * 16 + h8 * 8 < D) {
+              uint4 o4;
+              o4.x = pack_half2(__uint_as_float(oo[h8 * 8 + 0]) * inv_l, __uint_as_float(oo[h8 * 8 + 1]) * inv_l);
+              o4.y = pack_half2(__uint_as_float(oo[h8 * 8 + 2]) * inv_l, __uint_as_float(oo[h8 * 8 + 3]) * inv_l);
+              o4.z = pack_half2(__uint_as_float(oo[h8 * 8 + 4]) * inv_l, __uint_as_float(oo[h8 * 8 + 5]) * inv_l);
+              o4.w = pack_half2(__uint_as_float(oo[h8 * 8 + 6]) * inv_l, __uint_as_float(oo[h8 * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(op + c * 16 + h8 * 8) = o4;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
 void count_launch(int n = 1);
+
+static bool attn_use_v2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MDB_ATTN_V1");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <int D, int BKV>
+static int launch_attn2(const AttnKParams& kp, dim3 grid, cudaStream_t st) {
+  using C = Attn2Cfg<D, BKV>;
+  static bool attr_set = false;
+  auto kern = attn2_tc_kernel<D, BKV>;
+  if (!attr_set) {
+    MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    attr_set = true;
+  }
+  MDB_CHECK_CUDA(launch_pdl(kern, grid, dim3(kAttn2Threads), C::kSmem, st, kp));
+  count_launch();
+  return MDB_OK;
+}
 
 template <int D, int BKV>
 static int launch_attn(const AttnKParams& kp, dim3 grid, cudaStream_t st) {
@@ -353,6 +671,10 @@ static int build_and_launch(const mdb_attn_desc* a, cudaStream_t st) {
   kp.ldv1_batch = a->ldv1_batch;
   kp.bank_batches = a->n1 > 0 ? a->bank_batches : 0;
   kp.scale_log2 = a->scale * 1.4426950408889634f;
+  if (attn_use_v2() && a->nq > kBQ) {  // two Q tiles per CTA (ping-pong); tiny layers keep the 1-tile kernel
+    dim3 grid2((a->nq + 2 * kBQ - 1) / (2 * kBQ), a->heads, a->batch);
+    return launch_attn2<D, BKV>(kp, grid2, st);
+  }
   dim3 grid((a->nq + kBQ - 1) / kBQ, a->heads, a->batch);
   return launch_attn<D, BKV>(kp, grid, st);
 }

@@ -292,6 +292,9 @@ ALL_CASES = [
     (case_attention, (2, 8, 40, 1024, 1024, 1024, 1, 1)),
     (case_attention, (2, 8, 40, 1024, 77, 0, 1, None, True)),
     (case_attention, (2, 8, 80, 256, 256, 256, 1)),
+    (case_attention, (1, 8, 40, 384, 384, 128, 1)),
+    (case_attention, (2, 8, 80, 200, 200, 0, 1)),
+    (case_attention, (1, 8, 160, 320, 320, 64, 1)),
     (case_attention, (2, 8, 80, 1024, 77, 0, 1, None, True)),
     (case_attention, (2, 8, 160, 64, 64, 64, 2)),
     (case_attention, (1, 8, 160, 16, 16, 16, 1)),
