@@ -468,53 +468,18 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_tc_kernel(const __grid
         const int valid = min(BKV, (src1 ? p.n1 : p.n0) - key0);
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after_sync();
-        // pass 1: raw row max; the next chunk's TMEM load is issued before the current chunk is reduced
+        // TMEM reads run at ~64 B/clk/SM, so S (64 KB per 128x128 tile) should be read ONCE.  The exp
+        // reference is therefore chosen before looking at the tile: the running max m_run.  The tile is
+        // exponentiated against it while its own max is tracked; only if some row's max exceeds m_run by
+        // more than 2^8 (first tile, or a rare jump) the warp repeats the pass with the new max.
         float mt = -INFINITY;
-        {
-          uint32_t ra[32], rb[32];
-          tmem_ld_x32(t_s, ra);
-#pragma unroll
-          for (int c = 0; c < BKV / 32; ++c) {
-            uint32_t(&cur)[32] = (c & 1) ? rb : ra;
-            uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
-            tmem_wait_ld();
-            if (c + 1 < BKV / 32) tmem_ld_x32(t_s + (c + 1) * 32, nxt);
-            if (valid == BKV) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) mt = fmax3(mt, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i < valid) mt = fmaxf(mt, __uint_as_float(cur[i]));
-            }
-          }
-        }
-        mt *= p.scale_log2;
         float m_new = m_run;
-        if (mt - m_run > 8.0f) m_new = mt;
-        const float alpha = ex2_approx(m_run - m_new);
-        m_run = m_new;
-
+        float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
         if (j > 0) {
           mbar_wait(&o_done[t], (j - 1) & 1);  // PV_t(j-1) done: P_t may be overwritten, O_t rescaled
           tc_fence_after_sync();
-          if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll
-            for (int c = 0; c < C::kDV / 16; ++c) {
-              uint32_t oo[16];
-              tmem_ld_x16(t_o + c * 16, oo);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) oo[i] = __float_as_uint(__uint_as_float(oo[i]) * alpha);
-              tmem_st_x16(t_o + c * 16, oo);
-            }
-            tmem_wait_st();
-          }
         }
-        // pass 2: p = exp2(s * scale - m), row sum, P -> smem (K-major, 128B swizzle)
-        float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-        const float neg_m = -m_new;
-        {
+        auto pass = [&](bool track_max, bool emit, float neg_m) {
           uint32_t ra[32], rb[32];
           tmem_ld_x32(t_s, ra);
 #pragma unroll
@@ -522,32 +487,72 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_tc_kernel(const __grid
             uint32_t(&cur)[32] = (c & 1) ? rb : ra;
             uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
             tmem_wait_ld();
-            if (c + 1 < BKV / 32) tmem_ld_x32(t_s + (c + 1) * 32, nxt);
-            float pv[32];
-            if (valid == BKV) {
+            if (c + 1 < BKV / 32) tmem_ld_x32(t_s + (c + 1) * 32, nxt);  // overlaps the math below
+            if (track_max) {
+              if (valid == BKV) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m));
-            } else {
+                for (int i = 0; i < 32; i += 2) mt = fmax3(mt, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+              } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                pv[i] = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m)) : 0.f;
+                for (int i = 0; i < 32; ++i)
+                  if (c * 32 + i < valid) mt = fmaxf(mt, __uint_as_float(cur[i]));
+              }
             }
+            if (emit) {
+              float pv[32];
+              if (valid == BKV) {  // one FFMA + one MUFU.EX2 + one FADD per element
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              ls0 += pv[i]; ls1 += pv[i + 1]; ls2 += pv[i + 2]; ls3 += pv[i + 3];
-            }
+                for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m));
+              } else {
 #pragma unroll
-            for (int u4 = 0; u4 < 4; ++u4) {
-              uint4 pk;
-              pk.x = pack_half2(pv[u4 * 8 + 0], pv[u4 * 8 + 1]);
-              pk.y = pack_half2(pv[u4 * 8 + 2], pv[u4 * 8 + 3]);
-              pk.z = pack_half2(pv[u4 * 8 + 4], pv[u4 * 8 + 5]);
-              pk.w = pack_half2(pv[u4 * 8 + 6], pv[u4 * 8 + 7]);
-              const int u = c * 4 + u4;
-              const int kc = u >> 3, uu = u & 7;
-              *reinterpret_cast<uint4*>(p_row + kc * (kBQ * 128) + ((uu ^ sw) << 4)) = pk;
+                for (int i = 0; i < 32; ++i)
+                  pv[i] = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m)) : 0.f;
+              }
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                ls0 += pv[i]; ls1 += pv[i + 1]; ls2 += pv[i + 2]; ls3 += pv[i + 3];
+              }
+#pragma unroll
+              for (int u4 = 0; u4 < 4; ++u4) {
+                uint4 pk;
+                pk.x = pack_half2(pv[u4 * 8 + 0], pv[u4 * 8 + 1]);
+                pk.y = pack_half2(pv[u4 * 8 + 2], pv[u4 * 8 + 3]);
+                pk.z = pack_half2(pv[u4 * 8 + 4], pv[u4 * 8 + 5]);
+                pk.w = pack_half2(pv[u4 * 8 + 6], pv[u4 * 8 + 7]);
+                const int u = c * 4 + u4;
+                const int kc = u >> 3, uu = u & 7;
+                *reinterpret_cast<uint4*>(p_row + kc * (kBQ * 128) + ((uu ^ sw) << 4)) = pk;
+              }
             }
           }
+        };
+        bool redo;
+        if (j == 0) {
+          pass(true, false, 0.f);  // no reference yet: max only
+          redo = true;
+        } else {
+          pass(true, true, -m_run);  // optimistic: exponentiate against the running max
+          redo = __any_sync(0xffffffffu, mt * p.scale_log2 - m_run > 8.0f);
+        }
+        if (redo) {
+          const float mts = mt * p.scale_log2;
+          if (mts - m_run > 8.0f) m_new = mts;
+          ls0 = ls1 = ls2 = ls3 = 0.f;
+          pass(false, true, -m_new);
+        }
+        const float alpha = ex2_approx(m_run - m_new);  // m_run = -inf on the first tile -> 0
+        m_run = m_new;
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+          for (int c = 0; c < C::kDV / 16; ++c) {
+            uint32_t oo[16];
+            tmem_ld_x16(t_o + c * 16, oo);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) oo[i] = __float_as_uint(__uint_as_float(oo[i]) * alpha);
+            tmem_st_x16(t_o + c * 16, oo);
+          }
+          tmem_wait_st();
         }
         l_run = l_run * alpha + ((ls0 + ls1) + (ls2 + ls3));
         fence_proxy_async_smem();
