@@ -598,6 +598,309 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_tc_kernel(const __grid
 
 void count_launch(int n = 1);
 
+// ------------------------------------------------------------------------------------------------
+// v3: one Q tile per CTA like v1, but the MMA thread runs ONE KEY TILE AHEAD: S is double-buffered in
+// TMEM (S(j+1) = Q K(j+1)^T is computed while the softmax warps work on S(j)), P is double-buffered in
+// shared memory, and the K/V ring is STAGES deep.  The softmax warps therefore never wait for the
+// tensor core (ncu showed ~30% of their stall samples on the s_full barrier in v1/v2); with two CTAs
+// per SM the MUFU pipe — the real bound of d=40 attention — stays fed.
+// TMEM columns: S[0] [0,BKV)  S[1] [BKV,2BKV)  O [2BKV, 2BKV+DV).
+// ------------------------------------------------------------------------------------------------
+template <int D, int BKV, int STAGES>
+struct Attn3Cfg {
+  using C1 = AttnCfg<D, BKV>;
+  static constexpr int kDV = C1::kDV;
+  static constexpr int kQBytes = C1::kQBytes;
+  static constexpr int kKBytes = C1::kKBytes;
+  static constexpr int kVBytes = C1::kVBytes;
+  static constexpr int kPBytes = C1::kPBytes;
+  static constexpr int kSmem = kQBytes + STAGES * (kKBytes + kVBytes) + 2 * kPBytes + 1024;
+  static constexpr int kCols = 2 * BKV + kDV;
+  static constexpr int kTmemCols = kCols <= 128 ? 128 : (kCols <= 256 ? 256 : 512);
+  static constexpr int kCtasPerSm = (kSmem <= 113 * 1024 && kTmemCols <= 256) ? 2 : 1;
+};
+
+template <int D, int BKV, int STAGES>
+__global__ void __launch_bounds__(kAttnThreads, Attn3Cfg<D, BKV, STAGES>::kCtasPerSm)
+    attn3_tc_kernel(const __grid_constant__ AttnKParams p) {
+  using C = Attn3Cfg<D, BKV, STAGES>;
+  using C1 = AttnCfg<D, BKV>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t q_bar;
+  __shared__ __align__(8) uint64_t s_full[2], p_full[2], o_done[2];  // all indexed by tile parity: no barrier
+                                                                       // is ever more than one phase ahead of its waiter
+  __shared__ __align__(8) uint64_t kv_full[STAGES], kv_empty[STAGES];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + C::kQBytes;
+  uint8_t* sP = sKV + STAGES * (C::kKBytes + C::kVBytes);  // [2][kPBytes]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int t0 = (p.n0 + BKV - 1) / BKV;
+  const int t1 = (b < p.bank_batches && p.n1 > 0) ? (p.n1 + BKV - 1) / BKV : 0;
+  const int n_tiles = t0 + t1;
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK0);
+    tma_prefetch_desc(&p.tmV0);
+    mbar_init(&q_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&o_done[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, C::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&q_bar, C::kQBytes);
+      for (int dc = 0; dc < C1::kDkChunks; ++dc)
+        tma_load_3d(sQ + dc * (kBQ * 128), &p.tmQ, &q_bar, dc * 64, head, b * p.nq + q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % STAGES;
+        const uint32_t ph = (j / STAGES) & 1;
+        const bool src1 = j >= t0;
+        const int key0 = (src1 ? (j - t0) : j) * BKV;
+        const CUtensorMap* tk = src1 ? &p.tmK1 : &p.tmK0;
+        const CUtensorMap* tv = src1 ? &p.tmV1 : &p.tmV0;
+        const int nsrc = src1 ? p.n1 : p.n0;
+        const int kvb = src1 ? (p.kv1_batches > 1 ? b : 0) : (p.kv0_batches > 1 ? b : 0);
+        const int ldvb = src1 ? p.ldv1_batch : p.ldv0_batch;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_expect_tx(&kv_full[s], C::kKBytes + C::kVBytes);
+        uint8_t* sk = sKV + s * (C::kKBytes + C::kVBytes);
+        uint8_t* sv = sk + C::kKBytes;
+        for (int dc = 0; dc < C1::kDkChunks; ++dc)
+          tma_load_3d(sk + dc * (BKV * 128), tk, &kv_full[s], dc * 64, head, kvb * nsrc + key0);
+        for (int kc = 0; kc < C1::kKvChunks; ++kc)
+          tma_load_2d(sv + kc * (C::kDV * 128), tv, &kv_full[s], kvb * ldvb + key0 + kc * 64, head * D);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(kBQ, BKV);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(kBQ, C::kDV);
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_qk = [&](int j) {  // S[j & 1] = Q K(j)^T
+        const int s = j % STAGES;
+        mbar_wait(&kv_full[s], (j / STAGES) & 1);
+        tc_fence_after_sync();
+        const uint32_t k_addr = smem_u32(sKV + s * (C::kKBytes + C::kVBytes));
+#pragma unroll
+        for (int ks = 0; ks < C1::kKSteps; ++ks) {
+          const int dc = ks >> 2, kk = ks & 3;
+          const uint64_t da = umma_desc_k_sw128(q_addr + dc * (kBQ * 128)) + 2 * kk;
+          const uint64_t db = umma_desc_k_sw128(k_addr + dc * (BKV * 128)) + 2 * kk;
+          umma_f16_ss(tmem_base + (j & 1) * BKV, da, db, idesc_qk, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(&q_bar, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        // run ahead: S(j+1) while the softmax warps are still on S(j).  Buffer (j+1)&1 was last read for
+        // tile j-1, whose readers finished before arriving on p_full[(j-1)&1] — waited for in iteration j-1.
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        const int s = j % STAGES;
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t p_addr = smem_u32(sP + (j & 1) * C::kPBytes);
+        const uint32_t v_addr = smem_u32(sKV + s * (C::kKBytes + C::kVBytes)) + C::kKBytes;
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          const int kc = ks >> 2, kk = ks & 3;
+          const uint64_t da = umma_desc_k_sw128(p_addr + kc * (kBQ * 128)) + 2 * kk;
+          const uint64_t db = umma_desc_k_sw128(v_addr + kc * (C::kDV * 128)) + 2 * kk;
+          umma_f16_ss(tmem_base + 2 * BKV, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(&o_done[j & 1]);
+      }
+    }
+  } else {
+    // ---------------- softmax / correction / epilogue warps ----------------
+    const int g = warp & 3;
+    const int r = g * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
+    const uint32_t t_o = t_lane + 2 * BKV;
+    float m_run = -INFINITY;
+    float l_run = 0.f;
+    uint8_t* p_row0 = sP + (r >> 3) * 1024 + (r & 7) * 128;
+    const int sw = r & 7;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const bool src1 = j >= t0;
+      const int key0 = (src1 ? (j - t0) : j) * BKV;
+      const int valid = min(BKV, (src1 ? p.n1 : p.n0) - key0);
+      const uint32_t t_s = t_lane + (j & 1) * BKV;
+      uint8_t* p_row = p_row0 + (j & 1) * C::kPBytes;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after_sync();
+      float mt = -INFINITY;
+      float m_new = m_run;
+      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+      // P buffer (j&1) was last read by PV(j-2) — the previous completion of o_done[j&1]
+      if (j >= 2) mbar_wait(&o_done[j & 1], ((j - 2) >> 1) & 1);
+      auto pass = [&](bool track_max, bool emit, float neg_m) {
+        uint32_t ra[32], rb[32];
+        tmem_ld_x32(t_s, ra);
+#pragma unroll
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+          uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
+          tmem_wait_ld();
+          if (c + 1 < BKV / 32) tmem_ld_x32(t_s + (c + 1) * 32, nxt);
+          if (track_max) {
+            if (valid == BKV) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) mt = fmax3(mt, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i < valid) mt = fmaxf(mt, __uint_as_float(cur[i]));
+            }
+          }
+          if (emit) {
+            float pv[32];
+            if (valid == BKV) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                pv[i] = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m)) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              ls0 += pv[i]; ls1 += pv[i + 1]; ls2 += pv[i + 2]; ls3 += pv[i + 3];
+            }
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+              uint4 pk;
+              pk.x = pack_half2(pv[u4 * 8 + 0], pv[u4 * 8 + 1]);
+              pk.y = pack_half2(pv[u4 * 8 + 2], pv[u4 * 8 + 3]);
+              pk.z = pack_half2(pv[u4 * 8 + 4], pv[u4 * 8 + 5]);
+              pk.w = pack_half2(pv[u4 * 8 + 6], pv[u4 * 8 + 7]);
+              const int u = c * 4 + u4;
+              const int kc = u >> 3, uu = u & 7;
+              *reinterpret_cast<uint4*>(p_row + kc * (kBQ * 128) + ((uu ^ sw) << 4)) = pk;
+            }
+          }
+        }
+      };
+      bool redo;
+      if (j == 0) {
+        pass(true, false, 0.f);
+        redo = true;
+      } else {
+        pass(true, true, -m_run);  // optimistic: exponentiate against the running max (S is read once)
+        redo = __any_sync(0xffffffffu, mt * p.scale_log2 - m_run > 8.0f);
+      }
+      if (redo) {
+        const float mts = mt * p.scale_log2;
+        if (mts - m_run > 8.0f) m_new = mts;
+        ls0 = ls1 = ls2 = ls3 = 0.f;
+        pass(false, true, -m_new);
+      }
+      const float alpha = ex2_approx(m_run - m_new);
+      m_run = m_new;
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        // O must be stable: PV(j-1) complete (rare path — the lazy threshold keeps alpha == 1 almost always)
+        mbar_wait(&o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < C::kDV / 16; ++c) {
+          uint32_t oo[16];
+          tmem_ld_x16(t_o + c * 16, oo);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) oo[i] = __float_as_uint(__uint_as_float(oo[i]) * alpha);
+          tmem_st_x16(t_o + c * 16, oo);
+        }
+        tmem_wait_st();
+      }
+      l_run = l_run * alpha + ((ls0 + ls1) + (ls2 + ls3));
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&p_full[j & 1]);
+    }
+
+    mbar_wait(&o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+    tc_fence_after_sync();
+    const float inv_l = 1.0f / l_run;
+    const int q = q0 + r;
+    __half* op = p.out + (static_cast<long long>(b) * p.nq + q) * p.ldo + head * D;
+#pragma unroll
+    for (int c = 0; c < C::kDV / 16; ++c) {
+      uint32_t oo[16];
+      tmem_ld_x16(t_o + c * 16, oo);
+      tmem_wait_ld();
+      if (q < p.nq) {
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          if (c * 16 + h8 * 8 < D) {
+            uint4 o4;
+            o4.x = pack_half2(__uint_as_float(oo[h8 * 8 + 0]) * inv_l, __uint_as_float(oo[h8 * 8 + 1]) * inv_l);
+            o4.y = pack_half2(__uint_as_float(oo[h8 * 8 + 2]) * inv_l, __uint_as_float(oo[h8 * 8 + 3]) * inv_l);
+            o4.z = pack_half2(__uint_as_float(oo[h8 * 8 + 4]) * inv_l, __uint_as_float(oo[h8 * 8 + 5]) * inv_l);
+            o4.w = pack_half2(__uint_as_float(oo[h8 * 8 + 6]) * inv_l, __uint_as_float(oo[h8 * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(op + c * 16 + h8 * 8) = o4;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int D, int BKV, int STAGES>
+static int launch_attn3(const AttnKParams& kp, dim3 grid, cudaStream_t st) {
+  using C = Attn3Cfg<D, BKV, STAGES>;
+  static bool attr_set = false;
+  auto kern = attn3_tc_kernel<D, BKV, STAGES>;
+  if (!attr_set) {
+    MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    attr_set = true;
+  }
+  MDB_CHECK_CUDA(launch_pdl(kern, grid, dim3(kAttnThreads), C::kSmem, st, kp));
+  count_launch();
+  return MDB_OK;
+}
+
+static int attn_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MDB_ATTN");
+    v = (e != nullptr && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3;
+  }
+  return v;
+}
+
 static bool attn_use_v2() {
   static int v = -1;
   if (v < 0) {
@@ -635,7 +938,7 @@ static int launch_attn(const AttnKParams& kp, dim3 grid, cudaStream_t st) {
   return MDB_OK;
 }
 
-template <int D, int BKV>
+template <int D, int BKV, int VER>
 static int build_and_launch(const mdb_attn_desc* a, cudaStream_t st) {
   using C = AttnCfg<D, BKV>;
   AttnKParams kp;
@@ -676,11 +979,12 @@ static int build_and_launch(const mdb_attn_desc* a, cudaStream_t st) {
   kp.ldv1_batch = a->ldv1_batch;
   kp.bank_batches = a->n1 > 0 ? a->bank_batches : 0;
   kp.scale_log2 = a->scale * 1.4426950408889634f;
-  if (attn_use_v2() && a->nq > kBQ) {  // two Q tiles per CTA (ping-pong); tiny layers keep the 1-tile kernel
+  dim3 grid((a->nq + kBQ - 1) / kBQ, a->heads, a->batch);
+  if constexpr (VER == 3) return launch_attn3<D, BKV, (D == 40 ? 4 : 3)>(kp, grid, st);
+  if (VER == 2 && a->nq > kBQ) {  // two Q tiles per CTA (ping-pong)
     dim3 grid2((a->nq + 2 * kBQ - 1) / (2 * kBQ), a->heads, a->batch);
     return launch_attn2<D, BKV>(kp, grid2, st);
   }
-  dim3 grid((a->nq + kBQ - 1) / kBQ, a->heads, a->batch);
   return launch_attn<D, BKV>(kp, grid, st);
 }
 
@@ -700,10 +1004,16 @@ extern "C" int mdb_attention_f16(const mdb_attn_desc* a, mdb_stream_t stream) {
   MDB_REQUIRE(a->ldv0_batch >= a->n0 && a->ldv0_batch % 8 == 0, "mdb_attention_f16: ldv0_batch must be >= n0 and %% 8");
   MDB_REQUIRE(a->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "mdb_attention_f16: out alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int ver = attn_version();
   switch (a->d) {
-    case 40: return build_and_launch<40, 128>(a, st);
-    case 80: return build_and_launch<80, 64>(a, st);
-    case 160: return build_and_launch<160, 64>(a, st);
+    case 40:
+      if (ver == 3) return build_and_launch<40, 64, 3>(a, st);
+      return ver == 2 ? build_and_launch<40, 128, 2>(a, st) : build_and_launch<40, 128, 1>(a, st);
+    case 80:
+      if (ver == 3) return build_and_launch<80, 64, 3>(a, st);
+      return ver == 2 ? build_and_launch<80, 64, 2>(a, st) : build_and_launch<80, 64, 1>(a, st);
+    case 160:
+      return ver == 2 ? build_and_launch<160, 64, 2>(a, st) : build_and_launch<160, 64, 1>(a, st);
     default:
       set_error("mdb_attention_f16: head dim %d not supported (40, 80, 160)", a->d);
       return MDB_ERR_UNSUPPORTED;
