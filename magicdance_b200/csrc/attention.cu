@@ -620,7 +620,7 @@ struct Attn3Cfg {
   static constexpr int kCtasPerSm = (kSmem <= 113 * 1024 && kTmemCols <= 256) ? 2 : 1;
 };
 
-template <int D, int BKV, int STAGES>
+template <int D, int BKV, int STAGES, int EMU>  // EMU of every 4 exponentials run on the FMA pipe
 __global__ void __launch_bounds__(kAttnThreads, Attn3Cfg<D, BKV, STAGES>::kCtasPerSm)
     attn3_tc_kernel(const __grid_constant__ AttnKParams p) {
   using C = Attn3Cfg<D, BKV, STAGES>;
@@ -783,7 +783,10 @@ __global__ void __launch_bounds__(kAttnThreads, Attn3Cfg<D, BKV, STAGES>::kCtasP
             float pv[32];
             if (valid == BKV) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m));
+              for (int i = 0; i < 32; ++i) {
+                const float xs = fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m);
+                pv[i] = ((i & 3) < EMU) ? ex2_poly(xs) : ex2_approx(xs);
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
@@ -878,11 +881,11 @@ __global__ void __launch_bounds__(kAttnThreads, Attn3Cfg<D, BKV, STAGES>::kCtasP
   }
 }
 
-template <int D, int BKV, int STAGES>
+template <int D, int BKV, int STAGES, int EMU>
 static int launch_attn3(const AttnKParams& kp, dim3 grid, cudaStream_t st) {
   using C = Attn3Cfg<D, BKV, STAGES>;
   static bool attr_set = false;
-  auto kern = attn3_tc_kernel<D, BKV, STAGES>;
+  auto kern = attn3_tc_kernel<D, BKV, STAGES, EMU>;
   if (!attr_set) {
     MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     attr_set = true;
@@ -980,7 +983,14 @@ static int build_and_launch(const mdb_attn_desc* a, cudaStream_t st) {
   kp.bank_batches = a->n1 > 0 ? a->bank_batches : 0;
   kp.scale_log2 = a->scale * 1.4426950408889634f;
   dim3 grid((a->nq + kBQ - 1) / kBQ, a->heads, a->batch);
-  if constexpr (VER == 3) return launch_attn3<D, BKV, (D == 40 ? 4 : 3)>(kp, grid, st);
+  if constexpr (VER == 3) {
+    constexpr int ST = (D == 40 ? 4 : 3);
+    static const int emu = [] { const char* e = getenv("MDB_ATTN_EMU"); return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2; }();
+    if (emu == 1) return launch_attn3<D, BKV, ST, 1>(kp, grid, st);
+    if (emu == 2) return launch_attn3<D, BKV, ST, 2>(kp, grid, st);
+    if (emu == 3) return launch_attn3<D, BKV, ST, 3>(kp, grid, st);
+    return launch_attn3<D, BKV, ST, 0>(kp, grid, st);
+  }
   if (VER == 2 && a->nq > kBQ) {  // two Q tiles per CTA (ping-pong)
     dim3 grid2((a->nq + 2 * kBQ - 1) / (2 * kBQ), a->heads, a->batch);
     return launch_attn2<D, BKV>(kp, grid2, st);
