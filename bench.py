@@ -201,10 +201,16 @@ def roofline_probe(torch, ops, trace, peaks):
     ach = tot_fl / tot_t / 1e12
     top = [{"shape_mnk_conv_splits": list(map(int, r[2][:3])) + [bool(r[2][3]), int(r[2][4])], "count": r[3],
             "ms_total": r[1] * 1e3, "tflops": r[0] / r[1] / 1e12} for r in rows[:6]]
+    traffic = None
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("gemm_tc_kernel")
+    except Exception:  # noqa: BLE001
+        pass
     return {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + 3x3 implicit-GEMM conv)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1590",
-            "traffic": None, "gemm_gflop_per_step": tot_fl / 1e9, "gemm_ms_per_step_isolated": tot_t * 1e3,
+            "traffic": traffic, "gemm_gflop_per_step": tot_fl / 1e9, "gemm_ms_per_step_isolated": tot_t * 1e3,
             "launches_per_step": int(sum(cnt.values())), "top_by_time": top}
 
 

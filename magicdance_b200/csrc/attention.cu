@@ -904,15 +904,6 @@ static int attn_version() {
   return v;
 }
 
-static bool attn_use_v2() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MDB_ATTN_V1");
-    v = (e != nullptr && e[0] == '1') ? 0 : 1;
-  }
-  return v != 0;
-}
-
 template <int D, int BKV>
 static int launch_attn2(const AttnKParams& kp, dim3 grid, cudaStream_t st) {
   using C = Attn2Cfg<D, BKV>;
@@ -985,7 +976,7 @@ static int build_and_launch(const mdb_attn_desc* a, cudaStream_t st) {
   dim3 grid((a->nq + kBQ - 1) / kBQ, a->heads, a->batch);
   if constexpr (VER == 3) {
     constexpr int ST = (D == 40 ? 4 : 3);
-    static const int emu = [] { const char* e = getenv("MDB_ATTN_EMU"); return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2; }();
+    static const int emu = [] { const char* e = getenv("MDB_ATTN_EMU"); return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 1; }();  // 1 of 4 measured best on B200
     if (emu == 1) return launch_attn3<D, BKV, ST, 1>(kp, grid, st);
     if (emu == 2) return launch_attn3<D, BKV, ST, 2>(kp, grid, st);
     if (emu == 3) return launch_attn3<D, BKV, ST, 3>(kp, grid, st);
