@@ -236,11 +236,13 @@ def run_ours(args):
     except Exception:  # noqa: BLE001
         pass
 
-    sd = synth.synth_state_dict(seed=0)
+    sd = synth.synth_state_dict(seed=0, device=f"cuda:{local}")  # random-init weights, generated on the GPU
     eng = DenoiseEngine(sd, device=f"cuda:{local}")
     if args.no_cpu_baseline or rank != 0 or world > 1:
-        del sd
         sd = None
+    else:
+        sd = {k: v.cpu() for k, v in sd.items()}  # the CPU baseline runs the same weights
+    torch.cuda.empty_cache()
     pipe = DenoisePipeline(eng, ddim_steps=50, scale=7.0, eta=0.0)
     B, L, K, W = args.batch, args.latent, args.steps, args.warmup
     inp = synth.synth_inputs(B, L, seed=100 + rank, shared_reference=True)

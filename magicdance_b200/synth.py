@@ -25,24 +25,27 @@ SCHEDULE_KEYS = (
 )
 
 
-def _gen(seed: int, key: str) -> torch.Generator:
-    g = torch.Generator(device="cpu")
+def _gen(seed: int, key: str, device="cpu") -> torch.Generator:
+    g = torch.Generator(device=device)
     g.manual_seed((seed * 1000003 + zlib.crc32(key.encode())) & 0x7FFFFFFFFFFFFFFF)
     return g
 
 
-def synth_tensor(key: str, shape, seed: int = 0) -> torch.Tensor:
+def synth_tensor(key: str, shape, seed: int = 0, device="cpu") -> torch.Tensor:
+    """device='cpu' is the reproducible stream the golden fixtures were made with; a CUDA device uses the
+    GPU generator (same distributions, different values, ~100x faster) for benchmarks."""
     shape = tuple(shape)
-    g = _gen(seed, key)
+    g = _gen(seed, key, device)
+    rn = lambda: torch.randn(shape, generator=g, device=device)
     if len(shape) == 4:  # conv weight OIHW
         fan_in = shape[1] * shape[2] * shape[3]
-        return torch.randn(shape, generator=g) * (1.0 / fan_in) ** 0.5
+        return rn() * (1.0 / fan_in) ** 0.5
     if len(shape) == 2:  # linear weight (out, in)
-        return torch.randn(shape, generator=g) * (1.0 / shape[1]) ** 0.5
+        return rn() * (1.0 / shape[1]) ** 0.5
     if len(shape) == 1:
         if key.endswith(".weight"):  # GroupNorm / LayerNorm scale
-            return 1.0 + 0.1 * torch.randn(shape, generator=g)
-        return 0.05 * torch.randn(shape, generator=g)  # any bias
+            return 1.0 + 0.1 * rn()
+        return 0.05 * rn()  # any bias
     raise ValueError(f"unexpected parameter rank for {key}: {shape}")
 
 
@@ -51,7 +54,7 @@ def load_manifest(path: str = MANIFEST) -> dict:
         return json.load(f)
 
 
-def synth_state_dict(manifest: dict | None = None, seed: int = 0, prefixes=None) -> dict:
+def synth_state_dict(manifest: dict | None = None, seed: int = 0, prefixes=None, device="cpu") -> dict:
     """name -> fp32 tensor for every network parameter in the manifest (schedule buffers are
     derived, not synthesised: see restatement.make_schedule)."""
     manifest = manifest or load_manifest()
@@ -61,7 +64,7 @@ def synth_state_dict(manifest: dict | None = None, seed: int = 0, prefixes=None)
             continue
         if prefixes is not None and not key.startswith(tuple(prefixes)):
             continue
-        out[key] = synth_tensor(key, manifest[key], seed)
+        out[key] = synth_tensor(key, manifest[key], seed, device)
     return out
 
 
