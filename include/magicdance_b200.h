@@ -134,9 +134,12 @@ int mdb_conv3x3_direct_f16(const void* x, const void* wt, const float* bias, con
                            int32_t batch, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t stride,
                            int32_t silu, mdb_stream_t stream);
 
-/* im2col for 3x3 stride-2 pad-1 (Downsample.op, openaimodel.py:154-180): x NHWC [B][h][w][c] ->
- * col [B*(h/2)*(w/2)][9*c] with K order (kh, kw, c), consumed by mdb_gemm_f16. */
-int mdb_im2col3x3s2_f16(const void* x, void* col, int32_t batch, int32_t h, int32_t w, int32_t c, mdb_stream_t stream);
+/* im2col for 3x3 pad-1 convolutions, stride 1 or 2: x NHWC [B][h][w][c] -> col [B*ho*wo][9*c] with K order
+ * (kh, kw, c), ho = (h-1)/stride+1, consumed by mdb_gemm_f16.  Used for Downsample.op (stride 2,
+ * openaimodel.py:154-180) and as the general path for latent sizes whose rows do not tile into the
+ * 128-pixel TMA boxes of the implicit-GEMM conv (any image size the reference accepts works). */
+int mdb_im2col3x3_f16(const void* x, void* col, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t stride,
+                      mdb_stream_t stream);
 
 /* nearest x2 upsample (Upsample.forward, openaimodel.py:129-139): NHWC [B][h][w][c] -> [B][2h][2w][c] */
 int mdb_upsample2x_f16(const void* x, void* y, int32_t batch, int32_t h, int32_t w, int32_t c, mdb_stream_t stream);

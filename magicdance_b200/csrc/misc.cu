@@ -247,11 +247,11 @@ __global__ void conv3x3_smallcout_kernel(const __half* __restrict__ x, const __h
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void im2col3x3s2_kernel(const __half* __restrict__ x, __half* __restrict__ col, int batch, int h, int w,
-                                   int c) {
+__global__ void im2col3x3_kernel(const __half* __restrict__ x, __half* __restrict__ col, int batch, int h, int w,
+                                 int c, int stride, int ho, int wo) {
   pdl_launch_dependents();
   pdl_wait();
-  const int ho = h / 2, wo = w / 2, vecs = c / 8;
+  const int vecs = c / 8;
   const long long total = static_cast<long long>(batch) * ho * wo * 9 * vecs;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -262,7 +262,7 @@ __global__ void im2col3x3s2_kernel(const __half* __restrict__ x, __half* __restr
     const int ox = static_cast<int>(r % wo);
     const int oy = static_cast<int>((r / wo) % ho);
     const int b = static_cast<int>(r / (static_cast<long long>(wo) * ho));
-    const int yy = oy * 2 - 1 + t / 3, xx = ox * 2 - 1 + t % 3;
+    const int yy = oy * stride - 1 + t / 3, xx = ox * stride - 1 + t % 3;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (yy >= 0 && yy < h && xx >= 0 && xx < w)
       val = *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * h + yy) * w + xx) * c + v * 8);
@@ -510,13 +510,14 @@ extern "C" int mdb_conv3x3_direct_f16(const void* x, const void* wt, const float
   return MDB_OK;
 }
 
-extern "C" int mdb_im2col3x3s2_f16(const void* x, void* col, int32_t batch, int32_t h, int32_t w, int32_t c,
-                                   mdb_stream_t stream) {
-  MDB_REQUIRE(x && col, "mdb_im2col3x3s2_f16: null pointer");
-  MDB_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "mdb_im2col3x3s2_f16: need c %% 8 == 0 and even h, w");
-  const long long total = static_cast<long long>(batch) * (h / 2) * (w / 2) * 9 * (c / 8);
-  MDB_CHECK_CUDA(launch_pdl(im2col3x3s2_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream),
-                            static_cast<const __half*>(x), static_cast<__half*>(col), batch, h, w, c));
+extern "C" int mdb_im2col3x3_f16(const void* x, void* col, int32_t batch, int32_t h, int32_t w, int32_t c,
+                                 int32_t stride, mdb_stream_t stream) {
+  MDB_REQUIRE(x && col, "mdb_im2col3x3_f16: null pointer");
+  MDB_REQUIRE(c % 8 == 0 && (stride == 1 || stride == 2), "mdb_im2col3x3_f16: need c %% 8 == 0 and stride 1 or 2");
+  const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
+  const long long total = static_cast<long long>(batch) * ho * wo * 9 * (c / 8);
+  MDB_CHECK_CUDA(launch_pdl(im2col3x3_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                            static_cast<const __half*>(x), static_cast<__half*>(col), batch, h, w, c, stride, ho, wo));
   count_launch();
   return MDB_OK;
 }

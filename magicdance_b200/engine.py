@@ -341,6 +341,13 @@ class DenoiseEngine:
             m = x.b * x.hw
             y = ops.gemm(x.data, w, bias=bias, bias_batch_stride=bias_batch_stride, rows_per_batch=x.hw,
                          residual=residual, conv=(x.b, x.h, x.w, cin), splits=_auto_splits(m, cout, 9 * cin))
+        elif cin % 64 == 0 and cout % 8 == 0 and cout >= 64:
+            # latent sizes whose rows do not tile into 128-pixel TMA boxes (e.g. 96x64 -> 12x8 at the deepest
+            # level): explicit im2col + the same tensor-core GEMM
+            m = x.b * x.hw
+            col = ops.im2col3x3(x.data, batch=x.b, h=x.h, w=x.w, c=cin, stride=1)
+            y = ops.gemm(col, w, bias=bias, bias_batch_stride=bias_batch_stride, rows_per_batch=x.hw,
+                         residual=residual, splits=_auto_splits(m, cout, 9 * cin))
         else:
             assert bias_batch_stride == 0
             y = ops.conv3x3_direct(x.data, w, bias, batch=x.b, h=x.h, w=x.w, cin=cin, cout=cout, residual=residual)
@@ -407,10 +414,10 @@ class DenoiseEngine:
                                       state.get("bank_batches", 0))
                 state["attn_i"] = i + 1
             elif kind == "down":
-                col = ops.im2col3x3s2(x.data, batch=x.b, h=x.h, w=x.w, c=x.c)
-                m = x.b * (x.h // 2) * (x.w // 2)
-                y = ops.gemm(col, lw[0], bias=lw[1], splits=_auto_splits(m, cout, 9 * cin))
-                x = Act(y, x.b, x.h // 2, x.w // 2)
+                col = ops.im2col3x3(x.data, batch=x.b, h=x.h, w=x.w, c=x.c, stride=2)
+                ho, wo = (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1
+                y = ops.gemm(col, lw[0], bias=lw[1], splits=_auto_splits(x.b * ho * wo, cout, 9 * cin))
+                x = Act(y, x.b, ho, wo)
             elif kind == "up":
                 up = ops.upsample2x(x.data, batch=x.b, h=x.h, w=x.w, c=x.c)
                 x = self._conv3(Act(up, x.b, 2 * x.h, 2 * x.w), lw[0], lw[1], cout=cout)

@@ -213,11 +213,12 @@ def conv3x3_direct(x, wt, bias, *, batch, h, w, cin, cout, stride=1, silu=False,
     return out
 
 
-def im2col3x3s2(x, *, batch, h, w, c):
+def im2col3x3(x, *, batch, h, w, c, stride):
     lib = _lib.load()
     _chk(x, torch.float16, "x")
-    col = torch.empty((batch * (h // 2) * (w // 2), 9 * c), dtype=torch.float16, device=x.device)
-    _lib.check(lib.mdb_im2col3x3s2_f16(x.data_ptr(), col.data_ptr(), batch, h, w, c, _stream()), "im2col3x3s2_f16")
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    col = torch.empty((batch * ho * wo, 9 * c), dtype=torch.float16, device=x.device)
+    _lib.check(lib.mdb_im2col3x3_f16(x.data_ptr(), col.data_ptr(), batch, h, w, c, stride, _stream()), "im2col3x3_f16")
     return col
 
 

@@ -121,7 +121,7 @@ def main():
         x = h(1024, 640)
         timeit("upsample 32x32x640", lambda: ops.upsample2x(x, batch=1, h=32, w=32, c=640))
         x = h(4096, 320)
-        timeit("im2col 64x64x320", lambda: ops.im2col3x3s2(x, batch=1, h=64, w=64, c=320))
+        timeit("im2col 64x64x320", lambda: ops.im2col3x3(x, batch=1, h=64, w=64, c=320, stride=2))
         e, w, bb = f(1, 1280), h(20160, 1280), f(20160)
         timeit("skinny_linear 1x20160x1280", lambda: ops.skinny_linear(e, w, bb, silu_in=True), bytes_=2.0 * 20160 * 1280)
         for (hh, cin, cout, s) in ((512, 3, 16, 1), (512, 16, 16, 1), (512, 16, 32, 2), (256, 32, 32, 1), (256, 32, 96, 2),

@@ -119,10 +119,23 @@ def case_down(batch, h, w, c, seed=0):
     b = _rand(c, seed=seed + 2).float()
     from magicdance_b200.engine import pack_conv3x3
     xn = x.permute(0, 2, 3, 1).contiguous().reshape(batch * h * w, c)
-    col = ops.im2col3x3s2(xn, batch=batch, h=h, w=w, c=c)
+    col = ops.im2col3x3(xn, batch=batch, h=h, w=w, c=c, stride=2)
     out = ops.gemm(col, pack_conv3x3(wt, DEV), bias=b)
     ref = F.conv2d(x.float(), wt.float(), b, padding=1, stride=2).permute(0, 2, 3, 1).reshape(-1, c)
     return rel(out.float(), ref), 2e-3, f"downsample im2col+gemm B={batch} {h}x{w} c={c}"
+
+
+def case_conv_im2col(batch, h, w, cin, cout, seed=0):
+    """general-size 3x3 conv: explicit im2col (stride 1) + GEMM, for latents that do not tile into TMA boxes"""
+    x = _rand(batch, cin, h, w, seed=seed).half()
+    wt = _rand(cout, cin, 3, 3, seed=seed + 1, scale=(9 * cin) ** -0.5).half()
+    b = _rand(cout, seed=seed + 2).float()
+    from magicdance_b200.engine import pack_conv3x3
+    xn = x.permute(0, 2, 3, 1).contiguous().reshape(batch * h * w, cin)
+    col = ops.im2col3x3(xn, batch=batch, h=h, w=w, c=cin, stride=1)
+    out = ops.gemm(col, pack_conv3x3(wt, DEV), bias=b)
+    ref = F.conv2d(x.float(), wt.float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, cout)
+    return rel(out.float(), ref), 2e-3, f"conv3x3 im2col+gemm B={batch} {h}x{w} {cin}->{cout}"
 
 
 def case_upsample(batch, h, w, c, seed=0):
@@ -287,6 +300,9 @@ ALL_CASES = [
     (case_conv_direct, (1, 128, 128, 16, 32, 2, True)),
     (case_conv_direct, (1, 64, 64, 96, 256, 2, True)),
     (case_down, (2, 32, 32, 640)),
+    (case_down, (1, 24, 16, 640)),
+    (case_conv_im2col, (1, 12, 8, 1280, 1280)),
+    (case_conv_im2col, (2, 6, 10, 640, 320)),
     (case_attention, (1, 8, 40, 4096, 4096)),
     (case_attention, (2, 8, 40, 1024, 1024, 1024, 2)),
     (case_attention, (2, 8, 40, 1024, 1024, 1024, 1, 1)),

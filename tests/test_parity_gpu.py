@@ -127,3 +127,21 @@ def test_graphed_chain_matches_eager(engine):
         x_g = gd.step(ix, slots[j]).clone()
         assert G.rel_l2(x_g, x_e) <= 2e-3, (j, G.rel_l2(x_g, x_e))
     assert gd.step_launches > 500 and gd.bank_launches > 300
+
+
+def test_non_square_latent_matches_cpu_oracle(engine):
+    """768x512 image -> 96x64 latent: the deepest level (12x8 = 96 pixels) does not tile into the 128-pixel
+    TMA boxes, so those convs take the im2col path; everything must still match the oracle."""
+    from tests import golden_util as G
+    from magicdance_b200 import synth
+    from oracle import restatement as R
+    sd = synth.synth_state_dict(seed=0)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(1, 4, 96, 64, generator=g)
+    ref = 0.8 * torch.randn(1, 4, 96, 64, generator=g)
+    pose = (torch.rand(1, 3, 768, 512, generator=g) > 0.97).float() * torch.rand(1, 3, 768, 512, generator=g)
+    ctx = torch.randn(1, 77, 768, generator=g)
+    t = torch.tensor([621])
+    e_ref = R.apply_model(sd, x, t, ctx, pose, ref, uc=False)
+    e_gpu = engine.apply_model(x.cuda(), t.cuda(), ctx.cuda(), pose.cuda(), ref.cuda(), uc=False)
+    assert G.rel_l2(e_gpu, e_ref) <= TOL_EPS
