@@ -313,10 +313,10 @@ class DenoiseEngine:
     def context_kv(self, net: PackedNet, ctx16: torch.Tensor, key):
         """Text keys/values of every attn2 (CrossAttention.to_k/to_v on the CLIP context,
         attention.py:172-174); depends only on the context -> cached per (net, context)."""
-        ck = (id(net), key)  # per PackedNet object: drop-in modules all have an empty key prefix
+        ck = (id(net),) + tuple(key[:3])  # per PackedNet object: drop-in modules all have an empty key prefix
         hit = self._ctx_cache.get(ck)
-        if hit is not None:
-            return hit
+        if hit is not None:  # the entry's strong reference keeps that storage alive, so the address is still its own
+            return hit[0]
         b, n, cd = ctx16.shape
         flat = ctx16.reshape(b * n, cd)
         ldv = (n + 7) // 8 * 8
@@ -331,7 +331,7 @@ class DenoiseEngine:
             res.append((k, vt, n, b, ldv))
         if len(self._ctx_cache) > 8:
             self._ctx_cache.clear()
-        self._ctx_cache[ck] = res
+        self._ctx_cache[ck] = (res, key[3] if len(key) > 3 else None)  # strong ref to the context tensor
         return res
 
     # ---- blocks -------------------------------------------------------------------------------
@@ -429,7 +429,11 @@ class DenoiseEngine:
         b, c, h, w = x.shape
         act = Act(ops.nchw_f32_to_nhwc_f16(x), b, h, w)
         ctx16 = context.to(device=self.device, dtype=torch.float16).contiguous()
-        key = (context.data_ptr(), context._version, tuple(context.shape), str(context.device))
+        # cache key: storage address + view geometry + version counter (in-place edits invalidate).  The cache
+        # entry holds a strong reference to the tensor, so the storage cannot be freed and its address recycled
+        # by a different context while the entry exists.
+        key = ((context.untyped_storage().data_ptr(), context.storage_offset(), tuple(context.stride())),
+               context._version, tuple(context.shape), context)
         return act, ctx16, key
 
     def appearance_write(self, ref_latent, t, context):
@@ -548,7 +552,7 @@ class DenoiseEngine:
             t = torch.cat([t, t])
             if ctx16.shape[0] > 1:
                 ctx16 = torch.cat([ctx16, ctx16])
-                key = key + ("pair",)
+                key = (key[0], key[1], key[2] + ("pair",), key[3])
         ctx_kvs = self.context_kv(net, ctx16, key)
         emb_all = self.time_bias(net, t)
         state = {"mode": "plain" if uc else "read", "attn_i": 0}
