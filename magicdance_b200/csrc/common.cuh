@@ -53,8 +53,8 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 // MDB_PDL=0 in the environment turns the attribute off (then griddepcontrol.* are no-ops).
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                                       cudaStream_t stream, unsigned cluster_y, unsigned cluster_z, Args&&... args) {
+inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                      cudaStream_t stream, unsigned cluster_z, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -63,10 +63,10 @@ inline cudaError_t launch_pdl_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int n = 0;
-  if (cluster_y * cluster_z > 1) {  // cluster: y = N-tile partners sharing the A operand by TMA multicast,
-    attr[n].id = cudaLaunchAttributeClusterDimension;  //          z = split-K partners reducing through DSMEM
+  if (cluster_z > 1) {  // thread-block cluster along z (split-K partners reduce through distributed smem)
+    attr[n].id = cudaLaunchAttributeClusterDimension;
     attr[n].val.clusterDim.x = 1;
-    attr[n].val.clusterDim.y = cluster_y;
+    attr[n].val.clusterDim.y = 1;
     attr[n].val.clusterDim.z = cluster_z;
     ++n;
   }
@@ -82,7 +82,7 @@ inline cudaError_t launch_pdl_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args&&... args) {
-  return launch_pdl_cluster2(kernel, grid, block, smem, stream, 1u, 1u, static_cast<Args&&>(args)...);
+  return launch_pdl_cluster(kernel, grid, block, smem, stream, 1u, static_cast<Args&&>(args)...);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -183,26 +183,6 @@ __device__ __forceinline__ float4 dsmem_ld_f4(uint32_t cluster_addr) {
   return v;
 }
 
-// ---- TMA multicast: one load lands in the shared memory (same CTA-relative offset) and on the mbarrier of
-// every CTA of the cluster whose bit is set in cta_mask ---------------------------------------------------
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                               uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
-                                               int c3, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
-        "h"(cta_mask)
-      : "memory");
-}
-
 // ---- proxies / fences ---------------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / TMA reads of smem)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -254,13 +234,6 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
 // commit all prior tcgen05.mma of this thread to an mbarrier (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-// commit + arrive on the same-offset mbarrier of every CTA in cta_mask (cluster-wide stage release)
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
 

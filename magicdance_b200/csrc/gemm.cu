@@ -45,11 +45,7 @@ struct GemmKParams {
   int conv;            // conv mode
   int chunks_per_tap;  // c / 64
   int w, hw;           // conv geometry
-  int cluster_reduce;  // split-K partners form a cluster (1,cy,splits) and reduce through distributed smem
-  int cy;              // N-tile partners per cluster: the A tile is loaded once per cluster (TMA multicast)
-  int a_slice_rows;    // rows of the A tile each partner loads (128 / cy)
-  int a_slice_dim;     // conv: which box dim is sliced (2 = y, 3 = batch)
-  int a_slice_len;     // conv: extent of this partner's slice along that dim
+  int cluster_reduce;  // split-K partners form a cluster (1,1,splits) and reduce through distributed smem
 };
 
 // STAGES = 3: <=108 KB, two CTAs per SM (large grids: the co-resident CTA hides the TMA round trip).
@@ -137,28 +133,20 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
   constexpr int kRedLd = BN + 4;  // fp32 row pitch of the split-K partial tile parked in shared memory
   static_assert(kBM * kRedLd * 4 <= kStages * S::kStageBytes, "partial tile must fit in the operand ring");
 
-  // cluster geometry: rank = y_local + cy * z_local (x extent is 1)
-  const bool in_cluster = (p.cy > 1) || p.cluster_reduce;
-  const uint32_t crank = in_cluster ? cluster_ctarank() : 0u;
-  const int y_local = static_cast<int>(crank) % p.cy;
-  const int z_local = static_cast<int>(crank) / p.cy;
-  const uint16_t row_mask = static_cast<uint16_t>(((1u << p.cy) - 1u) << (z_local * p.cy));  // my N-tile partners
-
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], p.cy);  // every partner that reads the multicast A slice releases the stage
+      mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&acc_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
   tc_fence_before_sync();
-  if (p.cy > 1) cluster_sync_all();  // partners' barriers must exist before anything is multicast to them
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory from here on
@@ -179,24 +167,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
         uint8_t* sa = smem + s * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
         const int kc = kc_begin + it;
-        if (p.cy > 1) {
-          // this CTA fetches rows [y_local * R, +R) of the A tile and multicasts them to all N-tile partners;
-          // the partners' slices arrive the same way, so every full barrier still counts a whole A tile + its B.
-          uint8_t* sa_slice = sa + y_local * p.a_slice_rows * 128;
-          if (p.conv) {
-            const int tap = kc / p.chunks_per_tap;
-            const int cc = kc - tap * p.chunks_per_tap;
-            const int kh = tap / 3, kw = tap - kh * 3;
-            const int dy = (p.a_slice_dim == 2) ? y_local * p.a_slice_len : 0;
-            const int db = (p.a_slice_dim == 3) ? y_local * p.a_slice_len : 0;
-            tma_load_4d_mc(sa_slice, &p.tmA, &full_bar[s], cc * kBK, kw - 1, y0 + dy + kh - 1, b0 + db, row_mask);
-          } else if (kc < p.k1_chunks) {
-            tma_load_2d_mc(sa_slice, &p.tmA, &full_bar[s], kc * kBK, m0 + y_local * p.a_slice_rows, row_mask);
-          } else {
-            tma_load_2d_mc(sa_slice, &p.tmA2, &full_bar[s], (kc - p.k1_chunks) * kBK, m0 + y_local * p.a_slice_rows,
-                           row_mask);
-          }
-        } else if (p.conv) {
+        if (p.conv) {
           const int tap = kc / p.chunks_per_tap;
           const int cc = kc - tap * p.chunks_per_tap;
           const int kh = tap / 3, kw = tap - kh * 3;
@@ -226,8 +197,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
           // advance 16 halves (32 B) along K inside the 128B swizzle row: +2 in the >>4 address field
           umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
         }
-        if (p.cy > 1) umma_commit_mc(&empty_bar[s], row_mask);  // release the stage in every partner
-        else umma_commit(&empty_bar[s]);
+        umma_commit(&empty_bar[s]);
       }
       umma_commit(&acc_bar);
     }
@@ -334,13 +304,14 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
       // sums that slice over all partners' parked partials (ld.shared::cluster), applies the epilogue
       // and stores fp16.  No global workspace, no second kernel.
       cluster_sync_all();
+      const uint32_t crank = cluster_ctarank();
       const int S_ = p.splits;
       const int R = kBM / S_;
       const int groups = BN / 8;
       const uint32_t red_base = smem_u32(smem);
       for (int item = threadIdx.x; item < R * groups; item += kGemmThreads) {
         const int rl = item / groups, cgp = item - rl * groups;
-        const int rt = z_local * R + rl;  // row inside the tile
+        const int rt = static_cast<int>(crank) * R + rl;  // row inside the tile
         const long long row = static_cast<long long>(m0) + rt;
         const int col0 = n0 + cgp * 8;
         if (row >= p.m || col0 >= p.n) continue;
@@ -349,7 +320,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = 0.f;
         for (int pr = 0; pr < S_; ++pr) {
-          const uint32_t ra = dsmem_map(off, static_cast<uint32_t>(y_local + p.cy * pr));
+          const uint32_t ra = dsmem_map(off, static_cast<uint32_t>(pr));
           const float4 a = dsmem_ld_f4(ra), b = dsmem_ld_f4(ra + 16);
           o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
           o[4] += b.x; o[5] += b.y; o[6] += b.z; o[7] += b.w;
@@ -386,11 +357,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
         }
       }
       cluster_sync_all();  // nobody leaves while a partner may still read its shared memory
-    } else if (p.cy > 1) {
-      cluster_sync_all();  // nobody leaves while a partner may still multicast into it / arrive on its barriers
     }
-  } else if (p.cy > 1) {
-    cluster_sync_all();
   }
 
   tc_fence_before_sync();
@@ -503,7 +470,6 @@ void count_launch(int n = 1);
 template <int BN, bool GEGLU, int STAGES>
 static int launch_gemm(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
   const unsigned cluster_z = kp.cluster_reduce ? static_cast<unsigned>(kp.splits) : 1u;
-  const unsigned cluster_y = static_cast<unsigned>(kp.cy);
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, GEGLU, STAGES>;
   if (!attr_set) {
@@ -511,8 +477,7 @@ static int launch_gemm(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, STAGES>::kTotal));
     attr_set = true;
   }
-  MDB_CHECK_CUDA(launch_pdl_cluster2(kern, grid, dim3(kGemmThreads), GemmSmem<BN, STAGES>::kTotal, st, cluster_y,
-                                     cluster_z, kp));
+  MDB_CHECK_CUDA(launch_pdl_cluster(kern, grid, dim3(kGemmThreads), GemmSmem<BN, STAGES>::kTotal, st, cluster_z, kp));
   count_launch();
   return MDB_OK;
 }
@@ -554,62 +519,6 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   }
 
   int rc;
-  // ---- tile width, split-K factor and N-direction cluster size (they shape the A tensor map) ----
-  int bn;
-  if (geglu) {
-    MDB_REQUIRE(g->n % 128 == 0, "mdb_gemm_f16: GEGLU needs N %% 128 == 0 (N=%d)", g->n);
-    bn = 128;
-  } else if (g->n % 160 == 0) {
-    // 160-wide tiles unless that leaves most of the 148 SMs idle; then halve the tile width
-    const long long tiles160 = (long long)((g->m + kBM - 1) / kBM) * (g->n / 160) * (g->splits > 1 ? g->splits : 1);
-    bn = (tiles160 < 100) ? 80 : 160;
-  } else {
-    bn = 128;
-  }
-  int splits = g->splits > 1 ? g->splits : 1;
-  if (splits > kp.k_chunks) splits = kp.k_chunks;
-  if (geglu) splits = 1;
-  kp.chunks_per_split = (kp.k_chunks + splits - 1) / splits;
-  splits = (kp.k_chunks + kp.chunks_per_split - 1) / kp.chunks_per_split;  // no empty splits
-  kp.splits = splits;
-  kp.ws = g->splitk_ws;
-  // 2, 4 or 8 splits: the partners form a thread-block cluster and reduce through DSMEM (one kernel);
-  // other counts go through the global fp32 workspace + finalize kernel.
-  static const bool cluster_ok = [] { const char* e = getenv("MDB_CLUSTER_SPLITK"); return !(e && e[0] == '0'); }();
-  kp.cluster_reduce = (cluster_ok && !geglu && (splits == 2 || splits == 4 || splits == 8)) ? 1 : 0;
-  if (splits > 1 && !kp.cluster_reduce) {
-    MDB_REQUIRE(g->splitk_ws != nullptr, "mdb_gemm_f16: splits > 1 needs splitk_ws");
-  }
-  // A-operand multicast: cy CTAs that differ only in their N tile form a cluster row, each loads 1/cy of the
-  // 128x64 A tile and TMA-multicasts it to the others.  The A tile is 16 KB of the 26-36 KB a CTA pulls through
-  // its ~64 B/clk L2 port per K step, so this is worth up to ~1.8x on the main loop of weight-streaming layers.
-  static const bool mc_ok = [] { const char* e = getenv("MDB_MULTICAST"); return !(e && e[0] == '0'); }();
-  const int n_tiles_y = (g->n + bn - 1) / bn;
-  const int cz = kp.cluster_reduce ? splits : 1;
-  int cy = 1;
-  if (mc_ok && !geglu && kp.chunks_per_split >= 4 && (splits == 1 || kp.cluster_reduce)) {
-    for (int c = 4; c >= 2; c >>= 1)
-      if (n_tiles_y % c == 0 && c * cz <= 8) { cy = c; break; }
-  }
-  int conv_slice_dim = 0, conv_slice_len = 0;
-  if (g->conv && cy > 1) {
-    const int hw = g->h * g->w;
-    for (; cy > 1; cy >>= 1) {  // slice the TMA box along its outermost non-unit dim so that slices are row-contiguous
-      if (hw >= kBM) {
-        const int ybox = kBM / g->w;
-        if (ybox % cy == 0 && ((ybox / cy) * g->w) % 8 == 0) { conv_slice_dim = 2; conv_slice_len = ybox / cy; break; }
-      } else {
-        const int nbox = kBM / hw;
-        if (nbox % cy == 0 && ((nbox / cy) * hw) % 8 == 0) { conv_slice_dim = 3; conv_slice_len = nbox / cy; break; }
-        if (nbox == 1 && g->h % cy == 0 && ((g->h / cy) * g->w) % 8 == 0) { conv_slice_dim = 2; conv_slice_len = g->h / cy; break; }
-      }
-    }
-  }
-  kp.cy = cy;
-  kp.a_slice_rows = kBM / cy;
-  kp.a_slice_dim = conv_slice_dim;
-  kp.a_slice_len = conv_slice_len;
-
   if (g->conv) {
     MDB_REQUIRE(g->a2 == nullptr, "mdb_gemm_f16: conv mode takes a single source");
     MDB_REQUIRE(g->c % kBK == 0 && g->k == 9 * g->c, "mdb_gemm_f16: conv needs c %% 64 == 0 and k == 9c (c=%d k=%d)",
@@ -625,7 +534,6 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
       MDB_REQUIRE(kBM % hw == 0, "mdb_gemm_f16: conv tile needs h*w | 128 (h=%d w=%d)", g->h, g->w);
       box[0] = kBK; box[1] = g->w; box[2] = g->h; box[3] = kBM / hw;
     }
-    if (cy > 1) box[conv_slice_dim] = conv_slice_len;  // each partner loads its slice of the box
     uint64_t dims[4] = {(uint64_t)g->c, (uint64_t)g->w, (uint64_t)g->h, (uint64_t)g->nb};
     uint64_t str[3] = {(uint64_t)g->c * 2, (uint64_t)g->c * g->w * 2, (uint64_t)g->c * hw * 2};
     rc = make_tmap_f16(&kp.tmA, g->a, 4, dims, str, box);
@@ -637,7 +545,7 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   } else {
     const int k1 = g->a2 ? g->k1 : g->k;
     MDB_REQUIRE(k1 % kBK == 0 && k1 > 0 && k1 <= g->k, "mdb_gemm_f16: k1=%d must be a multiple of 64 within K", k1);
-    uint32_t box[2] = {kBK, (uint32_t)(kBM / cy)};
+    uint32_t box[2] = {kBK, kBM};
     uint64_t dims[2] = {(uint64_t)k1, (uint64_t)g->m};
     uint64_t str[1] = {(uint64_t)g->lda * 2};
     rc = make_tmap_f16(&kp.tmA, g->a, 2, dims, str, box);
@@ -650,12 +558,39 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     }
     kp.k1_chunks = k1 / kBK;
   }
+
+  int bn;
+  if (geglu) {
+    MDB_REQUIRE(g->n % 128 == 0, "mdb_gemm_f16: GEGLU needs N %% 128 == 0 (N=%d)", g->n);
+    bn = 128;
+  } else if (g->n % 160 == 0) {
+    // 160-wide tiles unless that leaves most of the 148 SMs idle; then halve the tile width
+    const long long tiles160 = (long long)((g->m + kBM - 1) / kBM) * (g->n / 160) * (g->splits > 1 ? g->splits : 1);
+    bn = (tiles160 < 100) ? 80 : 160;
+  } else {
+    bn = 128;
+  }
   {
     uint32_t box[2] = {kBK, (uint32_t)bn};
     uint64_t dims[2] = {(uint64_t)g->k, (uint64_t)g->n};
     uint64_t str[1] = {(uint64_t)g->ldb * 2};
     rc = make_tmap_f16(&kp.tmB, g->b, 2, dims, str, box);
     if (rc) return rc;
+  }
+
+  int splits = g->splits > 1 ? g->splits : 1;
+  if (splits > kp.k_chunks) splits = kp.k_chunks;
+  if (geglu) splits = 1;
+  kp.chunks_per_split = (kp.k_chunks + splits - 1) / splits;
+  splits = (kp.k_chunks + kp.chunks_per_split - 1) / kp.chunks_per_split;  // no empty splits
+  kp.splits = splits;
+  kp.ws = g->splitk_ws;
+  // 2, 4 or 8 splits: the partners form a thread-block cluster and reduce through DSMEM (one kernel);
+  // other counts go through the global fp32 workspace + finalize kernel.
+  static const bool cluster_ok = [] { const char* e = getenv("MDB_CLUSTER_SPLITK"); return !(e && e[0] == '0'); }();
+  kp.cluster_reduce = (cluster_ok && !geglu && (splits == 2 || splits == 4 || splits == 8)) ? 1 : 0;
+  if (splits > 1 && !kp.cluster_reduce) {
+    MDB_REQUIRE(g->splitk_ws != nullptr, "mdb_gemm_f16: splits > 1 needs splitk_ws");
   }
 
   dim3 grid((g->m + kBM - 1) / kBM, (g->n + bn - 1) / bn, splits);
