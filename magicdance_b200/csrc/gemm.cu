@@ -60,11 +60,11 @@ struct GemmSmem {
 };
 
 __device__ __forceinline__ void epi_store_chunk(const GemmKParams& p, long long row, int col0, int ncols,
-                                                float (&v)[32]) {
+                                                float (&v)[32], const float* bias_chunk, const uint4* res_pref) {
   // v holds columns col0 .. col0+31 of `row` (fp32 accumulators); bias + residual, then fp16 store.
   // Whole groups of 8 columns go through 16-byte accesses, a ragged tail (N = 77) is scalar.
-  const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
-  const float* bp = (p.bias != nullptr) ? p.bias + brow * p.bias_batch_stride + col0 : nullptr;
+  // bias_chunk: this chunk's 32 bias values (shared or global memory) or nullptr;
+  // res_pref:   this chunk's residual, prefetched into registers during the main loop, or nullptr.
   const __half* rp = (p.residual != nullptr) ? p.residual + row * p.ldr + col0 : nullptr;
   __half* dp = p.d + row * p.ldd + col0;
 #pragma unroll
@@ -73,14 +73,14 @@ __device__ __forceinline__ void epi_store_chunk(const GemmKParams& p, long long 
       float o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = v[q * 8 + e];
-      if (bp != nullptr) {
-        const float4 b0 = *reinterpret_cast<const float4*>(bp + q * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(bp + q * 8 + 4);
+      if (bias_chunk != nullptr) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_chunk + q * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias_chunk + q * 8 + 4);
         o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
         o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
       }
       if (rp != nullptr) {
-        const uint4 r4 = *reinterpret_cast<const uint4*>(rp + q * 8);
+        const uint4 r4 = (res_pref != nullptr) ? res_pref[q] : *reinterpret_cast<const uint4*>(rp + q * 8);
         const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -101,7 +101,7 @@ __device__ __forceinline__ void epi_store_chunk(const GemmKParams& p, long long 
         const int j = q * 8 + e;
         if (j < ncols) {
           float x = v[j];
-          if (bp != nullptr) x += bp[j];
+          if (bias_chunk != nullptr) x += bias_chunk[j];
           if (rp != nullptr) x += __half2float(rp[j]);
           dp[j] = __float2half_rn(x);
         }
@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
   __shared__ __align__(8) uint64_t empty_bar[kStages];
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_bias[BN];  // this N tile's bias row (when one row serves all batches)
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
@@ -204,13 +205,33 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
   } else if (n_iter > 0) {
     // ---------------- epilogue warps 2..5 ----------------
     const int g = warp & 3;  // TMEM lane group this warp may access
-    mbar_wait(&acc_bar, 0);
-    tc_fence_after_sync();
     const long long row = static_cast<long long>(m0) + g * 32 + lane;
     const bool row_ok = row < p.m;
+    // While the main loop runs these warps are idle: fetch what the epilogue will need — the bias row into
+    // shared memory and this thread's residual row into registers — so that the tail of the kernel does not
+    // pay two dependent global-memory round trips per 32-column chunk.
+    constexpr int kResVecs = (GEGLU ? 0 : ((BN + 31) / 32) * 4);
+    uint4 res_pref[kResVecs > 0 ? kResVecs : 1];
+    const bool bias_in_smem = (p.bias != nullptr) && (p.bias_batch_stride == 0) && !p.cluster_reduce;
+    const bool res_in_regs = !GEGLU && (p.residual != nullptr) && !p.cluster_reduce && (p.splits == 1);
+    if (bias_in_smem) {
+      const int et = (warp - 2) * 32 + lane;
+      for (int j = et; j < BN; j += 128) s_bias[j] = (n0 + j < p.n) ? p.bias[n0 + j] : 0.f;
+    }
+    if constexpr (!GEGLU) {
+      if (res_in_regs && row_ok) {
+        const __half* rrow = p.residual + row * p.ldr + n0;
+#pragma unroll
+        for (int q = 0; q < kResVecs; ++q)
+          if (q * 8 + 8 <= BN && n0 + q * 8 + 8 <= p.n) res_pref[q] = *reinterpret_cast<const uint4*>(rrow + q * 8);
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps: s_bias is complete
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after_sync();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
     if constexpr (!GEGLU) {
-#pragma unroll 1
+#pragma unroll
       for (int ch = 0; ch < (BN + 31) / 32; ++ch) {
         const int col0 = n0 + ch * 32;
         if (col0 >= p.n) break;  // warp-uniform
@@ -254,7 +275,14 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
             }
           }
         } else if (row_ok) {
-          epi_store_chunk(p, row, col0, ncols, v);
+          const float* bias_chunk = nullptr;
+          if (bias_in_smem) {
+            bias_chunk = s_bias + ch * 32;
+          } else if (p.bias != nullptr) {
+            const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
+            bias_chunk = p.bias + brow * p.bias_batch_stride + col0;
+          }
+          epi_store_chunk(p, row, col0, ncols, v, bias_chunk, (res_in_regs && ncols == 32) ? &res_pref[ch * 4] : nullptr);
         }
       }
     } else {
@@ -269,7 +297,8 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
         tmem_ld_x32(taddr + pr * 64 + 32, rg);
         tmem_wait_ld();
         if (row_ok) {
-          const float* bp = (p.bias != nullptr) ? p.bias + brow * p.bias_batch_stride + col0 : nullptr;
+          const float* bp = bias_in_smem ? (s_bias + pr * 64)
+                                         : ((p.bias != nullptr) ? p.bias + brow * p.bias_batch_stride + col0 : nullptr);
           uint4* d4 = reinterpret_cast<uint4*>(p.d + row * p.ldd + (col0 >> 1));
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
