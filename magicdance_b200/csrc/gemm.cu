@@ -146,6 +146,12 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
+  // a bias row that serves all batches is a constant weight: stage it before the PDL wait (overlaps the
+  // previous kernel's tail).  Per-batch biases (timestep embedding) are produced upstream and are read later.
+  const bool bias_in_smem = (p.bias != nullptr) && (p.bias_batch_stride == 0) && !p.cluster_reduce;
+  if (bias_in_smem && warp >= 2) {
+    for (int j = threadIdx.x - 64; j < BN; j += 128) s_bias[j] = (n0 + j < p.n) ? p.bias[n0 + j] : 0.f;
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -212,12 +218,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
     // pay two dependent global-memory round trips per 32-column chunk.
     constexpr int kResVecs = (GEGLU ? 0 : ((BN + 31) / 32) * 4);
     uint4 res_pref[kResVecs > 0 ? kResVecs : 1];
-    const bool bias_in_smem = (p.bias != nullptr) && (p.bias_batch_stride == 0) && !p.cluster_reduce;
     const bool res_in_regs = !GEGLU && (p.residual != nullptr) && !p.cluster_reduce && (p.splits == 1);
-    if (bias_in_smem) {
-      const int et = (warp - 2) * 32 + lane;
-      for (int j = et; j < BN; j += 128) s_bias[j] = (n0 + j < p.n) ? p.bias[n0 + j] : 0.f;
-    }
     if constexpr (!GEGLU) {
       if (res_in_regs && row_ok) {
         const __half* rrow = p.residual + row * p.ldr + n0;
@@ -226,7 +227,6 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
           if (q * 8 + 8 <= BN && n0 + q * 8 + 8 <= p.n) res_pref[q] = *reinterpret_cast<const uint4*>(rrow + q * 8);
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps: s_bias is complete
     mbar_wait(&acc_bar, 0);
     tc_fence_after_sync();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
@@ -332,13 +332,31 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
       // cluster = the `splits` CTAs of this output tile.  CTA r owns rows [r*R, (r+1)*R) of the tile: it
       // sums that slice over all partners' parked partials (ld.shared::cluster), applies the epilogue
       // and stores fp16.  No global workspace, no second kernel.
-      cluster_sync_all();
-      const uint32_t crank = cluster_ctarank();
       const int S_ = p.splits;
       const int R = kBM / S_;
       const int groups = BN / 8;
+      const uint32_t crank = cluster_ctarank();
+      // this thread's share of the residual is known up front: fetch it before the cluster barrier
+      constexpr int kMaxItems = 4;
+      uint4 rpre[kMaxItems];
+      if (p.residual != nullptr) {
+#pragma unroll
+        for (int q = 0; q < kMaxItems; ++q) {
+          const int item = threadIdx.x + q * kGemmThreads;
+          if (item < R * groups) {
+            const int rl = item / groups, cgp = item - rl * groups;
+            const long long row = static_cast<long long>(m0) + static_cast<int>(crank) * R + rl;
+            const int col0 = n0 + cgp * 8;
+            if (row < p.m && col0 + 8 <= p.n) rpre[q] = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
+          }
+        }
+      }
+      cluster_sync_all();
       const uint32_t red_base = smem_u32(smem);
-      for (int item = threadIdx.x; item < R * groups; item += kGemmThreads) {
+#pragma unroll 1
+      for (int it_ = 0; it_ * kGemmThreads < R * groups; ++it_) {
+        const int item = threadIdx.x + it_ * kGemmThreads;
+        if (item >= R * groups) break;
         const int rl = item / groups, cgp = item - rl * groups;
         const int rt = static_cast<int>(crank) * R + rl;  // row inside the tile
         const long long row = static_cast<long long>(m0) + rt;
@@ -362,7 +380,14 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
         }
         if (ncols == 8) {
           if (p.residual != nullptr) {
-            const uint4 r4 = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
+            uint4 r4 = make_uint4(0, 0, 0, 0);
+            if (it_ < kMaxItems) {
+#pragma unroll
+              for (int q = 0; q < kMaxItems; ++q)
+                if (q == it_) r4 = rpre[q];
+            } else {
+              r4 = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
+            }
             const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {

@@ -90,14 +90,19 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __h
   const int vecs = c / 8;
   const int b = blockIdx.y;
   const float inv_n = 1.0f / (static_cast<float>(cg) * hw);
-  pdl_wait();
+  // gamma / beta are constants: park them in shared memory before the PDL wait, combine with the statistics after
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    s_ab[ch] = gamma[ch];
+    s_ab[c + ch] = beta[ch];
+  }
+  pdl_wait();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {  // same thread owns the same channels: no sync needed
     const int g = ch / cg;
     const float mean = stats[(b * 32 + g) * 2] * inv_n;
     const float var = fmaxf(stats[(b * 32 + g) * 2 + 1] * inv_n - mean * mean, 0.f);
-    const float a = rsqrtf(var + eps) * gamma[ch];
+    const float a = rsqrtf(var + eps) * s_ab[ch];
     s_ab[ch] = a;
-    s_ab[c + ch] = beta[ch] - mean * a;
+    s_ab[c + ch] = s_ab[c + ch] - mean * a;
   }
   __syncthreads();
   const int row0 = blockIdx.x * rows_per_cta;
