@@ -159,6 +159,10 @@ int mdb_timestep_embedding_f32(const int64_t* t, float* out, int32_t batch, int3
 int mdb_skinny_linear_f32(const float* x, const void* w, const float* bias, float* out, int32_t rows, int32_t n,
                           int32_t k, int32_t silu_in, int32_t silu_out, mdb_stream_t stream);
 
+/* L2 prefetch hint for a weight tensor (cp.async.bulk.prefetch.L2); no reference counterpart — it only
+ * overlaps the next layers' cold weight reads with the current layer when one frame cannot fill the GPU. */
+int mdb_prefetch_l2(const void* ptr, int64_t bytes, mdb_stream_t stream);
+
 /* layout/precision boundary: the reference passes NCHW fp32 tensors (cldm.py:1099) */
 int mdb_nchw_f32_to_nhwc_f16(const float* x, void* y, int32_t batch, int32_t c, int32_t h, int32_t w, mdb_stream_t stream);
 int mdb_nhwc_f16_to_nchw_f32(const void* x, float* y, int32_t batch, int32_t c, int32_t h, int32_t w, mdb_stream_t stream);

@@ -58,6 +58,7 @@ SIGNATURES = {
                                         c_int32, c_void_p]),
     "mdb_nchw_f32_to_nhwc_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mdb_nhwc_f16_to_nchw_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "mdb_prefetch_l2": (c_int32, [c_void_p, c_int64, c_void_p]),
     "mdb_cfg_ddim_update_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                           c_void_p, c_void_p]),
 }

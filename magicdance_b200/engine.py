@@ -278,6 +278,10 @@ def _auto_splits(m, n, k):
     return 1
 
 
+class _BankComplete(Exception):
+    """unwinds appearance_write as soon as the last norm1 state is in the bank"""
+
+
 class DenoiseEngine:
     """Runs the three networks of ControlLDMReferenceOnlyPose on one GPU."""
 
@@ -376,6 +380,10 @@ class DenoiseEngine:
         n1 = ops.layernorm(h, *a.ln1)
         if mode == "write":
             bank.append(n1)
+            if bank_batches and len(bank) >= bank_batches:
+                # the LAST bank entry has been produced: everything after it in the appearance net (this
+                # block's attentions and feed-forward, the rest of the decoder) is dead compute
+                raise _BankComplete()
         qk = ops.gemm(n1, a.wqk, splits=_auto_splits(m, 2 * c, c))
         vt = ops.gemm(a.wv, n1, splits=_auto_splits(c, m, c))  # [C, B*N] == V^T
         kw = {}
@@ -445,17 +453,19 @@ class DenoiseEngine:
         x, ctx16, key = self._prep(ref_latent, context)
         ctx_kvs = self.context_kv(net, ctx16, key)
         emb_all = self.time_bias(net, t)
-        state = {"mode": "write", "attn_i": 0, "bank": []}
-        hs = []
-        for i, blk in enumerate(net.inp):
-            x = self._run_block(net, f"input_blocks.{i}.", blk, x, None, emb_all, ctx_kvs, state)
-            hs.append(x)
-        x = self._run_block(net, "middle_block.", net.mid, x, None, emb_all, ctx_kvs, state)
         n_total = len(net.attn_layers())
-        for i, blk in enumerate(net.out):
-            if state["attn_i"] >= n_total:
-                break
-            x = self._run_block(net, f"output_blocks.{i}.", blk, x, hs.pop(), emb_all, ctx_kvs, state)
+        # in write mode `bank_batches` carries the number of bank entries after which the pass may stop
+        state = {"mode": "write", "attn_i": 0, "bank": [], "bank_batches": n_total}
+        hs = []
+        try:
+            for i, blk in enumerate(net.inp):
+                x = self._run_block(net, f"input_blocks.{i}.", blk, x, None, emb_all, ctx_kvs, state)
+                hs.append(x)
+            x = self._run_block(net, "middle_block.", net.mid, x, None, emb_all, ctx_kvs, state)
+            for i, blk in enumerate(net.out):
+                x = self._run_block(net, f"output_blocks.{i}.", blk, x, hs.pop(), emb_all, ctx_kvs, state)
+        except _BankComplete:
+            pass
         return state["bank"]
 
     def attn_geometry(self, h, w):

@@ -73,6 +73,49 @@ def _workspace(key, numel, dtype, device):
     return t
 
 
+class WeightPrefetcher:
+    """Runs ahead of a network pass on a side stream and pulls the weights of the GEMMs `distance` calls ahead
+    into L2 (mdb_prefetch_l2).  The order of GEMM calls of a pass is fixed, so the first (eager) pass records
+    (pointer, bytes) per call and later passes — including the CUDA-graph capture — replay the plan.  Pacing is by
+    events: the prefetch for call i+distance is released when call i-1 has been launched on the main stream."""
+
+    def __init__(self, device, distance=2, min_bytes=1 << 20):
+        self.stream = torch.cuda.Stream(device=device)
+        self.distance, self.min_bytes = distance, min_bytes
+        self.plans, self.key, self.i, self.recording = {}, None, 0, False
+
+    def begin(self, key):
+        self.key, self.i = key, 0
+        self.recording = key not in self.plans
+        if self.recording:
+            self.plans[key] = []
+        else:
+            self.stream.wait_stream(torch.cuda.current_stream())
+
+    def on_gemm(self, w):
+        if self.key is None:
+            return
+        plan = self.plans[self.key]
+        if self.recording:
+            plan.append((w.data_ptr(), w.numel() * 2, w))
+        else:
+            j = self.i + self.distance
+            if j < len(plan) and plan[j][1] >= self.min_bytes:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                self.stream.wait_event(ev)
+                _lib.check(_lib.load().mdb_prefetch_l2(plan[j][0], plan[j][1], self.stream.cuda_stream), "prefetch_l2")
+        self.i += 1
+
+    def end(self):
+        if self.key is not None and not self.recording:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.key = None
+
+
+PREFETCHER = None  # set by the pipeline (GraphedDenoiser) for single-frame latency runs
+
+
 def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, residual=None, epilogue=EPI_NONE,
          a2=None, conv=None, splits=1, m=None):
     """D = epilogue(A @ W^T).  a: [M, K1] fp16 (last dim contiguous, row stride arbitrary) or, with
@@ -123,6 +166,8 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
         g.splits, g.splitk_ws = splits, ws.data_ptr()
     else:
         g.splits = 1
+    if PREFETCHER is not None:
+        PREFETCHER.on_gemm(w)
     _lib.check(lib.mdb_gemm_f16(C.byref(g), _stream()), "gemm_f16")
     return out
 

@@ -181,6 +181,13 @@ class GraphedDenoiser:
         self.replayed_launches = 0
         import os
         self.side = torch.cuda.Stream(device=dev) if os.environ.get("MDB_DUAL_STREAM", "1") != "0" else None
+        # run-ahead L2 weight prefetch (one prefetcher per concurrently running network pass)
+        if os.environ.get("MDB_PREFETCH", "1") != "0":
+            dist_ = int(os.environ.get("MDB_PREFETCH_DISTANCE", "2"))
+            self.pf_main = ops.WeightPrefetcher(dev, distance=dist_)
+            self.pf_side = ops.WeightPrefetcher(dev, distance=dist_)
+        else:
+            self.pf_main = self.pf_side = None
 
     # the two bodies, written against the static buffers only
     def _step_body(self):
@@ -192,17 +199,28 @@ class GraphedDenoiser:
         t = self.t_cur.expand(b).contiguous()
         bank_kv = self.layout.views(self.bank_cur, self.tokens, 1)
         main = torch.cuda.current_stream()
+        def with_prefetch(pf, key, fn):
+            if pf is None:
+                return fn()
+            ops.PREFETCHER = pf
+            pf.begin((id(self), key))
+            try:
+                return fn()
+            finally:
+                pf.end()
+                ops.PREFETCHER = None
+
         if self.side is not None:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side), ops.workspace_lane(1):
-                pose = eng.controlnet(self.x, self.hint, t, self.ctx)
+                pose = with_prefetch(self.pf_side, "controlnet", lambda: eng.controlnet(self.x, self.hint, t, self.ctx))
             join = lambda: main.wait_stream(self.side)
         else:
-            pose = eng.controlnet(self.x, self.hint, t, self.ctx)
+            pose = with_prefetch(self.pf_side, "controlnet", lambda: eng.controlnet(self.x, self.hint, t, self.ctx))
             join = None
         if 2 * b <= 16:
-            eps_c, eps_u = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, cfg_pair=True,
-                                            before_pose=join)
+            eps_c, eps_u = with_prefetch(self.pf_main, "unet_pair", lambda: eng.unet_forward(
+                self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, cfg_pair=True, before_pose=join))
         else:
             if join:
                 join()
