@@ -357,18 +357,39 @@ class DenoiseEngine:
             y = ops.conv3x3_direct(x.data, w, bias, batch=x.b, h=x.h, w=x.w, cin=cin, cout=cout, residual=residual)
         return Act(y, x.b, x.h, x.w)
 
+    # ---- optional intra-network concurrency ---------------------------------------------------------
+    # At one or two samples per launch most kernels fill a fraction of the SMs, so independent branches of a
+    # block (the 1x1 skip conv of a ResBlock vs its GroupNorm->conv chain; the V^T projection vs the q/k
+    # projection) can run on an auxiliary stream.  aux_streams maps the workspace lane of the calling pass to
+    # (stream, lane of the auxiliary work); set by pipeline.GraphedDenoiser, captured into the step graph.
+    aux_streams = None
+
+    def _fork(self, fn):
+        """Run fn() on this lane's auxiliary stream (if any); returns (result, join)."""
+        aux = self.aux_streams.get(ops.current_lane()) if self.aux_streams else None
+        if aux is None:
+            return fn(), (lambda: None)
+        stream, lane = aux
+        main = torch.cuda.current_stream()
+        stream.wait_stream(main)
+        with torch.cuda.stream(stream), ops.workspace_lane(lane):
+            out = fn()
+        return out, (lambda: main.wait_stream(stream))
+
     def _res(self, r: ResW, x: Act, skip: Act | None, emb_all):
         x2 = None if skip is None else skip.data
+        if r.skip_w is None:
+            assert skip is None
+            res, join = x.data, (lambda: None)
+        else:
+            m = x.b * x.hw
+            res, join = self._fork(lambda: ops.gemm(x.data, r.skip_w, bias=r.skip_b, a2=x2,
+                                                    splits=_auto_splits(m, r.cout, r.cin)))
         h = ops.groupnorm(x.data, *r.gn1, batch=x.b, hw=x.hw, eps=1e-5, silu=True, x2=x2)
         bias = emb_all[:, r.emb_off:r.emb_off + r.cout]
         h = self._conv3(Act(h, x.b, x.h, x.w), r.w1, bias, cout=r.cout, bias_batch_stride=emb_all.stride(0))
         h2 = ops.groupnorm(h.data, *r.gn2, batch=x.b, hw=x.hw, eps=1e-5, silu=True)
-        if r.skip_w is None:
-            assert skip is None
-            res = x.data
-        else:
-            m = x.b * x.hw
-            res = ops.gemm(x.data, r.skip_w, bias=r.skip_b, a2=x2, splits=_auto_splits(m, r.cout, r.cin))
+        join()
         return self._conv3(Act(h2, x.b, x.h, x.w), r.w2, r.b2, cout=r.cout, residual=res)
 
     def _transformer(self, a: AttnW, x: Act, ctx_kv, mode, bank, bank_kv, bank_batches):
@@ -384,8 +405,9 @@ class DenoiseEngine:
                 # the LAST bank entry has been produced: everything after it in the appearance net (this
                 # block's attentions and feed-forward, the rest of the decoder) is dead compute
                 raise _BankComplete()
+        vt, join_v = self._fork(lambda: ops.gemm(a.wv, n1, splits=_auto_splits(c, m, c)))  # [C, B*N] == V^T
         qk = ops.gemm(n1, a.wqk, splits=_auto_splits(m, 2 * c, c))
-        vt = ops.gemm(a.wv, n1, splits=_auto_splits(c, m, c))  # [C, B*N] == V^T
+        join_v()
         kw = {}
         if mode == "read" and bank_kv is not None:
             k1, vt1, nb1, kvb1 = bank_kv

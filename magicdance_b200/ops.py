@@ -64,6 +64,10 @@ class workspace_lane:
         _ws_tag = self.prev
 
 
+def current_lane():
+    return _ws_tag
+
+
 def _workspace(key, numel, dtype, device):
     k = (key, device, _ws_tag)
     t = _ws_cache.get(k)

@@ -181,6 +181,10 @@ class GraphedDenoiser:
         self.replayed_launches = 0
         import os
         self.side = torch.cuda.Stream(device=dev) if os.environ.get("MDB_DUAL_STREAM", "1") != "0" else None
+        # auxiliary streams for independent branches inside a block (engine._fork): lane 0 (UNet pass) -> lane 2,
+        # lane 1 (ControlNet pass on the side stream) -> lane 3
+        if os.environ.get("MDB_AUX_STREAMS", "1") != "0" and batch <= 2:
+            self.eng.aux_streams = {0: (torch.cuda.Stream(device=dev), 2), 1: (torch.cuda.Stream(device=dev), 3)}
         # run-ahead L2 weight prefetch (one prefetcher per concurrently running network pass)
         # (measured on B200: no gain at one frame per GPU — 9.06 vs 8.94 ms/step — so it is opt-in: MDB_PREFETCH=1)
         if os.environ.get("MDB_PREFETCH", "0") == "1":
