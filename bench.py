@@ -228,6 +228,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     torch.set_grad_enabled(False)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the banner goes to stdout; stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = {}
     try:
