@@ -53,8 +53,8 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 // MDB_PDL=0 in the environment turns the attribute off (then griddepcontrol.* are no-ops).
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                                      cudaStream_t stream, unsigned cluster_z, Args&&... args) {
+inline cudaError_t launch_pdl_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                       cudaStream_t stream, unsigned cluster_x, unsigned cluster_z, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -63,9 +63,11 @@ inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int n = 0;
-  if (cluster_z > 1) {  // thread-block cluster along z (split-K partners reduce through distributed smem)
+  if (cluster_z > 1 || cluster_x > 1) {
+    // thread-block cluster: along z = split-K partners reducing through distributed smem,
+    // along x = the CTA pair of a cta_group::2 UMMA (two neighbouring M tiles)
     attr[n].id = cudaLaunchAttributeClusterDimension;
-    attr[n].val.clusterDim.x = 1;
+    attr[n].val.clusterDim.x = cluster_x;
     attr[n].val.clusterDim.y = 1;
     attr[n].val.clusterDim.z = cluster_z;
     ++n;
@@ -80,9 +82,14 @@ inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                      cudaStream_t stream, unsigned cluster_z, Args&&... args) {
+  return launch_pdl_cluster2(kernel, grid, block, smem, stream, 1u, cluster_z, static_cast<Args&&>(args)...);
+}
+template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args&&... args) {
-  return launch_pdl_cluster(kernel, grid, block, smem, stream, 1u, static_cast<Args&&>(args)...);
+  return launch_pdl_cluster2(kernel, grid, block, smem, stream, 1u, 1u, static_cast<Args&&>(args)...);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -158,6 +165,23 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// CTA-pair (cta_group::2) variants: the destination is THIS CTA's shared memory, the completion bytes are
+// credited to an mbarrier given as a shared::cluster address — the pair leader's `full` barrier.
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                 int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // ---- thread-block clusters / distributed shared memory ---------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -201,6 +225,16 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// CTA-pair allocation: warp w of BOTH CTAs of the pair executes these (same column range in both SMs)
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 // ---- UMMA descriptors -----------------------------------------------------------------------------
 // K-major operand tile stored as [rows][64 halves] (128-byte rows, TMA SWIZZLE_128B, 1024B-aligned):
 // 8-row groups are 1024 B apart (SBO), LBO is ignored for swizzled K-major layouts (set to 1),
@@ -235,6 +269,26 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// CTA-pair UMMA (cta_group::2): D is 256 x N — rows 0..127 in the leader's TMEM, 128..255 in the peer's; each
+// CTA's shared memory holds its own 128 A rows and N/2 of the B rows at the SAME offsets.  Issued by one thread
+// of the leader CTA only.
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the leader's prior pair-MMAs: arrives on the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
 }
 
 // ---- TMEM <-> registers (warp w may only touch lanes 32*(w%4) .. +31) -------------------------------

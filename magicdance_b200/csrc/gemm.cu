@@ -51,10 +51,15 @@ struct GemmKParams {
 // STAGES = 3: <=108 KB, two CTAs per SM (large grids: the co-resident CTA hides the TMA round trip).
 // STAGES = 6 (8 for 80-wide tiles): one CTA per SM with a ring deep enough to cover the TMA latency on
 // its own — used when the grid has at most one CTA per SM anyway and the K loop is long.
-template <int BN, int STAGES>
+// PAIR: two CTAs (a cluster of 2 along M) run ONE cta_group::2 UMMA of shape 256 x BN: each keeps its own
+// 128 A rows and only BN/2 of the B rows, so a 256 x 160 pair tile pulls 26 KB per CTA and K chunk through
+// the L2 -> SM fabric where two independent 128 x 160 tiles pull 36 KB — the fabric (~6.3 KB/clk chip-wide)
+// is what bounds the large GEMMs of this path, not the tensor pipe.
+template <int BN, int STAGES, bool PAIR = false>
 struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;
+  static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTotal = STAGES * kStageBytes + 1024;  // + alignment slack
 };
@@ -110,10 +115,11 @@ __device__ __forceinline__ void epi_store_chunk(const GemmKParams& p, long long 
   }
 }
 
-template <int BN, bool GEGLU, int kStages>
-__global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
+template <int BN, bool GEGLU, int kStages, bool PAIR = false>
+__global__ void __launch_bounds__(kGemmThreads, (kStages <= (PAIR ? 4 : 3)) ? 2 : 1)
     gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
-  using S = GemmSmem<BN, kStages>;
+  using S = GemmSmem<BN, kStages, PAIR>;
+  static_assert(!PAIR || (BN % 16 == 0 && BN <= 256), "cta_group::2 UMMA: N must be a multiple of 16, at most 256");
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
   const int n_iter = kc_end - kc_begin;
   constexpr uint32_t kTmemCols = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
   constexpr int kRedLd = BN + 4;  // fp32 row pitch of the split-K partial tile parked in shared memory
-  static_assert(kBM * kRedLd * 4 <= kStages * S::kStageBytes, "partial tile must fit in the operand ring");
+  static_assert(PAIR || kBM * kRedLd * 4 <= kStages * S::kStageBytes, "partial tile must fit in the operand ring");
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -145,7 +151,10 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
     mbar_init(&acc_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair(&tmem_base_smem, kTmemCols);
+    else tmem_alloc(&tmem_base_smem, kTmemCols);
+  }
   // a bias row that serves all batches is a constant weight: stage it before the PDL wait (overlaps the
   // previous kernel's tail).  Per-batch biases (timestep embedding) are produced upstream and are read later.
   const bool bias_in_smem = (p.bias != nullptr) && (p.bias_batch_stride == 0) && !p.cluster_reduce;
@@ -153,9 +162,11 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
     for (int j = threadIdx.x - 64; j < BN; j += 128) s_bias[j] = (n0 + j < p.n) ? p.bias[n0 + j] : 0.f;
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the partner's barriers must exist before anything is sent to them
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
+  [[maybe_unused]] const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
@@ -170,10 +181,27 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], S::kStageBytes);
         uint8_t* sa = smem + s * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
         const int kc = kc_begin + it;
+        if constexpr (PAIR) {
+          // both CTAs' bytes are credited to the LEADER's barrier, which alone announces them
+          if (pair_rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
+          const uint32_t fb = dsmem_map(smem_u32(&full_bar[s]), 0);
+          if (p.conv) {
+            const int tap = kc / p.chunks_per_tap;
+            const int cc = kc - tap * p.chunks_per_tap;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d_pair(sa, &p.tmA, fb, cc * kBK, kw - 1, y0 + kh - 1, b0);
+          } else if (kc < p.k1_chunks) {
+            tma_load_2d_pair(sa, &p.tmA, fb, kc * kBK, m0);
+          } else {
+            tma_load_2d_pair(sa, &p.tmA2, fb, (kc - p.k1_chunks) * kBK, m0);
+          }
+          tma_load_2d_pair(sb, &p.tmB, fb, kc * kBK, n0 + static_cast<int>(pair_rank) * S::kBRows);
+          continue;
+        }
+        mbar_expect_tx(&full_bar[s], S::kStageBytes);
         if (p.conv) {
           const int tap = kc / p.chunks_per_tap;
           const int cc = kc - tap * p.chunks_per_tap;
@@ -188,8 +216,8 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_iter > 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
+    if (lane == 0 && n_iter > 0 && pair_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * kBM : kBM, BN);
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
@@ -202,11 +230,14 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k) {
           // advance 16 halves (32 B) along K inside the 128B swizzle row: +2 in the >>4 address field
-          umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          if constexpr (PAIR) umma_f16_ss_pair(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          else umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);
+        if constexpr (PAIR) umma_commit_pair(&empty_bar[s]);  // frees the stage in both CTAs
+        else umma_commit(&empty_bar[s]);
       }
-      umma_commit(&acc_bar);
+      if constexpr (PAIR) umma_commit_pair(&acc_bar);
+      else umma_commit(&acc_bar);
     }
   } else if (n_iter > 0) {
     // ---------------- epilogue warps 2..5 ----------------
@@ -326,7 +357,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
     }
   }
 
-  if constexpr (!GEGLU) {
+  if constexpr (!GEGLU && !PAIR) {
     if (p.cluster_reduce) {
       // ---- split-K reduction across the cluster through distributed shared memory ----
       // cluster = the `splits` CTAs of this output tile.  CTA r owns rows [r*R, (r+1)*R) of the tile: it
@@ -415,10 +446,12 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the leader's MMAs read the partner's shared memory and TMEM
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -521,17 +554,17 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 
 void count_launch(int n = 1);
 
-template <int BN, bool GEGLU, int STAGES>
+template <int BN, bool GEGLU, int STAGES, bool PAIR = false>
 static int launch_gemm(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
   const unsigned cluster_z = kp.cluster_reduce ? static_cast<unsigned>(kp.splits) : 1u;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, GEGLU, STAGES>;
+  auto kern = gemm_tc_kernel<BN, GEGLU, STAGES, PAIR>;
+  constexpr int kSmem = GemmSmem<BN, STAGES, PAIR>::kTotal;
   if (!attr_set) {
-    MDB_CHECK_CUDA(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, STAGES>::kTotal));
+    MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
-  MDB_CHECK_CUDA(launch_pdl_cluster(kern, grid, dim3(kGemmThreads), GemmSmem<BN, STAGES>::kTotal, st, cluster_z, kp));
+  MDB_CHECK_CUDA(launch_pdl_cluster2(kern, grid, dim3(kGemmThreads), kSmem, st, PAIR ? 2u : 1u, cluster_z, kp));
   count_launch();
   return MDB_OK;
 }
@@ -613,8 +646,29 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     kp.k1_chunks = k1 / kBK;
   }
 
+  // CTA-pair (cta_group::2, 256 x BN) tiles for the GEMMs large enough to be bound by L2 -> SM traffic:
+  // no split-K, at least two M tiles, and a grid of at least `pair_min` CTAs.  Measured on B200
+  // (scripts/gpu_microbench.py pair): +4..17 % from ~256 CTAs up (eight-frame batches, the bank build),
+  // neutral to -15 % on the one-wave grids of a single frame — hence the threshold.
+  // (both switches are read per call — launches are captured into graphs, so this is off the replay path —
+  //  which lets the tests force pair tiles onto small problems.)
+  const char* pair_env = getenv("MDB_GEMM_PAIR");
+  const char* pair_min_env = getenv("MDB_GEMM_PAIR_MIN");
+  const bool pair_ok = !(pair_env && pair_env[0] == '0');
+  const long long pair_min = pair_min_env ? atoll(pair_min_env) : 256ll;
+  const int m_tiles = (g->m + kBM - 1) / kBM;
+  bool pair = pair_ok && g->splits <= 1 && m_tiles >= 2;
   int bn;
-  if (geglu) {
+  if (pair) {
+    if (geglu) bn = (g->n % 256 == 0) ? 256 : 0;
+    else if (g->n % 160 == 0) bn = 160;
+    else if (g->n % 256 == 0) bn = 256;
+    else bn = 128;
+    if (bn == 0 || (long long)((m_tiles + 1) / 2) * 2 * ((g->n + bn - 1) / bn) < pair_min) pair = false;
+  }
+  if (pair) {
+    // bn chosen above
+  } else if (geglu) {
     MDB_REQUIRE(g->n % 128 == 0, "mdb_gemm_f16: GEGLU needs N %% 128 == 0 (N=%d)", g->n);
     bn = 128;
   } else if (g->n % 160 == 0) {
@@ -625,7 +679,7 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     bn = 128;
   }
   {
-    uint32_t box[2] = {kBK, (uint32_t)bn};
+    uint32_t box[2] = {kBK, (uint32_t)(pair ? bn / 2 : bn)};  // a pair CTA stages half of the B rows
     uint64_t dims[2] = {(uint64_t)g->k, (uint64_t)g->n};
     uint64_t str[1] = {(uint64_t)g->ldb * 2};
     rc = make_tmap_f16(&kp.tmB, g->b, 2, dims, str, box);
@@ -634,7 +688,7 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
 
   int splits = g->splits > 1 ? g->splits : 1;
   if (splits > kp.k_chunks) splits = kp.k_chunks;
-  if (geglu) splits = 1;
+  if (geglu || pair) splits = 1;
   kp.chunks_per_split = (kp.k_chunks + splits - 1) / splits;
   splits = (kp.k_chunks + kp.chunks_per_split - 1) / kp.chunks_per_split;  // no empty splits
   kp.splits = splits;
@@ -647,9 +701,14 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     MDB_REQUIRE(g->splitk_ws != nullptr, "mdb_gemm_f16: splits > 1 needs splitk_ws");
   }
 
-  dim3 grid((g->m + kBM - 1) / kBM, (g->n + bn - 1) / bn, splits);
+  dim3 grid(pair ? 2 * ((m_tiles + 1) / 2) : m_tiles, (g->n + bn - 1) / bn, splits);
   const bool deep = (long long)grid.x * grid.y * grid.z <= 148 && kp.chunks_per_split >= 12;
-  if (geglu) rc = launch_gemm<128, true, 3>(kp, grid, st);
+  if (pair) {
+    if (geglu) rc = launch_gemm<256, true, 3, true>(kp, grid, st);
+    else if (bn == 160) rc = deep ? launch_gemm<160, false, 8, true>(kp, grid, st) : launch_gemm<160, false, 4, true>(kp, grid, st);
+    else if (bn == 256) rc = deep ? launch_gemm<256, false, 6, true>(kp, grid, st) : launch_gemm<256, false, 3, true>(kp, grid, st);
+    else rc = deep ? launch_gemm<128, false, 8, true>(kp, grid, st) : launch_gemm<128, false, 4, true>(kp, grid, st);
+  } else if (geglu) rc = launch_gemm<128, true, 3>(kp, grid, st);
   else if (bn == 160) rc = deep ? launch_gemm<160, false, 6>(kp, grid, st) : launch_gemm<160, false, 3>(kp, grid, st);
   else if (bn == 80) rc = deep ? launch_gemm<80, false, 8>(kp, grid, st) : launch_gemm<80, false, 3>(kp, grid, st);
   else rc = deep ? launch_gemm<128, false, 6>(kp, grid, st) : launch_gemm<128, false, 3>(kp, grid, st);

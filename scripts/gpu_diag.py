@@ -22,6 +22,7 @@ GROUPS = {
     "gemm": ("case_gemm", "case_gemm_batch_bias", "case_gemm_dual", "case_gemm_strided_out", "case_geglu"),
     "conv": ("case_conv", "case_down", "case_conv_im2col"),
     "attn": ("case_attention",),
+    "pair": ("case_pair",),
 }
 
 

@@ -96,6 +96,31 @@ def main():
             conv_case(1, 8, 8, 1280, 1280, s)
         conv_case(2, 8, 8, 2560, 1280, 16)
         conv_case(8, 8, 8, 1280, 1280, 4)
+    if which == "pair":
+        # single-CTA 128 x BN tiles vs CTA-pair (cta_group::2) 256 x BN tiles, shape by shape, at the cond+uncond
+        # batch of one frame (2) and of eight frames (16)
+        for mode in ("0", "1"):
+            os.environ["MDB_GEMM_PAIR"] = mode
+            os.environ["MDB_GEMM_PAIR_MIN"] = "1"
+            print(f"--- MDB_GEMM_PAIR={mode}", flush=True)
+            for b in (2, 16):
+                conv_case(b, 64, 64, 320, 320)
+                conv_case(b, 64, 64, 640, 320)
+                conv_case(b, 32, 32, 640, 640)
+                conv_case(b, 32, 32, 1280, 640)
+                conv_case(b, 16, 16, 1280, 1280)
+                conv_case(b, 8, 8, 1280, 1280)
+                gemm_case(b * 4096, 320, 320)
+                gemm_case(b * 4096, 320, 1280)
+                gemm_case(b * 1024, 640, 640)
+                gemm_case(b * 1024, 640, 2560)
+                gemm_case(b * 256, 1280, 1280)
+                gemm_case(b * 256, 1280, 5120)
+                for hw, c in ((4096, 320), (1024, 640), (256, 1280)):
+                    x, (wp, bp) = h(b * hw, c), pack_geglu(torch.randn(8 * c, c), torch.randn(8 * c), D)
+                    timeit(f"geglu m={b * hw} c={c}", lambda: ops.gemm(x, wp, bias=bp, epilogue=ops.EPI_GEGLU),
+                           flops=2.0 * b * hw * 8 * c * c)
+        return
     if which in ("all", "attn"):
         attn_case(1, 40, 4096, 4096)
         attn_case(1, 40, 4096, 4096, 4096)

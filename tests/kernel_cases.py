@@ -35,6 +35,23 @@ def case_gemm(m, n, k, bias=False, residual=False, splits=1, seed=0):
     return rel(out.float(), ref), 2e-3, f"gemm m={m} n={n} k={k} bias={bias} res={residual} splits={splits}"
 
 
+def case_pair(fn, *args):
+    """Runs another GEMM-family case with the CTA-pair (cta_group::2, 256 x BN) tiles forced onto it, whatever
+    the grid size (the library reads MDB_GEMM_PAIR_MIN on every call)."""
+    import os
+    old = os.environ.get("MDB_GEMM_PAIR_MIN")
+    os.environ["MDB_GEMM_PAIR_MIN"] = "1"
+    try:
+        err, tol, desc = fn(*args)
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("MDB_GEMM_PAIR_MIN", None)
+        else:
+            os.environ["MDB_GEMM_PAIR_MIN"] = old
+    return err, tol, "pair tiles: " + desc
+
+
 def case_gemm_batch_bias(batch, hw, n, k, seed=0):
     m = batch * hw
     a = _rand(m, k, seed=seed).half()
@@ -294,6 +311,20 @@ ALL_CASES = [
     (case_conv, (1, 8, 8, 2560, 1280, True, False, 8)),
     (case_conv, (2, 16, 16, 1280, 1280, True, True, 4)),
     (case_conv, (2, 32, 32, 640, 640, True, True, 2)),
+    (case_pair, (case_gemm, 384, 320, 320, True, True)),       # odd number of M tiles: the last pair is half empty
+    (case_pair, (case_gemm, 1000, 640, 1280, True, False)),    # ragged M, 160-wide halves
+    (case_pair, (case_gemm, 512, 256, 128)),                   # 256-wide pair tile
+    (case_pair, (case_gemm, 300, 384, 192, True, True)),       # 128-wide pair tile, N = 3 tiles
+    (case_pair, (case_gemm, 4096, 320, 2880, True, True)),     # long K: the ring wraps many times
+    (case_pair, (case_gemm_strided_out, 320, 77, 768)),        # ragged N inside one half
+    (case_pair, (case_gemm_batch_bias, 2, 1024, 640, 320)),
+    (case_pair, (case_gemm_dual, 1024, 640, 640, 320)),
+    (case_pair, (case_geglu, 512, 320)),
+    (case_pair, (case_geglu, 4096, 320)),
+    (case_pair, (case_conv, 1, 64, 64, 320, 320)),
+    (case_pair, (case_conv, 2, 32, 32, 640, 640, True, True)),
+    (case_pair, (case_conv, 3, 8, 8, 1280, 1280, True, True)),  # 192 rows: second CTA of the pair is half out of range
+    (case_pair, (case_conv, 2, 16, 16, 1280, 1280)),
     (case_conv_direct, (1, 64, 64, 4, 320, 1, False, True)),
     (case_conv_direct, (2, 64, 64, 320, 4, 1, False)),
     (case_conv_direct, (1, 256, 256, 3, 16, 1, True)),

@@ -12,7 +12,7 @@ def _cases():
 
 def _ids():
     from tests import kernel_cases as K
-    return [f"{f.__name__}-{'-'.join(str(x) for x in a)}" for f, a in K.ALL_CASES]
+    return [f"{f.__name__}-{'-'.join(str(getattr(x, '__name__', x)) for x in a)}" for f, a in K.ALL_CASES]
 
 
 @pytest.mark.parametrize("fn,args", _cases(), ids=_ids())
