@@ -646,15 +646,20 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     kp.k1_chunks = k1 / kBK;
   }
 
-  // CTA-pair (cta_group::2, 256 x BN) tiles for the GEMMs large enough to be bound by L2 -> SM traffic:
-  // no split-K, at least two M tiles, and a grid of at least `pair_min` CTAs.  Measured on B200
-  // (scripts/gpu_microbench.py pair): +4..17 % from ~256 CTAs up (eight-frame batches, the bank build),
-  // neutral to -15 % on the one-wave grids of a single frame — hence the threshold.
-  // (both switches are read per call — launches are captured into graphs, so this is off the replay path —
-  //  which lets the tests force pair tiles onto small problems.)
+  // CTA-pair (cta_group::2, 256 x BN) tiles — EXPERIMENTAL, opt-in with MDB_GEMM_PAIR=1: no split-K, at least
+  // two M tiles, and a grid of at least MDB_GEMM_PAIR_MIN (default 256) CTAs.  Measured on B200
+  // (scripts/gpu_microbench.py pair): +4..17 % on grids from ~256 CTAs up (eight-frame batches, the bank
+  // build), neutral to -15 % on the one-wave grids of a single frame.  Bit-for-bit the same results as the
+  // single-CTA tiles in isolation (tests/kernel_cases.py case_pair), but inside the full step — where PDL and
+  // the second stream make CTAs of OTHER tensor-memory kernels co-resident with a pair — the pair kernels
+  // dead-lock (reproduced with either PDL or the second stream on, gone with both off): the two SMs of a pair
+  // must agree on one TMEM column range while each also hosts a foreign allocation.  The fix is a persistent
+  // one-CTA-per-SM pair kernel that owns all 512 columns (double-buffered accumulators); until then the
+  // default stays off.  Both switches are read per call (launches are captured into graphs, so this is off
+  // the replay path), which lets the tests force pair tiles onto small problems.
   const char* pair_env = getenv("MDB_GEMM_PAIR");
   const char* pair_min_env = getenv("MDB_GEMM_PAIR_MIN");
-  const bool pair_ok = !(pair_env && pair_env[0] == '0');
+  const bool pair_ok = (pair_env != nullptr && pair_env[0] == '1');
   const long long pair_min = pair_min_env ? atoll(pair_min_env) : 256ll;
   const int m_tiles = (g->m + kBM - 1) / kBM;
   bool pair = pair_ok && g->splits <= 1 && m_tiles >= 2;

@@ -6,12 +6,14 @@ below launches OUR kernels through ctypes.  No function has a PyTorch/CPU fallba
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib
 
 EPI_NONE, EPI_GEGLU = 0, 1
+_GEMM_DEBUG = os.environ.get("MDB_GEMM_DEBUG", "0") == "1"
 TRACE = None  # set to a list to record (m, n, k, conv, epilogue, splits, k2) of every gemm() call (bench.py)
 
 
@@ -172,7 +174,14 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
         g.splits = 1
     if PREFETCHER is not None:
         PREFETCHER.on_gemm(w)
+    if _GEMM_DEBUG:  # MDB_GEMM_DEBUG=1: name every GEMM before it runs and wait for it (pins down a hanging shape)
+        import sys
+        print(f"gemm m={m} n={n} k={k} conv={conv} epi={epilogue} splits={g.splits} a2={a2 is not None} lda={g.lda} "
+              f"ldd={g.ldd} bias={bias is not None} bbs={g.bias_batch_stride} res={residual is not None}",
+              file=sys.stderr, flush=True)
     _lib.check(lib.mdb_gemm_f16(C.byref(g), _stream()), "gemm_f16")
+    if _GEMM_DEBUG:
+        torch.cuda.synchronize()
     return out
 
 

@@ -36,19 +36,21 @@ def case_gemm(m, n, k, bias=False, residual=False, splits=1, seed=0):
 
 
 def case_pair(fn, *args):
-    """Runs another GEMM-family case with the CTA-pair (cta_group::2, 256 x BN) tiles forced onto it, whatever
-    the grid size (the library reads MDB_GEMM_PAIR_MIN on every call)."""
+    """Runs another GEMM-family case on the opt-in CTA-pair (cta_group::2, 256 x BN) tiles, whatever the grid
+    size (the library reads MDB_GEMM_PAIR / MDB_GEMM_PAIR_MIN on every call)."""
     import os
-    old = os.environ.get("MDB_GEMM_PAIR_MIN")
-    os.environ["MDB_GEMM_PAIR_MIN"] = "1"
+    forced = {"MDB_GEMM_PAIR": "1", "MDB_GEMM_PAIR_MIN": "1"}
+    old = {k: os.environ.get(k) for k in forced}
+    os.environ.update(forced)
     try:
         err, tol, desc = fn(*args)
         torch.cuda.synchronize()
     finally:
-        if old is None:
-            os.environ.pop("MDB_GEMM_PAIR_MIN", None)
-        else:
-            os.environ["MDB_GEMM_PAIR_MIN"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     return err, tol, "pair tiles: " + desc
 
 
