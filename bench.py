@@ -260,7 +260,11 @@ def run_ours(args):
     tokens = [n for n, _ in geo]
 
     use_graph = os.environ.get("MDB_GRAPH", "1") != "0"
-    chunk = int(os.environ.get("MDB_BANK_CHUNK", "10"))
+    # timesteps per bank-build launch: this rank's share of the sequence's timesteps split into equal chunks
+    # of at most 25 (50 -> 25+25, 25 -> 25, 13 -> 13, 7 -> 7); a short last chunk would be padded to full size
+    per_rank = (min(args.steps, 50) + world - 1) // world
+    n_chunks = (per_rank + 24) // 25
+    chunk = int(os.environ.get("MDB_BANK_CHUNK", str(max(1, (per_rank + n_chunks - 1) // n_chunks))))
     gd = None
     if use_graph:
         from magicdance_b200.pipeline import GraphedDenoiser

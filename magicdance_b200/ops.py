@@ -13,6 +13,7 @@ import torch
 from . import _lib
 
 EPI_NONE, EPI_GEGLU = 0, 1
+SKINNY_MAX_ROWS = 16  # mdb_skinny_linear_f32: rows per launch
 _GEMM_DEBUG = os.environ.get("MDB_GEMM_DEBUG", "0") == "1"
 TRACE = None  # set to a list to record (m, n, k, conv, epilogue, splits, k2) of every gemm() call (bench.py)
 
@@ -320,8 +321,12 @@ def skinny_linear(x, w, bias, *, silu_in=False, silu_out=False):
     n = w.shape[0]
     assert w.shape[1] == k and x.is_contiguous() and w.is_contiguous()
     out = torch.empty((rows, n), dtype=torch.float32, device=x.device)
-    _lib.check(lib.mdb_skinny_linear_f32(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), rows, n, k,
-                                         int(silu_in), int(silu_out), _stream()), "skinny_linear_f32")
+    # the kernel keeps at most 16 activation rows in registers per weight row; taller inputs (more than eight
+    # frames per batch, or more than 16 timesteps per bank-build chunk) go through it 16 rows at a time
+    for r0 in range(0, rows, SKINNY_MAX_ROWS):
+        r = min(SKINNY_MAX_ROWS, rows - r0)
+        _lib.check(lib.mdb_skinny_linear_f32(x[r0:].data_ptr(), w.data_ptr(), _ptr(bias), out[r0:].data_ptr(), r, n, k,
+                                             int(silu_in), int(silu_out), _stream()), "skinny_linear_f32")
     return out
 
 

@@ -227,7 +227,8 @@ def case_attention(batch, heads, d, nq, n0, n1=0, kv1_batches=1, bank_batches=No
 
 
 def case_time_path(batch, seed=0):
-    t = torch.tensor([981, 441, 1, 999, 500, 21, 7, 123][:batch], dtype=torch.long, device=DEV)
+    base = [981, 441, 1, 999, 500, 21, 7, 123]
+    t = torch.tensor([(base[i % 8] + 13 * (i // 8)) % 1000 for i in range(batch)], dtype=torch.long, device=DEV)
     emb = ops.timestep_embedding(t, 320)
     half = 160
     freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=DEV) / half)
@@ -278,6 +279,7 @@ ALL_CASES = [
     (case_add, (2, 64 * 1280, True)),
     (case_upsample, (2, 8, 8, 1280)),
     (case_time_path, (2,)),
+    (case_time_path, (37,)),  # more rows than one skinny-linear launch holds (16)
     (case_cfg_ddim, ()),
     (case_layernorm, (4096, 320)),
     (case_layernorm, (300, 640)),
