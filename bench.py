@@ -258,11 +258,8 @@ def run_ours(args):
     tokens = [n for n, _ in geo]
 
     use_graph = os.environ.get("MDB_GRAPH", "1") != "0"
-    # timesteps per bank-build launch: this rank's share of the sequence's timesteps split into equal chunks
-    # of at most 25 (50 -> 25+25, 25 -> 25, 13 -> 13, 7 -> 7); a short last chunk would be padded to full size
-    per_rank = (min(args.steps, 50) + world - 1) // world
-    n_chunks = (per_rank + 24) // 25
-    chunk = int(os.environ.get("MDB_BANK_CHUNK", str(max(1, (per_rank + n_chunks - 1) // n_chunks))))
+    # timesteps per bank-build launch (parallel.bank_chunk_size: equal chunks of <= 25 of this rank's share)
+    chunk = int(os.environ.get("MDB_BANK_CHUNK", str(parallel.bank_chunk_size(min(args.steps, 50), world))))
     gd = None
     if use_graph:
         from magicdance_b200.pipeline import GraphedDenoiser

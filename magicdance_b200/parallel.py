@@ -64,6 +64,15 @@ def bank_storage(slots: int, layout: BankLayout, device, world: int = 1):
     return local, gathered
 
 
+
+def bank_chunk_size(n_timesteps: int, world: int, max_chunk: int = 25) -> int:
+    """Timesteps per appearance-pass launch: a rank's share of the sequence's timesteps (ceil(n/world)) is
+    split into equal chunks of at most `max_chunk` (50 -> 25+25, 25 -> 25, 13 -> 13, 7 -> 7).  Equal, because
+    the captured bank-build graph has a fixed batch and a short last chunk would be padded to full size."""
+    per_rank = max(1, (n_timesteps + world - 1) // world)
+    n_chunks = (per_rank + max_chunk - 1) // max_chunk
+    return (per_rank + n_chunks - 1) // n_chunks
+
 def build_and_gather_bank(indices: Sequence[int], layout: BankLayout,
                           build_fn: Callable[[List[int], torch.Tensor], None], device, world: int = 1, rank: int = 0,
                           group=None, chunk: int = 10, storage=None) -> Dict[int, torch.Tensor]:

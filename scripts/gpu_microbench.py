@@ -99,7 +99,7 @@ def main():
     if which == "pair":
         # single-CTA 128 x BN tiles vs CTA-pair (cta_group::2) 256 x BN tiles, shape by shape, at the cond+uncond
         # batch of one frame (2) and of eight frames (16)
-        for mode in ("0", "1"):
+        for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("0", "1")):
             os.environ["MDB_GEMM_PAIR"] = mode
             os.environ["MDB_GEMM_PAIR_MIN"] = "1"
             print(f"--- MDB_GEMM_PAIR={mode}", flush=True)

@@ -39,7 +39,8 @@ def case_pair(fn, *args):
     """Runs another GEMM-family case on the opt-in CTA-pair (cta_group::2, 256 x BN) tiles, whatever the grid
     size (the library reads MDB_GEMM_PAIR / MDB_GEMM_PAIR_MIN on every call)."""
     import os
-    forced = {"MDB_GEMM_PAIR": "1", "MDB_GEMM_PAIR_MIN": "1"}
+    # MDB_TEST_PAIR_MODE: "1" = one pair tile per cluster launch, "2" = the persistent pair kernel
+    forced = {"MDB_GEMM_PAIR": os.environ.get("MDB_TEST_PAIR_MODE", "1"), "MDB_GEMM_PAIR_MIN": "1"}
     old = {k: os.environ.get(k) for k in forced}
     os.environ.update(forced)
     try:

@@ -27,7 +27,7 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     from magicdance_b200 import build
     path = build.build()
     sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
-    for mnem in ("UTCHMMA", "LDTM", "STTM", "UTMALDG"):
+    for mnem in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST"):
         assert mnem in sass, f"{mnem} (tcgen05 / TMA) missing from the compiled kernels"
     assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync path must not be present"
 
@@ -106,3 +106,10 @@ def test_sharding_helpers():
     for r, sh in enumerate(shares):
         for s, ix in enumerate(sh):
             assert table[ix] == (r, s)
+    # bank-build batches: equal chunks of at most 25 of the rank's share, never more launches than needed
+    assert [P.bank_chunk_size(50, w) for w in (1, 2, 4, 8)] == [25, 25, 13, 7]
+    assert P.bank_chunk_size(3, 1) == 3 and P.bank_chunk_size(1, 8) == 1 and P.bank_chunk_size(51, 1) == 17
+    for n in range(1, 60):
+        for w in (1, 2, 3, 8):
+            c, share = P.bank_chunk_size(n, w), (n + w - 1) // w
+            assert 1 <= c <= 25 and -(-share // c) == -(-share // 25)
