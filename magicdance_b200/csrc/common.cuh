@@ -107,10 +107,10 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------
-// Every kernel of this library starts with pdl_launch_dependents() (the NEXT kernel in the stream may
+// Every kernel of this library (except the persistent gemm_pairp_kernel) starts with pdl_launch_dependents() (the NEXT kernel in the stream may
 // begin its prologue: barrier init, TMEM alloc, descriptor prefetch, index math) and calls pdl_wait()
 // before it touches global memory (waits until the PREVIOUS kernel has completed and flushed).  With
-// ~900 small kernels per denoise step this hides most of the launch-to-launch latency.
+// ~650 small kernels per denoise step this was meant to hide launch-to-launch latency (measured: neutral).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

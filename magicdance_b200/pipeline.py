@@ -152,7 +152,7 @@ def build_bank_slots(eng: DenoiseEngine, ref_latent, t_vec, context, layout, tok
 
 class GraphedDenoiser:
     """The whole DDIM step and the (timestep-batched) appearance-bank build captured once as CUDA
-    graphs and replayed: at batch 1 the step is ~1400 small kernels, so launch latency and Python
+    graphs and replayed: at batch 1 the step is ~650 small kernels, so launch latency and Python
     would otherwise dominate.  Everything timestep-dependent is read from device
     memory refreshed by tiny copies before each replay (the timestep, the DDIM coefficient row, the
     bank K/V of that timestep), so ONE graph serves every step."""
