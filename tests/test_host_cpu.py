@@ -113,3 +113,27 @@ def test_sharding_helpers():
         for w in (1, 2, 3, 8):
             c, share = P.bank_chunk_size(n, w), (n + w - 1) // w
             assert 1 <= c <= 25 and -(-share // c) == -(-share // 25)
+
+
+def test_header_is_plain_c_and_matches_the_ctypes_structs(tmp_path):
+    """include/magicdance_b200.h must compile as C99 (it is what a cgo/JNI/ctypes host binds) and the
+    descriptor structs must have exactly the layout magicdance_b200/_lib.py declares."""
+    import ctypes as C
+    import os
+    from magicdance_b200 import _lib
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "magicdance_b200.h"', 'int main(void) {']
+    for cname, cls in (("mdb_gemm_desc", _lib.GemmDesc), ("mdb_attn_desc", _lib.AttnDesc)):
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in (("mdb_gemm_desc", _lib.GemmDesc), ("mdb_attn_desc", _lib.AttnDesc)):
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
