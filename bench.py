@@ -163,7 +163,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def roofline_probe(torch, ops, trace, peaks):
+def roofline_probe(torch, ops, trace, peaks, frames_per_gpu=1):
     """Replays every distinct tensor-core GEMM/conv launch of one step standalone, L2 flushed before
     each launch, CUDA-event timed; achieved = sum(2MNK) / sum(avg duration x count)."""
     from collections import Counter
@@ -201,16 +201,22 @@ def roofline_probe(torch, ops, trace, peaks):
     ach = tot_fl / tot_t / 1e12
     top = [{"shape_mnk_conv_splits": list(map(int, r[2][:3])) + [bool(r[2][3]), int(r[2][4])], "count": r[3],
             "ms_total": r[1] * 1e3, "tflops": r[0] / r[1] / 1e12} for r in rows[:6]]
-    traffic = None
+    # DRAM bytes per launch of the family (dram__bytes_read.sum + dram__bytes_write.sum, ncu): a committed
+    # capture of the one-frame step (profiles/traffic.json); other batch sizes have no capture -> null
+    traffic, traffic_detail = None, None
     try:
         with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("gemm_tc_kernel")
+            traffic_detail = json.load(f).get("gemm_tc_kernel")
+        if traffic_detail is not None and frames_per_gpu == 1:
+            traffic = float(traffic_detail["dram_bytes_per_launch_avg"])
+        else:
+            traffic_detail = None
     except Exception:  # noqa: BLE001
-        pass
+        traffic, traffic_detail = None, None
     return {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + 3x3 implicit-GEMM conv)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1590",
-            "traffic": traffic, "gemm_gflop_per_step": tot_fl / 1e9, "gemm_ms_per_step_isolated": tot_t * 1e3,
+            "traffic": traffic, "traffic_detail": traffic_detail, "gemm_gflop_per_step": tot_fl / 1e9, "gemm_ms_per_step_isolated": tot_t * 1e3,
             "launches_per_step": int(sum(cnt.values())), "top_by_time": top}
 
 
@@ -406,7 +412,7 @@ def run_ours(args):
         pipe.step(x_host.cuda(), 49, ctx, hint_, bank_)
         torch.cuda.synchronize()
         trace, ops.TRACE = ops.TRACE, None
-        line["roofline"] = roofline_probe(torch, ops, trace, peaks)
+        line["roofline"] = roofline_probe(torch, ops, trace, peaks, frames_per_gpu=B)
     if sd is not None:
         torch.set_num_threads(host_threads())
         csec = cpu_port_step_seconds(sd, L, 1, 0, torch)
