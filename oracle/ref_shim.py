@@ -133,10 +133,20 @@ def load_reference():
         if k == "model_lib" or k.startswith("model_lib."):
             raise RuntimeError("a different `model_lib` is already imported in this process; "
                                "run the reference shim in its own process")
-    sys.path.insert(0, REFERENCE_ROOT)
+    # The reference's `model_lib` is a namespace package (no __init__.py); a regular package of the same name
+    # anywhere on sys.path — this repo's drop-in tree — would win regardless of order.  Hide every such entry
+    # while `model_lib` is first bound; later submodule imports go through the bound package's __path__.
+    saved_path = list(sys.path)
+    sys.path[:] = [REFERENCE_ROOT] + [
+        e for e in saved_path
+        if e != REFERENCE_ROOT and not os.path.isfile(os.path.join(e or os.getcwd(), "model_lib", "__init__.py"))]
     _install_stubs()
     import importlib
 
+    try:
+        importlib.import_module("model_lib.ControlNet")
+    finally:
+        sys.path[:] = [REFERENCE_ROOT] + [e for e in saved_path if e != REFERENCE_ROOT]
     attention = importlib.import_module("model_lib.ControlNet.ldm.modules.attention")
     assert attention.XFORMERS_IS_AVAILBLE is False
     xf = _mod("xformers")
