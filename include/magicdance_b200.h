@@ -163,6 +163,12 @@ int mdb_skinny_linear_f32(const float* x, const void* w, const float* bias, floa
  * overlaps the next layers' cold weight reads with the current layer when one frame cannot fill the GPU. */
 int mdb_prefetch_l2(const void* ptr, int64_t bytes, mdb_stream_t stream);
 
+/* Row softmax in place over fp16 logits x[rows][cols] (row pitch ld elements), fp32 arithmetic:
+ * x <- softmax(scale * x) along the columns.  The single-head, 512-channel attention of the first-stage VAE's
+ * middle block (ldm/modules/diffusionmodules/model.py:186-193: torch.bmm -> * c^-0.5 -> softmax) is run as
+ * GEMM -> this -> GEMM, its head dimension being outside the fused attention kernel's range (<= 160). */
+int mdb_softmax_rows_f16(void* x, int64_t ld, int32_t rows, int32_t cols, float scale, mdb_stream_t stream);
+
 /* layout/precision boundary: the reference passes NCHW fp32 tensors (cldm.py:1099) */
 int mdb_nchw_f32_to_nhwc_f16(const float* x, void* y, int32_t batch, int32_t c, int32_t h, int32_t w, mdb_stream_t stream);
 int mdb_nhwc_f16_to_nchw_f32(const void* x, float* y, int32_t batch, int32_t c, int32_t h, int32_t w, mdb_stream_t stream);

@@ -59,6 +59,7 @@ SIGNATURES = {
     "mdb_nchw_f32_to_nhwc_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mdb_nhwc_f16_to_nchw_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mdb_prefetch_l2": (c_int32, [c_void_p, c_int64, c_void_p]),
+    "mdb_softmax_rows_f16": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p]),
     "mdb_cfg_ddim_update_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                           c_void_p, c_void_p]),
 }

@@ -470,6 +470,84 @@ extern "C" int mdb_device_check(void) {
   return MDB_OK;
 }
 
+namespace {
+// one CTA per row; three passes over the row (max, sum of exp2, normalise) — rows of a few KB stay in L1/L2
+__global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, long long ld, int cols, float scale_log2) {
+  mdb::pdl_launch_dependents();
+  mdb::pdl_wait();
+  __shared__ float red[8];
+  __shared__ float bcast;
+  __half* row = x + static_cast<long long>(blockIdx.x) * ld;
+  const int vecs = cols >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < vecs; v += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + v * 8);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      m = fmaxf(m, fmaxf(f.x, f.y));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int w = 1; w < 8; ++w) t = fmaxf(t, red[w]);
+    bcast = t;
+  }
+  __syncthreads();
+  m = bcast * scale_log2;  // scale > 0: the maximum of the scaled row
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < vecs; v += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + v * 8);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      sum += exp2f(fmaf(f.x, scale_log2, -m)) + exp2f(fmaf(f.y, scale_log2, -m));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();  // red[] / bcast of the first reduction have been consumed
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    bcast = 1.0f / t;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  for (int v = threadIdx.x; v < vecs; v += blockDim.x) {
+    uint4 u = *reinterpret_cast<const uint4*>(row + v * 8);
+    __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      h2[e] = __floats2half2_rn(exp2f(fmaf(f.x, scale_log2, -m)) * inv, exp2f(fmaf(f.y, scale_log2, -m)) * inv);
+    }
+    *reinterpret_cast<uint4*>(row + v * 8) = u;
+  }
+}
+}  // namespace
+
+extern "C" int mdb_softmax_rows_f16(void* x, int64_t ld, int32_t rows, int32_t cols, float scale, mdb_stream_t stream) {
+  MDB_REQUIRE(x != nullptr && rows > 0 && cols > 0, "mdb_softmax_rows_f16: bad arguments");
+  MDB_REQUIRE(cols % 8 == 0 && ld % 8 == 0 && ld >= cols && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+              "mdb_softmax_rows_f16: cols and ld must be multiples of 8, ld >= cols, x 16-byte aligned (cols=%d)", cols);
+  MDB_REQUIRE(scale > 0.f, "mdb_softmax_rows_f16: scale must be positive");
+  MDB_CHECK_CUDA(mdb::launch_pdl(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0,
+                                 static_cast<cudaStream_t>(stream), static_cast<__half*>(x), static_cast<long long>(ld),
+                                 cols, scale * 1.4426950408889634f));
+  mdb::count_launch();
+  return MDB_OK;
+}
+
 extern "C" int mdb_prefetch_l2(const void* ptr, int64_t bytes, mdb_stream_t stream) {
   MDB_REQUIRE(ptr != nullptr && bytes > 0 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "mdb_prefetch_l2: bad arguments");
   const long long pieces = (bytes + 16383) / 16384;

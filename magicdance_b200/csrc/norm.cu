@@ -64,7 +64,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __h
     }
     atomicAdd(&sh[g_first], sa);
     atomicAdd(&sh[32 + g_first], qa);
-    if ((v * 8 + 7) / cg != g_first) {  // cg >= 8 so a vector spans at most two groups
+    if ((v * 8 + 7) / cg != g_first) {  // cg >= 8 or cg == 4: a vector spans at most two groups
       atomicAdd(&sh[g_first + 1], sb);
       atomicAdd(&sh[32 + g_first + 1], qb);
     }
@@ -187,8 +187,10 @@ extern "C" int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int
   const int c = c1 + (x2 ? c2 : 0);
   if (!x2) c2 = 0;
   MDB_REQUIRE(x1 && y && gamma && beta && stats_ws, "mdb_groupnorm_f16: null pointer");
-  MDB_REQUIRE(c % 32 == 0 && c1 % 8 == 0 && c2 % 8 == 0 && c / 32 >= 8,
-              "mdb_groupnorm_f16: channels must be multiples of 8, c %% 32 == 0 and c/32 >= 8 (c1=%d c2=%d)", c1, c2);
+  // a thread's 8-channel vector may straddle at most two groups: 8 or more channels per group, or exactly 4
+  // (the first-stage VAE's 128-channel level), where every vector is exactly two whole groups
+  MDB_REQUIRE(c % 32 == 0 && c1 % 8 == 0 && c2 % 8 == 0 && (c / 32 >= 8 || c / 32 == 4),
+              "mdb_groupnorm_f16: channels must be multiples of 8, c %% 32 == 0 and c/32 >= 8 or == 4 (c1=%d c2=%d)", c1, c2);
   MDB_REQUIRE(c / 8 <= 512, "mdb_groupnorm_f16: too many channels (%d)", c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!stats_prezeroed) MDB_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * batch * 64, st));

@@ -330,6 +330,16 @@ def skinny_linear(x, w, bias, *, silu_in=False, silu_out=False):
     return out
 
 
+def softmax_rows(x, scale=1.0):
+    """in place: x[r, :] <- softmax(scale * x[r, :]) (fp16 storage, fp32 arithmetic)"""
+    lib = _lib.load()
+    _chk(x, torch.float16, "x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    _lib.check(lib.mdb_softmax_rows_f16(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], float(scale), _stream()),
+               "softmax_rows_f16")
+    return x
+
+
 def nchw_f32_to_nhwc_f16(x, out=None):
     lib = _lib.load()
     _chk(x, torch.float32, "x")

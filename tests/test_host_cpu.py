@@ -137,3 +137,65 @@ def test_header_is_plain_c_and_matches_the_ctypes_structs(tmp_path):
         assert int(got[cname]) == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
+def test_vae_decoder_packing_consumes_every_decoder_tensor():
+    """host logic of the (GPU-unvalidated, opt-in) VAE decoder: the repack reads every
+    first_stage_model.{post_quant_conv,decoder}.* tensor of the reference state dict exactly once, and the folds
+    (1/scale_factor into post_quant_conv, c^-0.5 into q, the v bias into proj_out) are the ones the oracle implies."""
+    import json
+    import os
+    import torch
+    from magicdance_b200 import synth
+    from magicdance_b200.vae import PackedVaeDecoder, PREFIX, SCALE_FACTOR
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(here, "magicdance_b200", "vae_manifest.json")) as f:
+        manifest = json.load(f)
+    sd = synth.synth_state_dict(manifest, seed=0)
+    p = PackedVaeDecoder(sd, "cpu")
+    want = {k for k in manifest if k.startswith(PREFIX + "decoder.") or k.startswith(PREFIX + "post_quant_conv.")}
+    assert sorted(p.consumed) == sorted(want) and len(set(p.consumed)) == len(p.consumed)
+    assert tuple(p.in_w.shape) == (512, 36) and tuple(p.out_w.shape) == (3, 9 * 128) and p.c_mid == 512
+    assert [r.cout for lvl in (3, 2, 1, 0) for r in p.up[lvl][0]] == [512] * 6 + [256] * 3 + [128] * 3
+    assert p.up[0][1] is None and all(p.up[lvl][1] is not None for lvl in (1, 2, 3))
+    # centre-tap 1x1 with the 1/scale fold
+    w = sd[PREFIX + "post_quant_conv.weight"][:, :, 0, 0] / SCALE_FACTOR
+    got = p.pq_w.float().reshape(4, 3, 3, 4)
+    assert torch.allclose(got[:, 1, 1, :], w.half().float()) and float(got.abs().sum() - got[:, 1, 1, :].abs().sum()) == 0.0
+    # proj_out(P (V + 1 bv^T)) == proj_out(P V) + Wp bv + bp
+    c = 512
+    wp = sd[PREFIX + "decoder.mid.attn_1.proj_out.weight"].reshape(c, c)
+    bias = sd[PREFIX + "decoder.mid.attn_1.proj_out.bias"] + wp @ sd[PREFIX + "decoder.mid.attn_1.v.bias"]
+    assert torch.allclose(p.bp, bias, atol=1e-6)
+    assert torch.allclose(p.wq.float(), (sd[PREFIX + "decoder.mid.attn_1.q.weight"].reshape(c, c) * c ** -0.5).half().float())
+
+
+def test_vae_decoder_orchestration_matches_the_oracle_with_cpu_test_doubles(monkeypatch):
+    """The VAE decoder's host logic (magicdance_b200/vae.py: operand order, layouts, the three folds, the
+    GEMM -> softmax -> GEMM attention) run on tests/fake_ops.py — PyTorch stand-ins that read the same packed
+    layouts as the kernels — must reproduce the pinned oracle / the reference golden at latent 16.  The CUDA
+    kernels are not exercised here (tests/test_kernels_gpu.py, scripts/gpu_vae_parity.py)."""
+    import json
+    import os
+    import numpy as np
+    import torch
+    from magicdance_b200 import ops, synth, vae
+    from oracle import vae_restatement as V
+    from tests import fake_ops
+    for name in ("gemm", "conv3x3_direct", "groupnorm", "upsample2x", "softmax_rows", "nchw_f32_to_nhwc_f16",
+                 "nhwc_f16_to_nchw_f32", "im2col3x3"):
+        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(here, "magicdance_b200", "vae_manifest.json")) as f:
+        manifest = json.load(f)
+    torch.set_grad_enabled(False)
+    sd = synth.synth_state_dict(manifest, seed=0)
+    dec = vae.VaeDecoder.__new__(vae.VaeDecoder)  # no device check: the test doubles run on the CPU
+    dec.p = vae.PackedVaeDecoder(sd, "cpu")
+    z, _, _ = V.vae_inputs(2, 16)
+    img = dec._decode(z)
+    gold = torch.from_numpy(np.load(os.path.join(here, "tests", "golden", "vae16.npz"))["vae16/decoded"])
+    err = float((img.double() - gold.double()).norm() / gold.double().norm())
+    assert tuple(img.shape) == (2, 3, 128, 128) and err <= 5e-3, err
+    with __import__("pytest").raises(RuntimeError, match="no CPU fallback"):
+        dec.decode(z)  # the public entry refuses CPU tensors
