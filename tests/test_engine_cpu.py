@@ -1,0 +1,70 @@
+"""Host logic of the denoiser (magicdance_b200/engine.py + pipeline.py) on the CPU.
+
+Every `magicdance_b200.ops` entry point the engine calls is replaced by a PyTorch stand-in from tests/fake_ops.py
+that reads the SAME packed layouts as the CUDA kernels (NHWC fp16 activations, tap-major conv weights, interleaved
+GEGLU rows, transposed V, per-batch bias rows, dual-source A ...).  What is checked here is the orchestration — the
+block plan walk, weight packing, bank projection and its two-source attention, pose-residual bookkeeping, the
+cond/uncond paired batch, the DDIM update — against the golden vectors of the UNMODIFIED reference.  The kernels
+themselves are checked on the GPU (tests/test_kernels_gpu.py, tests/test_parity_gpu.py)."""
+import pytest
+import torch
+
+from oracle import synth
+from tests import fake_ops
+from tests import golden_util as G
+
+TOL = 5e-3  # fp16 storage (emulated by the stand-ins) vs the fp32 reference
+
+_PATCHED = ("gemm", "attention", "conv3x3_direct", "groupnorm", "layernorm", "upsample2x", "add", "im2col3x3",
+            "timestep_embedding", "skinny_linear", "nchw_f32_to_nhwc_f16", "nhwc_f16_to_nchw_f32", "softmax_rows",
+            "ensure_device", "gn_ring_reset")
+
+
+@pytest.fixture()
+def engine(monkeypatch):
+    from magicdance_b200 import ops
+    from magicdance_b200.engine import DenoiseEngine
+    for name in _PATCHED:
+        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    torch.set_grad_enabled(False)
+    return DenoiseEngine(synth.synth_state_dict(seed=0), device="cpu")
+
+
+def test_apply_model_orchestration_matches_reference_small32(engine):
+    g = G.load("small32")
+    inp = G.small32_inputs()
+    eps_c, bank, pose, _ = engine.apply_model(inp["x"], inp["t"], inp["context"], inp["pose"], inp["ref"], uc=False,
+                                              return_parts=True)
+    assert len(bank) == 16 and len(pose) == 13
+    for i, b in enumerate(bank):  # the appearance net's norm1 states: ours [B*N, C], the reference's (B, N, C)
+        shape = tuple(int(v) for v in g[f"small32/bank{i}/shape"])
+        G.check_summary(g, f"small32/bank{i}", b.reshape(shape), TOL)
+    for i, p_ in enumerate(pose):  # 13 ControlNet residuals: ours NHWC [B*H*W, C], the reference's NCHW
+        bsz, c, h, w = (int(v) for v in g[f"small32/pose{i}/shape"])
+        G.check_summary(g, f"small32/pose{i}", p_.reshape(bsz, h, w, c).permute(0, 3, 1, 2), TOL)
+    e_c = G.rel_l2(eps_c, torch.from_numpy(g["small32/eps_c"]))
+    eps_u = engine.apply_model(inp["x"], inp["t"], inp["context"], inp["pose"], None, uc=True)
+    e_u = G.rel_l2(eps_u, torch.from_numpy(g["small32/eps_u"]))
+    assert e_c <= TOL and e_u <= TOL, (e_c, e_u)
+    assert G.rel_l2(eps_c, eps_u) > 1e-2  # the two branches really differ
+
+
+def test_sampler_step_orchestration_matches_reference_full64(engine, monkeypatch):
+    """One full p_sample_ddim (ddim.py:518-645; index 49, t = 981, CFG 7) at the headline size through
+    pipeline.DenoisePipeline.step — bank build, K/V projection, cached hint features, the paired cond/uncond
+    UNet batch and the fused update — against the unmodified reference's x_prev / pred_x0 / eps."""
+    from magicdance_b200 import ops
+    from magicdance_b200.pipeline import DenoisePipeline
+    monkeypatch.setattr(ops, "cfg_ddim_update", fake_ops.cfg_ddim_update)
+    g = G.load("full64")
+    inp = G.full64_inputs()
+    pipe = DenoisePipeline(engine, ddim_steps=50, scale=7.0, eta=0.0)
+    assert int(pipe.t_dev[49]) == int(inp["t"][0]) == 981
+    bank_kv = pipe.reference_bank(inp["ref"], inp["context"], 49)
+    hint = pipe.hint(inp["pose"])
+    x_prev, pred_x0, eps_c, eps_u = pipe.step(inp["x"], 49, inp["context"], hint, bank_kv)
+    errs = {k: G.rel_l2(v, torch.from_numpy(g["full64/" + k]))
+            for k, v in (("eps_c", eps_c), ("eps_u", eps_u), ("x_prev", x_prev), ("pred_x0", pred_x0))}
+    assert errs["eps_c"] <= TOL and errs["eps_u"] <= TOL, errs
+    # CFG 7 amplifies the difference of two nearly equal fp16-rounded fields (ddim.py:605)
+    assert errs["x_prev"] <= 2 * TOL and errs["pred_x0"] <= 4 * TOL, errs
