@@ -16,6 +16,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from .. import ops
 from ..engine import NetConfig, PackedNet, block_plan
 
 
@@ -238,9 +239,7 @@ class UNetModel(nn.Module):
 
     def packed(self, device=None) -> PackedNet:
         dev = torch.device(device) if device is not None else next(self.parameters()).device
-        if dev.type != "cuda":
-            raise RuntimeError("magicdance_b200: the networks run only on an sm_100 CUDA device — move the model to "
-                               "the GPU first (there is no CPU/PyTorch fallback for the hot path)")
+        ops.require_cuda(dev)
         if self._packed is None or self._packed.device != dev:
             self._packed = PackedNet(self.state_dict(), "", self.cfg, self._kind, dev)
         return self._packed

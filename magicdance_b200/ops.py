@@ -33,6 +33,13 @@ def _chk(t: torch.Tensor, dtype, name):
         raise RuntimeError(f"magicdance_b200: {name} must be {dtype}, got {t.dtype}")
 
 
+def require_cuda(device):
+    """The single place that decides where the networks may live: an sm_100 CUDA device, nothing else."""
+    if torch.device(device).type != "cuda":
+        raise RuntimeError("magicdance_b200: the networks run only on an sm_100 CUDA device — move the model to "
+                           "the GPU first (there is no CPU/PyTorch fallback for the hot path)")
+
+
 def ensure_device():
     lib = _lib.load()
     if not torch.cuda.is_available():

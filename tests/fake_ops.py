@@ -182,3 +182,7 @@ def cfg_ddim_update(x, eps_c, eps_u, coef, noise=None, x_prev=None, pred_x0=None
     if noise is not None:
         xp = xp + sigma * noise
     return xp, p0
+
+
+def require_cuda(device):
+    return None  # the stand-ins run wherever the tensors are

@@ -74,3 +74,37 @@ def test_strict_load_of_a_reference_checkpoint_layout(model):
     missing, unexpected = model.load_state_dict(sd, strict=True)
     assert not missing and not unexpected
     assert model.model.diffusion_model._packed is None  # packed fp16 copies are invalidated by a load
+
+
+def test_dropin_apply_model_orchestration_matches_reference_small32(model, monkeypatch):
+    """The drop-in module tree end to end on the CPU: reference-layout state dict -> strict load -> lazily packed
+    networks -> engine -> apply_model(x, t, cond dict, reference latent), with the kernels replaced by the
+    layout-faithful PyTorch stand-ins of tests/fake_ops.py.  Result vs the UNMODIFIED reference's golden eps."""
+    from magicdance_b200 import ops, synth
+    from tests import fake_ops, golden_util as G
+    from tests.test_engine_cpu import _PATCHED
+    for name in _PATCHED:
+        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    torch.set_grad_enabled(False)
+    sd = synth.synth_state_dict(seed=0)
+    own = model.state_dict()
+    sd.update({k: own[k] for k in synth.SCHEDULE_KEYS})  # the 13 schedule buffers are derived, not synthesised
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    g = G.load("small32")
+    inp = G.small32_inputs()
+    cond = {"c_concat": [inp["pose"]], "c_crossattn": [inp["context"]]}
+    eps_c = model.apply_model(inp["x"], inp["t"], cond, inp["ref"])
+    eps_u = model.apply_model(inp["x"], inp["t"], cond, None, uc=True)
+    e_c = G.rel_l2(eps_c, torch.from_numpy(g["small32/eps_c"]))
+    e_u = G.rel_l2(eps_u, torch.from_numpy(g["small32/eps_u"]))
+    assert e_c <= 5e-3 and e_u <= 5e-3, (e_c, e_u)
+    # the sub-networks called on their own, as the reference's apply_model does (cldm.py:1105-1117)
+    bank = []
+    assert model.appearance_control_model(x=inp["ref"], hint=None, timesteps=inp["t"], context=inp["context"],
+                                          attention_bank=bank, attention_mode="write", uc=False) == []
+    assert len(bank) == 16 and all(isinstance(b, list) and b[0].dim() == 3 for b in bank)
+    res = model.pose_control_model(x=inp["x"], hint=inp["pose"], timesteps=inp["t"], context=inp["context"])
+    assert len(res) == 13
+    for i, r in enumerate(res):
+        G.check_summary(g, f"small32/pose{i}", r, 5e-3)
