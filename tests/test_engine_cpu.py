@@ -68,3 +68,35 @@ def test_sampler_step_orchestration_matches_reference_full64(engine, monkeypatch
     assert errs["eps_c"] <= TOL and errs["eps_u"] <= TOL, errs
     # CFG 7 amplifies the difference of two nearly equal fp16-rounded fields (ddim.py:605)
     assert errs["x_prev"] <= 2 * TOL and errs["pred_x0"] <= 4 * TOL, errs
+
+
+def test_timestep_batched_bank_slots_feed_the_step_like_the_direct_bank(engine, monkeypatch):
+    """The multi-GPU / multi-frame data path: the appearance pass batched over TIMESTEPS
+    (pipeline.build_bank_slots) writes each timestep's projected K / V^T into one flat slot (parallel.BankLayout —
+    what the NCCL all-gather moves); a step that reads its bank through views of that slot must equal a step that
+    builds the bank for its own timestep directly."""
+    from magicdance_b200 import ops, parallel
+    from magicdance_b200.pipeline import DenoisePipeline, build_bank_slots
+    monkeypatch.setattr(ops, "cfg_ddim_update", fake_ops.cfg_ddim_update)
+    inp = synth.synth_inputs(1, 32, seed=3, shared_reference=True)
+    pipe = DenoisePipeline(engine, ddim_steps=50, scale=7.0, eta=0.0)
+    geo = engine.attn_geometry(32, 32)
+    tokens = [n for n, _ in geo]
+    layout = parallel.BankLayout([(n, c) for n, c in geo])
+    indices = [49, 20, 3]                                   # three timesteps in ONE appearance pass
+    slots = torch.zeros((len(indices), layout.numel), dtype=torch.float16)
+    build_bank_slots(engine, inp["ref"], pipe.t_dev[torch.as_tensor(indices)], inp["context"], layout, tokens, slots)
+    hint = pipe.hint(inp["pose"])
+    for j, ix in enumerate(indices[:2]):
+        via_slot = layout.views(slots[j], tokens, 1)
+        direct = pipe.reference_bank(inp["ref"], inp["context"], ix)
+        assert len(via_slot) == len(direct) == 16
+        for (k_s, vt_s, n_s, b_s), (k_d, vt_d, n_d, b_d) in zip(via_slot, direct):
+            assert (n_s, b_s) == (n_d, b_d)
+            # batched over 3 timesteps vs alone: the same arithmetic per sample up to fp16 rounding noise
+            assert G.rel_l2(k_s, k_d) <= 3e-3 and G.rel_l2(vt_s, vt_d[:, :n_d]) <= 3e-3
+        x1, _, ec1, _ = pipe.step(inp["x"], ix, inp["context"], hint, via_slot)
+        x2, _, ec2, _ = pipe.step(inp["x"], ix, inp["context"], hint, direct)
+        assert G.rel_l2(ec1, ec2) <= 3e-3 and G.rel_l2(x1, x2) <= 3e-3
+    # the bank really depends on the timestep (SURVEY §8a semantics 4)
+    assert G.rel_l2(slots[0].float(), slots[1].float()) > 1e-2
