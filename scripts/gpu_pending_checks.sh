@@ -1,0 +1,12 @@
+#!/bin/bash
+# Everything that was written after the round-1 GPU budget ran out and is therefore still opt-in.
+# One gpurun call (~3-4 min of box time); each leg is bounded by `timeout` and writes under gpurun_out/.
+#   gpurun --timeout 600 -- 'bash scripts/gpu_pending_checks.sh'
+mkdir -p gpurun_out
+echo "== persistent CTA-pair GEMM: numerics (14 cases), then all three GEMM variants shape by shape"
+MDB_TEST_PAIR_MODE=2 timeout 120 python scripts/gpu_diag.py --group pair > gpurun_out/pending_pairp.log 2>&1; echo "rc=$?"; tail -n 2 gpurun_out/pending_pairp.log
+timeout 200 python scripts/gpu_microbench.py pair 0,1,2 > gpurun_out/pending_microbench_pair.log 2>&1; echo "rc=$?"
+echo "== VAE decoder (softmax kernel, GroupNorm with 4 channels/group, 128-pixel-row implicit GEMM, im2col at 256/512)"
+timeout 200 python scripts/gpu_vae_parity.py > gpurun_out/pending_vae.log 2>&1; echo "rc=$?"; tail -n 12 gpurun_out/pending_vae.log
+echo "== full step with the persistent pair kernel (eight frames)"
+MDB_GEMM_PAIR=2 timeout 90 python bench.py --batch 8 --steps 20 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b8_pair2.json 2> gpurun_out/pending_b8_pair2.err; echo "rc=$? (124 = hung)"
