@@ -20,14 +20,20 @@ _PATCHED = ("gemm", "attention", "conv3x3_direct", "groupnorm", "layernorm", "up
             "ensure_device", "gn_ring_reset", "require_cuda")
 
 
-@pytest.fixture()
-def engine(monkeypatch):
+@pytest.fixture(scope="module")
+def engine():
+    """One engine (2.1 G parameters repacked to fp16 on the CPU) for the whole module, with the kernel entry points
+    patched for exactly as long as it lives."""
     from magicdance_b200 import ops
     from magicdance_b200.engine import DenoiseEngine
-    for name in _PATCHED:
-        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    mp = pytest.MonkeyPatch()
+    for name in _PATCHED + ("cfg_ddim_update",):
+        mp.setattr(ops, name, getattr(fake_ops, name))
     torch.set_grad_enabled(False)
-    return DenoiseEngine(synth.synth_state_dict(seed=0), device="cpu")
+    try:
+        yield DenoiseEngine(synth.synth_state_dict(seed=0), device="cpu")
+    finally:
+        mp.undo()
 
 
 def test_apply_model_orchestration_matches_reference_small32(engine):
@@ -49,13 +55,11 @@ def test_apply_model_orchestration_matches_reference_small32(engine):
     assert G.rel_l2(eps_c, eps_u) > 1e-2  # the two branches really differ
 
 
-def test_sampler_step_orchestration_matches_reference_full64(engine, monkeypatch):
+def test_sampler_step_orchestration_matches_reference_full64(engine):
     """One full p_sample_ddim (ddim.py:518-645; index 49, t = 981, CFG 7) at the headline size through
     pipeline.DenoisePipeline.step — bank build, K/V projection, cached hint features, the paired cond/uncond
     UNet batch and the fused update — against the unmodified reference's x_prev / pred_x0 / eps."""
-    from magicdance_b200 import ops
     from magicdance_b200.pipeline import DenoisePipeline
-    monkeypatch.setattr(ops, "cfg_ddim_update", fake_ops.cfg_ddim_update)
     g = G.load("full64")
     inp = G.full64_inputs()
     pipe = DenoisePipeline(engine, ddim_steps=50, scale=7.0, eta=0.0)
@@ -70,14 +74,13 @@ def test_sampler_step_orchestration_matches_reference_full64(engine, monkeypatch
     assert errs["x_prev"] <= 2 * TOL and errs["pred_x0"] <= 4 * TOL, errs
 
 
-def test_timestep_batched_bank_slots_feed_the_step_like_the_direct_bank(engine, monkeypatch):
+def test_timestep_batched_bank_slots_feed_the_step_like_the_direct_bank(engine):
     """The multi-GPU / multi-frame data path: the appearance pass batched over TIMESTEPS
     (pipeline.build_bank_slots) writes each timestep's projected K / V^T into one flat slot (parallel.BankLayout —
     what the NCCL all-gather moves); a step that reads its bank through views of that slot must equal a step that
     builds the bank for its own timestep directly."""
-    from magicdance_b200 import ops, parallel
+    from magicdance_b200 import parallel
     from magicdance_b200.pipeline import DenoisePipeline, build_bank_slots
-    monkeypatch.setattr(ops, "cfg_ddim_update", fake_ops.cfg_ddim_update)
     inp = synth.synth_inputs(1, 32, seed=3, shared_reference=True)
     pipe = DenoisePipeline(engine, ddim_steps=50, scale=7.0, eta=0.0)
     geo = engine.attn_geometry(32, 32)
