@@ -103,3 +103,22 @@ def test_timestep_batched_bank_slots_feed_the_step_like_the_direct_bank(engine):
         assert G.rel_l2(ec1, ec2) <= 3e-3 and G.rel_l2(x1, x2) <= 3e-3
     # the bank really depends on the timestep (SURVEY §8a semantics 4)
     assert G.rel_l2(slots[0].float(), slots[1].float()) > 1e-2
+
+
+def test_shared_reference_bank_and_paired_batch_match_the_oracle(engine):
+    """The bench / video configuration: several frames share ONE reference image, so the bank is built for a
+    single sample (kv1_batches = 1) and read by the conditional half of the paired cond/uncond batch only
+    (bank_batches = frames).  Checked against the CPU oracle (itself pinned to the reference) on fresh inputs."""
+    from oracle import restatement as R
+    inp = synth.synth_inputs(2, 32, seed=5, shared_reference=True)
+    inp["t"] = torch.full((2,), 441, dtype=torch.long)
+    weights = synth.synth_state_dict(seed=0)
+    ref_c = R.apply_model(weights, inp["x"], inp["t"], inp["context"], inp["pose"], inp["ref"], uc=False)
+    ref_u = R.apply_model(weights, inp["x"], inp["t"], inp["context"], inp["pose"], None, uc=True)
+    del weights
+    bank = engine.appearance_write(inp["ref"][:1], inp["t"][:1], inp["context"][:1])
+    bank_kv = engine.project_bank(bank, 1)
+    pose = engine.controlnet(inp["x"], engine.hint_features(inp["pose"]), inp["t"], inp["context"])
+    eps_c, eps_u = engine.unet_forward(inp["x"], inp["t"], inp["context"], bank_kv=bank_kv, pose=pose, cfg_pair=True)
+    e_c, e_u = G.rel_l2(eps_c, ref_c), G.rel_l2(eps_u, ref_u)
+    assert e_c <= TOL and e_u <= TOL, (e_c, e_u)
