@@ -43,6 +43,9 @@ void set_error(const char* fmt, ...);
 // byte stride of dims[i+1].  Returns 0 on success.
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box);
+// same, un-swizzled (dense row-major box in shared memory): the output map of the TMA-store epilogues
+int make_tmap_f16_plain(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box);
 
 // ----------------------------------------------------------------------------------------------
 // device-side PTX wrappers
@@ -186,6 +189,23 @@ __device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m
       : "memory");
 }
 
+// ---- TMA stores (shared -> global, bulk async-group completion) -----------------------------------
+// The issuing thread's earlier generic-proxy writes of the source tile must be ordered before this with
+// fence_proxy_async_smem() (+ a barrier when other threads wrote parts of the tile).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups may still be READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// all of this thread's bulk groups have completed (writes performed)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- thread-block clusters / distributed shared memory ---------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -292,6 +312,14 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+// same, for a pair that sits at cluster ranks (leader, leader + 1) of a larger cluster
+__device__ __forceinline__ void umma_commit_pair_at(uint64_t* bar, uint32_t leader_rank) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3u << leader_rank))
       : "memory");
 }
 

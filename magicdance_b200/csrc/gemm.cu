@@ -652,6 +652,520 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_pairp_kernel(const __gri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent CTA-pair GEMM, second cut (MDB_GEMM_PAIR=3) — written after the round-1 GPU budget was spent:
+// compiled and SASS-checked, NOT YET RUN ON A GPU, therefore opt-in (scripts/gpu_pending_checks.sh is its gate).
+// Same operand staging, barriers and tile walk as gemm_pairp_kernel above; what changes is the epilogue, which
+// bounded that kernel on the short-K layers (K = 320 / 640: four warps per CTA drained a 128 x BN fp32 tile
+// with dependent global loads of bias and residual per 32-column chunk and 16-byte stores strided by the row
+// pitch):
+//   * EIGHT epilogue warps per CTA (warps 2..9): two per TMEM lane quarter, each taking half of the tile's
+//     32-column chunks; acc_empty counts 16 arrivals (8 warps x 2 CTAs) and a warp arrives as soon as its last
+//     tcgen05.ld has returned, before it converts and stores;
+//   * the residual of the NEXT chunk (or of the next tile's first chunk) is fetched into registers while the
+//     current one is converted;
+//   * output through shared memory and TMA: a warp packs its 32 rows x 32 columns of fp16 into a 2 KB staging
+//     buffer (two per warp) and one lane issues cp.async.bulk.tensor (store); rows >= M and columns >= N are
+//     clipped by the tensor map, whole 64-byte row segments reach L2 instead of 16-byte pieces.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairqThreads = 320;                    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kPairqEpiWarps = 8;
+constexpr int kOutBox = 32;                           // TMA-store box: 32 rows x 32 fp16 columns
+constexpr int kOutBufBytes = kOutBox * kOutBox * 2;   // 2 KB
+
+template <int BN, int STAGES>
+struct PairqSmem {
+  using S = GemmSmem<BN, STAGES, true>;
+  static constexpr int kRing = STAGES * S::kStageBytes;               // multiple of 1024
+  static constexpr int kOut = kPairqEpiWarps * 2 * kOutBufBytes;      // 32 KB
+  static constexpr int kTotal = kRing + kOut + 1024;
+};
+
+// this thread's residual for output columns [col0, col0 + 32) of `row` (N % 8 == 0 is a launch condition)
+__device__ __forceinline__ void pairq_load_res(const GemmKParams& p, long long row, bool row_ok, int col0,
+                                               uint4 (&dst)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (row_ok && col0 + q * 8 + 8 <= p.n) dst[q] = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0 + q * 8);
+    else dst[q] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+template <int BN, bool GEGLU, int kStages>
+__global__ void __launch_bounds__(kPairqThreads, 1)
+    gemm_pairq_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ CUtensorMap tmD) {
+  using S = GemmSmem<BN, kStages, true>;
+  using Q = PairqSmem<BN, kStages>;
+  static_assert(BN % 32 == 0 && BN <= 256, "cta_group::2 UMMA: N <= 256; the epilogue works in 32-column chunks");
+  static_assert(!GEGLU || BN % 64 == 0, "GEGLU tiles hold (value, gate) chunk pairs");
+  static_assert(Q::kRing % 1024 == 0, "the staging buffers follow the ring and need 128-byte alignment");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t kAccStride = 256;  // columns between the two accumulator buffers
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&tmD);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 2 * kPairqEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(&tmem_base_smem, kTmemCols);
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t pair_rank = cluster_ctarank();
+  const int n_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x >> 1;
+  const int m_pairs = (p.m + 2 * kBM - 1) / (2 * kBM);
+  const int n_tiles = (p.n + BN - 1) / BN;
+  const int total_tiles = m_pairs * n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;  // K chunks issued so far (ring position)
+      for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+        const int mp = t % m_pairs, nt = t / m_pairs;
+        const int m0 = (2 * mp + static_cast<int>(pair_rank)) * kBM;
+        const int n0 = nt * BN;
+        int b0 = 0, y0 = 0;
+        if (p.conv) {
+          b0 = m0 / p.hw;
+          y0 = (p.hw >= kBM) ? (m0 % p.hw) / p.w : 0;
+        }
+        for (int kc = 0; kc < p.k_chunks; ++kc, ++g) {
+          const int s = g % kStages;
+          const uint32_t ph = (g / kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          if (pair_rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
+          const uint32_t fb = dsmem_map(smem_u32(&full_bar[s]), 0);
+          if (p.conv) {
+            const int tap = kc / p.chunks_per_tap;
+            const int cc = kc - tap * p.chunks_per_tap;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d_pair(sa, &p.tmA, fb, cc * kBK, kw - 1, y0 + kh - 1, b0);
+          } else if (kc < p.k1_chunks) {
+            tma_load_2d_pair(sa, &p.tmA, fb, kc * kBK, m0);
+          } else {
+            tma_load_2d_pair(sa, &p.tmA2, fb, (kc - p.k1_chunks) * kBK, m0);
+          }
+          tma_load_2d_pair(sb, &p.tmB, fb, kc * kBK, n0 + static_cast<int>(pair_rank) * S::kBRows);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && pair_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * kBM, BN);
+      uint32_t g = 0;
+      int i = 0;
+      for (int t = cluster_id; t < total_tiles; t += n_clusters, ++i) {
+        const int buf = i & 1;
+        mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);  // all 16 epilogue warps of the pair have drained this buffer
+        tc_fence_after_sync();
+        const uint32_t tacc = tmem_base + buf * kAccStride;
+        for (int kc = 0; kc < p.k_chunks; ++kc, ++g) {
+          const int s = g % kStages;
+          const uint32_t ph = (g / kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
+          const uint32_t b_addr = a_addr + S::kABytes;
+          const uint64_t da = umma_desc_k_sw128(a_addr);
+          const uint64_t db = umma_desc_k_sw128(b_addr);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) umma_f16_ss_pair(tacc, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[s]);
+        }
+        umma_commit_pair(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps 2..9 of both CTAs ----------------
+    const int ew = warp - 2;
+    const int gq = warp & 3;     // TMEM lane quarter this warp may access (hardware rule: warp % 4)
+    const int half = ew >> 2;    // which half of the tile's column chunks this warp drains
+    uint8_t* obuf = smem + Q::kRing + ew * (2 * kOutBufBytes);
+    const uint32_t acc_empty_leader0 = dsmem_map(smem_u32(&acc_empty[0]), 0);
+    const uint32_t acc_empty_leader1 = dsmem_map(smem_u32(&acc_empty[1]), 0);
+    constexpr int kUnits = GEGLU ? BN / 64 : BN / 32;   // 32 OUTPUT columns each
+    constexpr int kUnitsLo = (kUnits + 1) / 2;
+    const int u_begin = half ? kUnitsLo : 0;
+    const int u_end = half ? kUnits : kUnitsLo;
+    constexpr int kAccColsPerUnit = GEGLU ? 64 : 32;
+    const bool have_res = !GEGLU && (p.residual != nullptr);
+    uint32_t ob = 0;  // staging-buffer parity, runs on across tiles
+    uint4 rcur[4], rnxt[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rcur[q] = rnxt[q] = make_uint4(0u, 0u, 0u, 0u);
+    if (have_res && cluster_id < total_tiles) {  // residual of the first tile's first chunk
+      const int mp = cluster_id % m_pairs, nt = cluster_id / m_pairs;
+      const long long row = static_cast<long long>((2 * mp + static_cast<int>(pair_rank)) * kBM) + gq * 32 + lane;
+      pairq_load_res(p, row, row < p.m, nt * BN + u_begin * 32, rcur);
+    }
+    int i = 0;
+    for (int t = cluster_id; t < total_tiles; t += n_clusters, ++i) {
+      const int buf = i & 1;
+      const int mp = t % m_pairs, nt = t / m_pairs;
+      const int m0 = (2 * mp + static_cast<int>(pair_rank)) * kBM;
+      const int n0 = nt * BN;
+      const int row0 = m0 + gq * 32;                       // first row of this warp's slab
+      const long long row = static_cast<long long>(row0) + lane;
+      const bool row_ok = row < p.m;
+      const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
+      mbar_wait(&acc_full[buf], (i >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + buf * kAccStride + (static_cast<uint32_t>(gq * 32) << 16);
+      bool arrived = false;
+#pragma unroll 1
+      for (int u = u_begin; u < u_end; ++u) {
+        const int col0 = n0 + u * kAccColsPerUnit;          // first accumulator column of this unit (global N index)
+        if (col0 >= p.n) break;                             // warp-uniform
+        const bool last = (u + 1 == u_end) || (col0 + kAccColsPerUnit >= p.n);
+        uint4 o4[4];
+        if constexpr (!GEGLU) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr + u * 32, r);
+          if (have_res && !last) pairq_load_res(p, row, row_ok, col0 + 32, rnxt);
+          tmem_wait_ld();
+          if (last) {  // this warp's share of the buffer is in registers: hand it back to the MMA thread now
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(buf == 0 ? acc_empty_leader0 : acc_empty_leader1);
+            arrived = true;
+          }
+          const int ncols = min(32, p.n - col0);
+          const float* bp = (p.bias != nullptr && row_ok) ? p.bias + brow * p.bias_batch_stride + col0 : nullptr;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[q * 8 + e]);
+            if (bp != nullptr && q * 8 + 8 <= ncols) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bp + q * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bp + q * 8 + 4);
+              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+              o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+            }
+            if (have_res) {
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rcur[q]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                o[2 * e] += f.x;
+                o[2 * e + 1] += f.y;
+              }
+            }
+            o4[q].x = pack_half2(o[0], o[1]);
+            o4[q].y = pack_half2(o[2], o[3]);
+            o4[q].z = pack_half2(o[4], o[5]);
+            o4[q].w = pack_half2(o[6], o[7]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rcur[q] = rnxt[q];
+        } else {
+          uint32_t rv[32], rg[32];
+          tmem_ld_x32(taddr + u * 64, rv);
+          tmem_ld_x32(taddr + u * 64 + 32, rg);
+          tmem_wait_ld();
+          if (last) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(buf == 0 ? acc_empty_leader0 : acc_empty_leader1);
+            arrived = true;
+          }
+          const float* bp = (p.bias != nullptr && row_ok) ? p.bias + brow * p.bias_batch_stride + col0 : nullptr;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int j = q * 8 + e;
+              float a = __uint_as_float(rv[j]);
+              float gt = __uint_as_float(rg[j]);
+              if (bp != nullptr) {
+                a += bp[j];
+                gt += bp[32 + j];
+              }
+              o[e] = a * gelu_erf_f(gt);
+            }
+            o4[q].x = pack_half2(o[0], o[1]);
+            o4[q].y = pack_half2(o[2], o[3]);
+            o4[q].z = pack_half2(o[4], o[5]);
+            o4[q].w = pack_half2(o[6], o[7]);
+          }
+        }
+        // registers -> staging buffer -> TMA store.  The buffer was last used two stores ago: at most one
+        // younger bulk group may still be reading shared memory.
+        uint8_t* sbuf = obuf + ob * kOutBufBytes;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint4* srow = reinterpret_cast<uint4*>(sbuf + lane * (kOutBox * 2));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) srow[q] = o4[q];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < p.m) {
+          tma_store_2d(&tmD, sbuf, GEGLU ? (col0 >> 1) : col0, row0);
+          tma_store_commit();
+        }
+        ob ^= 1u;
+      }
+      if (!arrived) {  // no column of this warp's half lies inside N
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(buf == 0 ? acc_empty_leader0 : acc_empty_leader1);
+      }
+      if (have_res && t + n_clusters < total_tiles) {  // residual of the next tile's first chunk
+        const int tn = t + n_clusters;
+        const int mpn = tn % m_pairs, ntn = tn / m_pairs;
+        const long long rown = static_cast<long long>((2 * mpn + static_cast<int>(pair_rank)) * kBM) + gq * 32 + lane;
+        pairq_load_res(p, rown, rown < p.m, ntn * BN + u_begin * 32, rcur);
+      }
+    }
+    if (lane == 0) tma_store_wait_all();  // the staging buffers must outlive the stores that read them
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();  // the leader's MMAs read the partner's shared memory and write its TMEM
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair tiles WITH split-K inside one cluster (MDB_GEMM_PAIR_SPLITK=1) — for the single-frame, weight-
+// streaming layers (M = 256 ... 8192 rows, K up to 11520, at most one wave of CTAs).  NOT YET RUN ON A GPU,
+// opt-in (same gate as above).  Why: those layers are bound by the bytes every SM pulls through the L2 -> SM
+// fabric (~46 B/clk per SM), not by DRAM or the tensor pipe: a 128 x 80 tile moves 26 KB per K chunk for
+// 128 x 80 outputs; one half of a 256 x 160 pair tile moves the same 26 KB (its own 128 A rows + 80 of the 160
+// B rows) for 128 x 160 outputs.  Keeping the CTA count (~one per SM) by splitting K across the cluster halves
+// the fabric traffic of the layer.
+// Cluster = (2, 1, S), S in {1, 2, 4}: x = the cta_group::2 pair (cluster ranks 2z, 2z+1: the pair of split z),
+// z = the K split.  Every CTA parks its 128 x BN fp32 partial in its own (by then idle) operand ring; the S
+// CTAs with the same pair rank then reduce it through DSMEM exactly like gemm_tc_kernel's cluster split-K (CTA
+// z sums rows [z*128/S, (z+1)*128/S) over all partners, applies bias/residual, stores fp16).
+// One CTA per SM by construction (>= 190 KB of shared memory), no early griddepcontrol.launch_dependents: no
+// foreign tensor-memory CTA can sit next to a pair whose cta_group::2 allocation is still pending — the
+// situation in which the one-tile pair mode of gemm_tc_kernel dead-locked inside the full step.
+// ------------------------------------------------------------------------------------------------
+template <int BN, int kStages>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_pairs_kernel(const __grid_constant__ GemmKParams p) {
+  using S = GemmSmem<BN, kStages, true>;
+  static_assert(BN % 16 == 0 && BN <= 256, "cta_group::2 UMMA: N must be a multiple of 16, at most 256");
+  constexpr int kRedLd = BN + 4;  // fp32 row pitch of the parked partial tile
+  static_assert(kBM * kRedLd * 4 <= kStages * S::kStageBytes, "partial tile must fit in the operand ring");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM;
+  const int n0 = blockIdx.y * BN;
+  const int split = blockIdx.z;
+  const int kc_begin = split * p.chunks_per_split;
+  const int kc_end = min(p.k_chunks, kc_begin + p.chunks_per_split);
+  const int n_iter = kc_end - kc_begin;  // > 0: the host never creates an empty split
+  constexpr uint32_t kTmemCols = (BN <= 128) ? 128 : 256;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(&tmem_base_smem, kTmemCols);
+  tc_fence_before_sync();
+  cluster_sync_all();  // every CTA's barriers exist and every pair owns its tensor memory from here on
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t crank = cluster_ctarank();     // x + 2 * z inside the (2, 1, S) cluster
+  const uint32_t pair_rank = crank & 1u;        // 0 = leader of its pair (issues the MMAs)
+  const uint32_t leader = crank & ~1u;
+  pdl_wait();  // a no-op unless launched with programmatic serialization
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int b0 = 0, y0 = 0;
+      if (p.conv) {
+        b0 = m0 / p.hw;
+        y0 = (p.hw >= kBM) ? (m0 % p.hw) / p.w : 0;
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::kStageBytes;
+        uint8_t* sb = sa + S::kABytes;
+        const int kc = kc_begin + it;
+        if (pair_rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
+        const uint32_t fb = dsmem_map(smem_u32(&full_bar[s]), leader);
+        if (p.conv) {
+          const int tap = kc / p.chunks_per_tap;
+          const int cc = kc - tap * p.chunks_per_tap;
+          const int kh = tap / 3, kw = tap - kh * 3;
+          tma_load_4d_pair(sa, &p.tmA, fb, cc * kBK, kw - 1, y0 + kh - 1, b0);
+        } else if (kc < p.k1_chunks) {
+          tma_load_2d_pair(sa, &p.tmA, fb, kc * kBK, m0);
+        } else {
+          tma_load_2d_pair(sa, &p.tmA2, fb, (kc - p.k1_chunks) * kBK, m0);
+        }
+        tma_load_2d_pair(sb, &p.tmB, fb, kc * kBK, n0 + static_cast<int>(pair_rank) * S::kBRows);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && pair_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * kBM, BN);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
+        const uint32_t b_addr = a_addr + S::kABytes;
+        const uint64_t da = umma_desc_k_sw128(a_addr);
+        const uint64_t db = umma_desc_k_sw128(b_addr);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) umma_f16_ss_pair(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        umma_commit_pair_at(&empty_bar[s], leader);  // frees the stage in both CTAs of THIS pair
+      }
+      umma_commit_pair_at(&acc_bar, leader);
+    }
+  } else {
+    // ---------------- epilogue warps 2..5: park the fp32 partial tile in shared memory ----------------
+    const int g = warp & 3;
+    mbar_wait(&acc_bar, 0);  // all MMAs of the pair are complete: both CTAs' operand rings are idle
+    tc_fence_after_sync();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
+#pragma unroll
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld_x32(taddr + ch * 32, r);
+      tmem_wait_ld();
+      float* rp = reinterpret_cast<float*>(smem) + (g * 32 + lane) * kRedLd + ch * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(rp + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+    }
+  }
+
+  {
+    // ---- split-K reduction across the cluster through distributed shared memory (all 192 threads) ----
+    const int S_ = p.splits;
+    const int R = kBM / S_;
+    const int groups = BN / 8;
+    const int sidx = static_cast<int>(crank >> 1);  // this CTA's split == the row slice it reduces
+    constexpr int kMaxItems = 4;
+    uint4 rpre[kMaxItems];
+    if (p.residual != nullptr) {
+#pragma unroll
+      for (int q = 0; q < kMaxItems; ++q) {
+        const int item = threadIdx.x + q * kGemmThreads;
+        if (item < R * groups) {
+          const int rl = item / groups, cgp = item - rl * groups;
+          const long long row = static_cast<long long>(m0) + sidx * R + rl;
+          const int col0 = n0 + cgp * 8;
+          if (row < p.m && col0 + 8 <= p.n) rpre[q] = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
+        }
+      }
+    }
+    cluster_sync_all();  // every partial is parked (release) and visible (acquire)
+    const uint32_t red_base = smem_u32(smem);
+#pragma unroll 1
+    for (int it_ = 0; it_ * kGemmThreads < R * groups; ++it_) {
+      const int item = threadIdx.x + it_ * kGemmThreads;
+      if (item >= R * groups) break;
+      const int rl = item / groups, cgp = item - rl * groups;
+      const int rt = sidx * R + rl;  // row inside the 128-row tile
+      const long long row = static_cast<long long>(m0) + rt;
+      const int col0 = n0 + cgp * 8;
+      if (row >= p.m || col0 >= p.n) continue;
+      const uint32_t off = red_base + static_cast<uint32_t>((rt * kRedLd + cgp * 8) * 4);
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = 0.f;
+      for (int pr = 0; pr < S_; ++pr) {
+        const uint32_t ra = dsmem_map(off, pair_rank + 2u * static_cast<uint32_t>(pr));  // same half of split pr's pair
+        const float4 a = dsmem_ld_f4(ra), b = dsmem_ld_f4(ra + 16);
+        o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+        o[4] += b.x; o[5] += b.y; o[6] += b.z; o[7] += b.w;
+      }
+      const int ncols = min(8, p.n - col0);
+      const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
+      if (p.bias != nullptr) {
+        const float* bp = p.bias + brow * p.bias_batch_stride + col0;
+        for (int e = 0; e < ncols; ++e) o[e] += bp[e];
+      }
+      if (ncols == 8) {
+        if (p.residual != nullptr) {
+          uint4 r4 = make_uint4(0, 0, 0, 0);
+          if (it_ < kMaxItems) {
+#pragma unroll
+            for (int q = 0; q < kMaxItems; ++q)
+              if (q == it_) r4 = rpre[q];
+          } else {
+            r4 = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
+          }
+          const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h2[e]);
+            o[2 * e] += f.x;
+            o[2 * e + 1] += f.y;
+          }
+        }
+        uint4 o4;
+        o4.x = pack_half2(o[0], o[1]);
+        o4.y = pack_half2(o[2], o[3]);
+        o4.z = pack_half2(o[4], o[5]);
+        o4.w = pack_half2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(p.d + row * p.ldd + col0) = o4;
+      } else {
+        for (int e = 0; e < ncols; ++e) {
+          float x = o[e];
+          if (p.residual != nullptr) x += __half2float(p.residual[row * p.ldr + col0 + e]);
+          p.d[row * p.ldd + col0 + e] = __float2half_rn(x);
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();  // nobody leaves while a partner may still read its shared memory or write its TMEM
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
 // split-K second pass: sum of the fp32 partial slabs ws[splits][M][N] -> bias/residual -> fp16 D
 __global__ void splitk_finalize_kernel(GemmKParams p) {
   pdl_launch_dependents();
@@ -706,8 +1220,8 @@ __global__ void splitk_finalize_kernel(GemmKParams p) {
 // ------------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
-int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box) {
+static int make_tmap_f16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
   if (g_encode == nullptr) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -739,7 +1253,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     }
   }
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu,%llu box %u,%u)", (int)r, rank,
@@ -747,6 +1261,16 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     return MDB_ERR_CUDA;
   }
   return MDB_OK;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  return make_tmap_f16_sw(out, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int make_tmap_f16_plain(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap_f16_sw(out, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 void count_launch(int n = 1);
@@ -795,6 +1319,58 @@ static int launch_gemm_pairp(const GemmKParams& kp, int total_tiles, cudaStream_
   MDB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
   count_launch();
   return MDB_OK;
+}
+
+static int launch_cluster_nopdl(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cx,
+                                unsigned cz, void** args) {
+  // no programmatic stream serialization: a pair kernel starts only after its predecessor has completed
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cx;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = cz;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MDB_CHECK_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+  count_launch();
+  return MDB_OK;
+}
+
+template <int BN, bool GEGLU, int STAGES>
+static int launch_gemm_pairq(const GemmKParams& kp, const CUtensorMap& tmD, int total_tiles, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = gemm_pairq_kernel<BN, GEGLU, STAGES>;
+  constexpr int kSmem = PairqSmem<BN, STAGES>::kTotal;
+  static_assert(kSmem <= 227 * 1024, "shared memory budget");
+  if (!attr_set) {
+    MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_set = true;
+  }
+  const int clusters = total_tiles < 74 ? total_tiles : 74;  // one pair per TPC (148 SMs)
+  void* args[2] = {const_cast<GemmKParams*>(&kp), const_cast<CUtensorMap*>(&tmD)};
+  return launch_cluster_nopdl(reinterpret_cast<const void*>(kern), dim3(2 * clusters), dim3(kPairqThreads), kSmem, st, 2u,
+                              1u, args);
+}
+
+template <int BN, int STAGES>
+static int launch_gemm_pairs(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = gemm_pairs_kernel<BN, STAGES>;
+  constexpr int kSmem = GemmSmem<BN, STAGES, true>::kTotal;
+  static_assert(kSmem <= 227 * 1024 && kSmem >= 190 * 1024, "one CTA per SM, nothing else with tensor memory beside it");
+  if (!attr_set) {
+    MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_set = true;
+  }
+  void* args[1] = {const_cast<GemmKParams*>(&kp)};
+  return launch_cluster_nopdl(reinterpret_cast<const void*>(kern), grid, dim3(kGemmThreads), kSmem, st, 2u,
+                              static_cast<unsigned>(kp.splits), args);
 }
 
 }  // namespace mdb
@@ -884,15 +1460,55 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   // same results as the single-CTA tiles (tests/kernel_cases.py case_pair).  The switches are read per call
   // (launches are captured into graphs, so this is off the replay path), which lets the tests force pair
   // tiles onto small problems.
+  // Pair tiles with split-K inside the cluster (gemm_pairs_kernel) — EXPERIMENTAL, opt-in, not yet run on a GPU:
+  // MDB_GEMM_PAIR_SPLITK=1.  Takes the layers that fit in one wave of CTAs (the single-frame regime) and have at
+  // least two M tiles; picks its own split count S in {1, 2, 4} (cluster of 2*S <= 8 CTAs) so that about one CTA
+  // lands on every SM, whatever `splits` the caller asked for (no workspace is needed: DSMEM reduction).
+  {
+    const char* ps_env = getenv("MDB_GEMM_PAIR_SPLITK");
+    const int mt = (g->m + kBM - 1) / kBM;
+    if (ps_env != nullptr && ps_env[0] == '1' && !geglu && mt >= 2 && g->n % 8 == 0) {
+      const int bnp = (g->n % 160 == 0) ? 160 : 128;
+      const int m_pairs = (mt + 1) / 2;
+      const int n_tiles = (g->n + bnp - 1) / bnp;
+      const int ctas = 2 * m_pairs * n_tiles;
+      if (ctas <= 148) {
+        // co-resident CTAs at one 200 KB CTA per SM: 148 in clusters of 2, 132 in clusters of 4, 128 in clusters of 8
+        // (8 GPCs of 16/18/20 SMs, a cluster never straddles a GPC)
+        int S_ = 1;
+        if (ctas * 4 <= 128 && kp.k_chunks >= 16) S_ = 4;
+        else if (ctas * 2 <= 132 && kp.k_chunks >= 8) S_ = 2;
+        uint32_t boxb[2] = {kBK, (uint32_t)(bnp / 2)};  // each CTA of a pair stages half of the B rows
+        uint64_t dimsb[2] = {(uint64_t)g->k, (uint64_t)g->n};
+        uint64_t strb[1] = {(uint64_t)g->ldb * 2};
+        rc = make_tmap_f16(&kp.tmB, g->b, 2, dimsb, strb, boxb);
+        if (rc) return rc;
+        kp.chunks_per_split = (kp.k_chunks + S_ - 1) / S_;
+        S_ = (kp.k_chunks + kp.chunks_per_split - 1) / kp.chunks_per_split;  // no empty splits
+        if (S_ == 3) {  // 4 requested, 3 non-empty: a (2,1,3) cluster is legal but R = 128/3 is not
+          S_ = 2;
+          kp.chunks_per_split = (kp.k_chunks + 1) / 2;
+        }
+        kp.splits = S_;
+        kp.cluster_reduce = 1;
+        dim3 gridp(2 * m_pairs, n_tiles, S_);
+        if (bnp == 160) return launch_gemm_pairs<160, 8>(kp, gridp, st);
+        return launch_gemm_pairs<128, 8>(kp, gridp, st);
+      }
+    }
+  }
+
   const char* pair_env = getenv("MDB_GEMM_PAIR");
   const char* pair_min_env = getenv("MDB_GEMM_PAIR_MIN");
-  const bool pair_ok = (pair_env != nullptr && (pair_env[0] == '1' || pair_env[0] == '2'));
+  const bool pairq = (pair_env != nullptr && pair_env[0] == '3');  // gemm_pairq_kernel: see its header comment
+  const bool pair_ok = (pair_env != nullptr && (pair_env[0] == '1' || pair_env[0] == '2')) || (pairq && g->n % 8 == 0);
   const long long pair_min = pair_min_env ? atoll(pair_min_env) : 256ll;
   const int m_tiles = (g->m + kBM - 1) / kBM;
   bool pair = pair_ok && g->splits <= 1 && m_tiles >= 2;
   int bn;
   if (pair) {
     if (geglu) bn = (g->n % 256 == 0) ? 256 : 0;
+    else if (pairq && g->n % 256 == 0) bn = 256;  // widest tile first: fewest L2 -> SM bytes per flop
     else if (g->n % 160 == 0) bn = 160;
     else if (g->n % 256 == 0) bn = 256;
     else bn = 128;
@@ -937,6 +1553,20 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   const bool deep = (long long)grid.x * grid.y * grid.z <= 148 && kp.chunks_per_split >= 12;
   if (pair) {
     // MDB_GEMM_PAIR=2: the persistent one-pair-per-TPC kernel (owns the SMs and all of their tensor memory)
+    if (pairq) {
+      // output tensor map of the TMA-store epilogue: [M][N_out] fp16, 32 x 32 boxes, dense (no swizzle)
+      CUtensorMap tmD;
+      uint32_t boxd[2] = {(uint32_t)kOutBox, (uint32_t)kOutBox};
+      uint64_t dimsd[2] = {(uint64_t)(geglu ? g->n / 2 : g->n), (uint64_t)g->m};
+      uint64_t strd[1] = {(uint64_t)g->ldd * 2};
+      rc = make_tmap_f16_plain(&tmD, g->d, 2, dimsd, strd, boxd);
+      if (rc) return rc;
+      const int total_tiles = ((m_tiles + 1) / 2) * (int)grid.y;
+      if (geglu) return launch_gemm_pairq<256, true, 5>(kp, tmD, total_tiles, st);
+      if (bn == 160) return launch_gemm_pairq<160, false, 6>(kp, tmD, total_tiles, st);
+      if (bn == 256) return launch_gemm_pairq<256, false, 5>(kp, tmD, total_tiles, st);
+      return launch_gemm_pairq<128, false, 6>(kp, tmD, total_tiles, st);
+    }
     if (pair_env[0] == '2') {
       const int total_tiles = ((m_tiles + 1) / 2) * (int)grid.y;
       if (geglu) return launch_gemm_pairp<256, true, 6>(kp, total_tiles, st);

@@ -121,6 +121,21 @@ def main():
                     timeit(f"geglu m={b * hw} c={c}", lambda: ops.gemm(x, wp, bias=bp, epilogue=ops.EPI_GEGLU),
                            flops=2.0 * b * hw * 8 * c * c)
         return
+    if which == "pairs":
+        # single-frame (cond+uncond batch of 2) weight-streaming layers: default tiles / split-K against pair tiles
+        # with split-K inside the cluster (gemm_pairs_kernel); both take the split count the engine would pass
+        from magicdance_b200.engine import _auto_splits
+        for mode in ("0", "1"):
+            os.environ["MDB_GEMM_PAIR_SPLITK"] = mode
+            print(f"--- MDB_GEMM_PAIR_SPLITK={mode}", flush=True)
+            for (hh, cin, cout) in ((64, 320, 320), (64, 640, 320), (32, 640, 640), (32, 1280, 640), (16, 1280, 1280),
+                                    (16, 2560, 1280), (8, 1280, 1280), (8, 2560, 1280)):
+                conv_case(2, hh, hh, cin, cout, _auto_splits(2 * hh * hh, cout, 9 * cin))
+            for (m, n, k) in ((8192, 320, 320), (8192, 320, 1280), (2048, 640, 640), (2048, 640, 2560), (2048, 1280, 640),
+                              (512, 1280, 1280), (512, 1280, 5120), (512, 2560, 1280)):
+                gemm_case(m, n, k, _auto_splits(m, n, k))
+        os.environ.pop("MDB_GEMM_PAIR_SPLITK", None)
+        return
     if which in ("all", "attn"):
         attn_case(1, 40, 4096, 4096)
         attn_case(1, 40, 4096, 4096, 4096)

@@ -10,3 +10,11 @@ echo "== VAE decoder (softmax kernel, GroupNorm with 4 channels/group, 128-pixel
 timeout 200 python scripts/gpu_vae_parity.py > gpurun_out/pending_vae.log 2>&1; echo "rc=$?"; tail -n 12 gpurun_out/pending_vae.log
 echo "== full step with the persistent pair kernel (eight frames)"
 MDB_GEMM_PAIR=2 timeout 90 python bench.py --batch 8 --steps 20 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b8_pair2.json 2> gpurun_out/pending_b8_pair2.err; echo "rc=$? (124 = hung)"
+echo "== round-1 late additions: persistent pair GEMM with TMA-store epilogue (MDB_GEMM_PAIR=3), pair tiles + cluster split-K (MDB_GEMM_PAIR_SPLITK=1)"
+timeout 150 python scripts/gpu_diag.py --group pending --pending-filter MDB_GEMM_PAIR_SPLITK > gpurun_out/pending_pairs.log 2>&1; echo "rc=$? (124 = hung)"; tail -n 3 gpurun_out/pending_pairs.log
+timeout 150 python scripts/gpu_diag.py --group pending --pending-filter "'MDB_GEMM_PAIR', '3'" > gpurun_out/pending_pairq.log 2>&1; echo "rc=$? (124 = hung)"; tail -n 3 gpurun_out/pending_pairq.log
+timeout 200 python scripts/gpu_microbench.py pair 0,3 > gpurun_out/pending_microbench_pairq.log 2>&1; echo "rc=$?"
+timeout 200 python scripts/gpu_microbench.py pairs > gpurun_out/pending_microbench_pairs.log 2>&1; echo "rc=$?"
+MDB_GEMM_PAIR=3 timeout 90 python bench.py --batch 8 --steps 20 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b8_pair3.json 2> gpurun_out/pending_b8_pair3.err; echo "rc=$? (124 = hung)"
+MDB_GEMM_PAIR_SPLITK=1 timeout 90 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b1_pairs.json 2> gpurun_out/pending_b1_pairs.err; echo "rc=$? (124 = hung)"
+MDB_GEMM_PAIR=3 MDB_GEMM_PAIR_SPLITK=1 timeout 90 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b1_pair3_pairs.json 2> gpurun_out/pending_b1_pair3_pairs.err; echo "rc=$? (124 = hung)"

@@ -27,7 +27,7 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     from magicdance_b200 import build
     path = build.build()
     sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
-    for mnem in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST"):
+    for mnem in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST", "UTMASTG.2D"):
         assert mnem in sass, f"{mnem} (tcgen05 / TMA) missing from the compiled kernels"
     assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync path must not be present"
 
