@@ -323,8 +323,12 @@ struct Attn2Cfg {
   static_assert(kCols <= 512, "TMEM budget");
 };
 
-template <int D, int BKV>
-__global__ void __launch_bounds__(kAttn2Threads, 1) attn2_tc_kernel(const __grid_constant__ AttnKParams p) {
+// MINB = 2 (MDB_ATTN=4, d=40 with 64-key tiles: 224 TMEM columns, 93 KB of shared memory) puts TWO such CTAs on
+// an SM — 16 softmax warps instead of the 8 that v1 (two CTAs), v2 (one CTA) and v3 (two CTAs) all run with and
+// that all land on ~2200 cycles per 128x128 tile; the register cap becomes 65536 / 640 = 102 per thread.
+// Opt-in: this instantiation has not run on a GPU yet (tests/kernel_cases.py PENDING_CASES).
+template <int D, int BKV, int MINB = 1>
+__global__ void __launch_bounds__(kAttn2Threads, MINB) attn2_tc_kernel(const __grid_constant__ AttnKParams p) {
   using C = Attn2Cfg<D, BKV>;
   using C1 = AttnCfg<D, BKV>;
   extern __shared__ uint8_t smem_raw[];
@@ -899,16 +903,17 @@ static int attn_version() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MDB_ATTN");
-    v = (e != nullptr && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3;
+    v = (e != nullptr && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 3;  // 4: like 3, but d=40 on v2 at two CTAs/SM
   }
   return v;
 }
 
-template <int D, int BKV>
+template <int D, int BKV, int MINB = 1>
 static int launch_attn2(const AttnKParams& kp, dim3 grid, cudaStream_t st) {
   using C = Attn2Cfg<D, BKV>;
+  static_assert(MINB == 1 || (C::kTmemCols <= 256 && C::kSmem <= 113 * 1024), "two CTAs per SM must fit");
   static bool attr_set = false;
-  auto kern = attn2_tc_kernel<D, BKV>;
+  auto kern = attn2_tc_kernel<D, BKV, MINB>;
   if (!attr_set) {
     MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     attr_set = true;
@@ -982,6 +987,13 @@ static int build_and_launch(const mdb_attn_desc* a, cudaStream_t st) {
     if (emu == 3) return launch_attn3<D, BKV, ST, 3>(kp, grid, st);
     return launch_attn3<D, BKV, ST, 0>(kp, grid, st);
   }
+  if constexpr (VER == 4) {  // two Q tiles per CTA AND two CTAs per SM (d = 40 only)
+    if (a->nq > kBQ) {
+      dim3 grid2((a->nq + 2 * kBQ - 1) / (2 * kBQ), a->heads, a->batch);
+      return launch_attn2<D, BKV, 2>(kp, grid2, st);
+    }
+    return launch_attn3<D, BKV, 4, 1>(kp, grid, st);
+  }
   if (VER == 2 && a->nq > kBQ) {  // two Q tiles per CTA (ping-pong)
     dim3 grid2((a->nq + 2 * kBQ - 1) / (2 * kBQ), a->heads, a->batch);
     return launch_attn2<D, BKV>(kp, grid2, st);
@@ -1008,10 +1020,11 @@ extern "C" int mdb_attention_f16(const mdb_attn_desc* a, mdb_stream_t stream) {
   const int ver = attn_version();
   switch (a->d) {
     case 40:
+      if (ver == 4) return build_and_launch<40, 64, 4>(a, st);
       if (ver == 3) return build_and_launch<40, 64, 3>(a, st);
       return ver == 2 ? build_and_launch<40, 128, 2>(a, st) : build_and_launch<40, 128, 1>(a, st);
     case 80:
-      if (ver == 3) return build_and_launch<80, 64, 3>(a, st);
+      if (ver == 3 || ver == 4) return build_and_launch<80, 64, 3>(a, st);
       return ver == 2 ? build_and_launch<80, 64, 2>(a, st) : build_and_launch<80, 64, 1>(a, st);
     case 160:
       return ver == 2 ? build_and_launch<160, 64, 2>(a, st) : build_and_launch<160, 64, 1>(a, st);

@@ -18,3 +18,8 @@ timeout 200 python scripts/gpu_microbench.py pairs > gpurun_out/pending_microben
 MDB_GEMM_PAIR=3 timeout 90 python bench.py --batch 8 --steps 20 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b8_pair3.json 2> gpurun_out/pending_b8_pair3.err; echo "rc=$? (124 = hung)"
 MDB_GEMM_PAIR_SPLITK=1 timeout 90 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b1_pairs.json 2> gpurun_out/pending_b1_pairs.err; echo "rc=$? (124 = hung)"
 MDB_GEMM_PAIR=3 MDB_GEMM_PAIR_SPLITK=1 timeout 90 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b1_pair3_pairs.json 2> gpurun_out/pending_b1_pair3_pairs.err; echo "rc=$? (124 = hung)"
+echo "== attention d=40 on the two-Q-tile kernel at two CTAs per SM (MDB_ATTN=4): numerics, then per-shape time against the default (v3)"
+MDB_ATTN=4 timeout 120 python scripts/gpu_diag.py --group attn > gpurun_out/pending_attn4.log 2>&1; echo "rc=$? (124 = hung)"; tail -n 2 gpurun_out/pending_attn4.log
+timeout 100 python scripts/gpu_microbench.py attn > gpurun_out/pending_microbench_attn3.log 2>&1; echo "rc=$?"
+MDB_ATTN=4 timeout 100 python scripts/gpu_microbench.py attn > gpurun_out/pending_microbench_attn4.log 2>&1; echo "rc=$?"
+MDB_ATTN=4 timeout 90 python bench.py --batch 8 --steps 20 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b8_attn4.json 2> gpurun_out/pending_b8_attn4.err; echo "rc=$? (124 = hung)"
