@@ -23,3 +23,7 @@ MDB_ATTN=4 timeout 120 python scripts/gpu_diag.py --group attn > gpurun_out/pend
 timeout 100 python scripts/gpu_microbench.py attn > gpurun_out/pending_microbench_attn3.log 2>&1; echo "rc=$?"
 MDB_ATTN=4 timeout 100 python scripts/gpu_microbench.py attn > gpurun_out/pending_microbench_attn4.log 2>&1; echo "rc=$?"
 MDB_ATTN=4 timeout 90 python bench.py --batch 8 --steps 20 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b8_attn4.json 2> gpurun_out/pending_b8_attn4.err; echo "rc=$? (124 = hung)"
+echo "== secondary baseline: the reference's path as eager PyTorch (cuDNN/cuBLAS/SDPA, fp16 autocast) on this GPU"
+timeout 150 python tests/torch_gpu_baseline.py --batch 1 --steps 10 --warmup 2 > gpurun_out/torch_gpu_baseline_b1.json 2> gpurun_out/torch_gpu_baseline_b1.err; echo "rc=$?"; cat gpurun_out/torch_gpu_baseline_b1.json
+timeout 150 python tests/torch_gpu_baseline.py --batch 1 --steps 10 --warmup 2 --algorithmic > gpurun_out/torch_gpu_baseline_b1_alg.json 2>> gpurun_out/torch_gpu_baseline_b1.err; echo "rc=$?"; cat gpurun_out/torch_gpu_baseline_b1_alg.json
+timeout 150 python tests/torch_gpu_baseline.py --batch 8 --steps 5 --warmup 1 --algorithmic > gpurun_out/torch_gpu_baseline_b8_alg.json 2>> gpurun_out/torch_gpu_baseline_b1.err; echo "rc=$?"; cat gpurun_out/torch_gpu_baseline_b8_alg.json
