@@ -119,6 +119,13 @@ int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, co
                       void* y, float* stats_ws, int32_t batch, int32_t hw, float eps, int32_t silu,
                       int32_t stats_prezeroed, mdb_stream_t stream);
 
+/* Same operation in ONE launch for small batches (single-frame latency): a thread-block cluster per (batch
+ * element, group) reads its slice twice and exchanges the partial sums through distributed shared memory; no
+ * statistics scratch.  Channels per group must be even (c a multiple of 64); same references as above. */
+int mdb_groupnorm_fused_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* gamma,
+                            const float* beta, void* y, int32_t batch, int32_t hw, float eps, int32_t silu,
+                            mdb_stream_t stream);
+
 /* LayerNorm over the last dim (eps 1e-5), fp16 [rows][c] -> fp16; replaces nn.LayerNorm norm1/2/3 of
  * BasicTransformerBlock (attention.py:270-272). */
 int mdb_layernorm_f16(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int32_t c,

@@ -47,6 +47,8 @@ SIGNATURES = {
     "mdb_attention_f16": (c_int32, [C.POINTER(AttnDesc), c_void_p]),
     "mdb_groupnorm_f16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int32, c_int32, c_float, c_int32, c_int32, c_void_p]),
+    "mdb_groupnorm_fused_f16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                          c_int32, c_int32, c_float, c_int32, c_void_p]),
     "mdb_layernorm_f16": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),
     "mdb_conv3x3_direct_f16": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_int32, c_int32, c_void_p]),

@@ -137,6 +137,120 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __h
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-launch GroupNorm for small batches (mdb_groupnorm_fused_f16) — written after the round-1 GPU budget
+// was spent, NOT YET RUN ON A GPU, opt-in (MDB_GN_FUSED=1 in magicdance_b200/ops.py).
+// At one frame the stats -> apply pair above costs two dependent launches (~7 + ~9 us, 88 pairs per step) for
+// tensors of 0.1 ... 8 MB.  Here one CLUSTER owns one (batch element, group): its CTAs split the pixels, each
+// reads its hw/CS x cg slice twice (the second pass hits L1/L2), the partial (sum, sum of squares) pairs are
+// exchanged through distributed shared memory — no atomics, no statistics buffer, no second kernel.
+// Thread layout: a group is cg = C/32 consecutive channels = cg/2 half2 words per pixel; thread t owns word
+// t % (cg/2) of pixels t / (cg/2), + rows_per_iter, ... so a warp reads whole pixels' slices back to back and
+// there is no division in the loops.  Numerics as above: fp32 sums, var = E[x^2] - mean^2 clamped at 0.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGnFusedThreads = 512;
+
+__global__ void __launch_bounds__(kGnFusedThreads) gn_fused_kernel(const __half* __restrict__ x1, int c1,
+                                                                    const __half* __restrict__ x2, int c2,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, __half* __restrict__ y,
+                                                                    int hw, float eps, int silu) {
+  __shared__ float s_warp[2][kGnFusedThreads / 32];
+  __shared__ __align__(8) float s_part[2];  // this CTA's (sum, sumsq): read by the cluster partners
+  pdl_launch_dependents();
+  const int c = c1 + c2;
+  const int cg = c / 32;
+  const int wpp = cg >> 1;  // half2 words per pixel in one group
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cs = gridDim.z;          // cluster = (1, 1, cs): the CTAs that share this (batch element, group)
+  const int part = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int rows_per_iter = kGnFusedThreads / wpp;
+  const int w = tid % wpp, r0 = tid / wpp;
+  const bool active = r0 < rows_per_iter;
+  const int ch = g * cg + 2 * w;  // this thread's channel pair (c1 is even: a pair never straddles the sources)
+  const __half* src;
+  long long pitch;
+  if (ch < c1) { src = x1 + ch; pitch = c1; } else { src = x2 + (ch - c1); pitch = c2; }
+  src += static_cast<long long>(b) * hw * pitch;
+  __half* dst = y + static_cast<long long>(b) * hw * c + ch;
+  // pixels [p_begin, p_end) belong to this CTA
+  const int per = (hw + cs - 1) / cs;
+  const int p_begin = part * per;
+  const int p_end = min(hw, p_begin + per);
+  const float ga0 = gamma[ch], ga1 = gamma[ch + 1], be0 = beta[ch], be1 = beta[ch + 1];  // constants: before the wait
+  pdl_wait();
+
+  float s = 0.f, q = 0.f;
+  if (active) {
+#pragma unroll 8
+    for (int pix = p_begin + r0; pix < p_end; pix += rows_per_iter) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(src + static_cast<long long>(pix) * pitch));
+      s += f.x + f.y;
+      q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((tid & 31) == 0) {
+    s_warp[0][tid >> 5] = s;
+    s_warp[1][tid >> 5] = q;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float ss = (tid < kGnFusedThreads / 32) ? s_warp[0][tid] : 0.f;
+    float qq = (tid < kGnFusedThreads / 32) ? s_warp[1][tid] : 0.f;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    }
+    if (tid == 0) {
+      s_part[0] = ss;
+      s_part[1] = qq;
+    }
+  }
+  float tot_s, tot_q;
+  if (cs > 1) {
+    cluster_sync_all();  // every partner's partial is written (release) and visible (acquire)
+    tot_s = tot_q = 0.f;
+    const uint32_t a = smem_u32(&s_part[0]);
+    for (int r = 0; r < cs; ++r) {  // same order in every CTA: identical statistics across the cluster
+      const uint32_t ra = dsmem_map(a, static_cast<uint32_t>(r));
+      float ps, pq;
+      asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(ps), "=f"(pq) : "r"(ra));
+      tot_s += ps;
+      tot_q += pq;
+    }
+  } else {
+    __syncthreads();
+    tot_s = s_part[0];
+    tot_q = s_part[1];
+  }
+  const float inv_n = 1.0f / (static_cast<float>(cg) * hw);
+  const float mean = tot_s * inv_n;
+  const float var = fmaxf(tot_q * inv_n - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const float a0 = rstd * ga0, a1 = rstd * ga1;
+  const float b0 = be0 - mean * a0, b1 = be1 - mean * a1;
+  if (active) {
+#pragma unroll 8
+    for (int pix = p_begin + r0; pix < p_end; pix += rows_per_iter) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(src + static_cast<long long>(pix) * pitch));
+      float o0 = fmaf(f.x, a0, b0), o1 = fmaf(f.y, a1, b1);
+      if (silu) {
+        o0 = silu_f(o0);
+        o1 = silu_f(o1);
+      }
+      *reinterpret_cast<__half2*>(dst + static_cast<long long>(pix) * c) = __floats2half2_rn(o0, o1);
+    }
+  }
+  if (cs > 1) cluster_sync_all();  // nobody leaves while a partner may still read its shared memory
+}
+
 // LayerNorm: one warp per row, row cached in registers (c <= 1280 -> <= 40 values per lane)
 template <int VPL>  // half2 pairs per lane
 __global__ void layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
@@ -219,6 +333,28 @@ extern "C" int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int
                               static_cast<const float*>(stats_ws), static_cast<__half*>(y), hw, rows_apply, eps, silu));
   }
   count_launch(2);
+  return MDB_OK;
+}
+
+extern "C" int mdb_groupnorm_fused_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* gamma,
+                                       const float* beta, void* y, int32_t batch, int32_t hw, float eps, int32_t silu,
+                                       mdb_stream_t stream) {
+  const int c = c1 + (x2 ? c2 : 0);
+  if (!x2) c2 = 0;
+  MDB_REQUIRE(x1 && y && gamma && beta, "mdb_groupnorm_fused_f16: null pointer");
+  MDB_REQUIRE(c > 0 && c % 64 == 0 && c1 % 2 == 0 && c2 % 2 == 0 && c / 64 <= kGnFusedThreads,
+              "mdb_groupnorm_fused_f16: c must be a multiple of 64 (even channels per group), sources even (c1=%d c2=%d)",
+              c1, c2);
+  MDB_REQUIRE(batch > 0 && hw > 0 && batch <= 65535, "mdb_groupnorm_fused_f16: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // cluster size: enough CTAs to cover the SMs about twice, at least ~64 pixels per CTA, at most 8 (portable)
+  int cs = 1;
+  while (cs < 8 && 32 * batch * cs * 2 <= 320 && hw / (cs * 2) >= 64) cs *= 2;
+  MDB_CHECK_CUDA(launch_pdl_cluster(gn_fused_kernel, dim3(32, batch, cs), dim3(kGnFusedThreads), 0, st,
+                                    static_cast<unsigned>(cs), static_cast<const __half*>(x1), c1,
+                                    static_cast<const __half*>(x2), c2, gamma, beta, static_cast<__half*>(y), hw, eps,
+                                    silu));
+  count_launch(1);
   return MDB_OK;
 }
 

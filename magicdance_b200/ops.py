@@ -222,6 +222,14 @@ def attention(q, k0, vt0, n0, *, heads, d, batch, nq, out=None, kv0_batches=None
     return out
 
 
+def _gn_fused_max_batch():
+    """MDB_GN_FUSED=1 (opt-in; read per call — calls are captured into graphs, so this is off the replay path):
+    the single-launch GroupNorm for batches up to MDB_GN_FUSED_MAX_BATCH (default 4 = cond+uncond of two frames)"""
+    if os.environ.get("MDB_GN_FUSED", "0") != "1":
+        return 0
+    return int(os.environ.get("MDB_GN_FUSED_MAX_BATCH", "4"))
+
+
 GN_RING_SLOTS = 160     # >= GroupNorm calls of one network pass (61) with margin
 GN_RING_MAX_BATCH = 64
 _gn_ring_pos = {}
@@ -243,6 +251,11 @@ def groupnorm(x1, gamma, beta, *, batch, hw, eps, silu, x2=None, out=None):
     assert x1.is_contiguous() and (x2 is None or x2.is_contiguous())
     if out is None:
         out = torch.empty((batch * hw, c1 + c2), dtype=torch.float16, device=x1.device)
+    if batch <= _gn_fused_max_batch() and (c1 + c2) % 64 == 0:
+        # opt-in (MDB_GN_FUSED=1), not yet run on a GPU: one launch instead of stats -> apply for small batches
+        _lib.check(lib.mdb_groupnorm_fused_f16(x1.data_ptr(), c1, _ptr(x2), c2, gamma.data_ptr(), beta.data_ptr(),
+                                               out.data_ptr(), batch, hw, eps, int(silu), _stream()), "groupnorm_fused_f16")
+        return out
     key = (x1.device, _ws_tag)
     pos = _gn_ring_pos.get(key)
     if pos is not None and pos < GN_RING_SLOTS and batch <= GN_RING_MAX_BATCH:

@@ -27,3 +27,8 @@ echo "== secondary baseline: the reference's path as eager PyTorch (cuDNN/cuBLAS
 timeout 150 python tests/torch_gpu_baseline.py --batch 1 --steps 10 --warmup 2 > gpurun_out/torch_gpu_baseline_b1.json 2> gpurun_out/torch_gpu_baseline_b1.err; echo "rc=$?"; cat gpurun_out/torch_gpu_baseline_b1.json
 timeout 150 python tests/torch_gpu_baseline.py --batch 1 --steps 10 --warmup 2 --algorithmic > gpurun_out/torch_gpu_baseline_b1_alg.json 2>> gpurun_out/torch_gpu_baseline_b1.err; echo "rc=$?"; cat gpurun_out/torch_gpu_baseline_b1_alg.json
 timeout 150 python tests/torch_gpu_baseline.py --batch 8 --steps 5 --warmup 1 --algorithmic > gpurun_out/torch_gpu_baseline_b8_alg.json 2>> gpurun_out/torch_gpu_baseline_b1.err; echo "rc=$?"; cat gpurun_out/torch_gpu_baseline_b8_alg.json
+echo "== single-launch GroupNorm for small batches (MDB_GN_FUSED=1): numerics, per-shape time, one-frame step"
+timeout 100 python scripts/gpu_diag.py --group pending --pending-filter MDB_GN_FUSED > gpurun_out/pending_gnfused.log 2>&1; echo "rc=$? (124 = hung)"; tail -n 3 gpurun_out/pending_gnfused.log
+timeout 100 python scripts/gpu_microbench.py misc > gpurun_out/pending_microbench_misc.log 2>&1; echo "rc=$?"
+MDB_GN_FUSED=1 timeout 100 python scripts/gpu_microbench.py misc > gpurun_out/pending_microbench_misc_gnfused.log 2>&1; echo "rc=$?"
+MDB_GN_FUSED=1 timeout 90 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b1_gnfused.json 2> gpurun_out/pending_b1_gnfused.err; echo "rc=$? (124 = hung)"

@@ -377,7 +377,15 @@ ALL_CASES = [
 # by one under the caller's timeout (scripts/gpu_pending_checks.sh).  Move a case to ALL_CASES once it is green.
 _PAIRQ = (("MDB_GEMM_PAIR", "3"), ("MDB_GEMM_PAIR_MIN", "1"))     # persistent pair GEMM, TMA-store epilogue
 _PAIRS = (("MDB_GEMM_PAIR_SPLITK", "1"),)                         # pair tiles + split-K inside the cluster
+_GNF = (("MDB_GN_FUSED", "1"),)                                   # single-launch GroupNorm (cluster per batch x group)
 PENDING_CASES = [
+    (case_env, (_GNF, case_groupnorm, 2, 4096, 320, 0, 1e-5, True)),      # cluster of 4, 5 words per pixel
+    (case_env, (_GNF, case_groupnorm, 1, 1024, 640, 320, 1e-5, True)),    # concat: groups straddle the two sources
+    (case_env, (_GNF, case_groupnorm, 2, 64, 1280, 1280, 1e-5, True)),    # 8x8 level: one CTA per group
+    (case_env, (_GNF, case_groupnorm, 2, 256, 1280, 0, 1e-6, False)),
+    (case_env, (_GNF, case_groupnorm, 1, 16, 1280, 640, 1e-5, True)),
+    (case_env, (_GNF, case_groupnorm, 2, 4096, 640, 320, 1e-5, True)),    # 960 channels at 64x64: the largest slice
+    (case_env, (_GNF, case_groupnorm, 4, 1000, 320, 0, 1e-5, True)),      # pixel count not a multiple of anything
     (case_env, (_PAIRQ, case_gemm, 512, 256, 128)),                       # 256-wide tile, 2 pairs, one K pass of 2 chunks
     (case_env, (_PAIRQ, case_gemm, 384, 320, 320, True, True)),           # odd M tiles: last pair half empty; bias+residual
     (case_env, (_PAIRQ, case_gemm, 1000, 640, 1280, True, False)),        # ragged M (TMA store clips rows)
