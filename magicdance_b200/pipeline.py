@@ -150,6 +150,13 @@ def build_bank_slots(eng: DenoiseEngine, ref_latent, t_vec, context, layout, tok
         out_slots[:, off + n * c:off + 2 * n * c].view(tb, c, n).copy_(vt.view(c, tb, n).permute(1, 0, 2))
 
 
+def plan_bank_chunks(indices, chunk):
+    """[(first slot, [ddim indices])]: the sequence's distinct timesteps in the order the steps consume them, cut
+    into appearance-pass batches of at most `chunk`."""
+    idx = list(dict.fromkeys(int(i) for i in indices))
+    return [(s0, idx[s0:s0 + chunk]) for s0 in range(0, len(idx), chunk)]
+
+
 class GraphedDenoiser:
     """The whole DDIM step and the (timestep-batched) appearance-bank build captured once as CUDA
     graphs and replayed: at batch 1 the step is ~650 small kernels, so launch latency and Python
@@ -181,6 +188,12 @@ class GraphedDenoiser:
         self.replayed_launches = 0
         import os
         self.side = torch.cuda.Stream(device=dev) if os.environ.get("MDB_DUAL_STREAM", "1") != "0" else None
+        # Opt-in (MDB_BANK_OVERLAP=1; the stream plumbing below has not run on a GPU yet): build the appearance bank
+        # on its own stream WHILE the first DDIM steps run — a step only needs the bank of its own timestep, and at one
+        # frame per GPU the step's ~650 small kernels leave most of the tensor pipe idle.  The bank graph then owns
+        # its scratch lane and its memory pool (two graphs that replay concurrently must not share either).
+        self.overlap = os.environ.get("MDB_BANK_OVERLAP", "0") == "1"
+        self.bank_stream = torch.cuda.Stream(device=dev) if self.overlap else None
         # auxiliary streams for independent branches inside a block (engine._fork): lane 0 (UNet pass) -> lane 2,
         # lane 1 (ControlNet pass on the side stream) -> lane 3
         if os.environ.get("MDB_AUX_STREAMS", "1") != "0" and batch <= 2:
@@ -235,7 +248,13 @@ class GraphedDenoiser:
                             pred_x0=self.pred_x0)
         self.x.copy_(self.x_prev)
 
+    BANK_LANE = 4  # scratch lane of a bank build that overlaps the steps (lanes 0-3: UNet, ControlNet, their aux streams)
+
     def _bank_body(self):
+        if self.overlap:
+            with ops.workspace_lane(self.BANK_LANE):
+                build_bank_slots(self.eng, self.ref, self.t_vec, self.ctx, self.layout, self.tokens, self.bank_built)
+            return
         build_bank_slots(self.eng, self.ref, self.t_vec, self.ctx, self.layout, self.tokens, self.bank_built)
 
     def capture(self):
@@ -254,7 +273,7 @@ class GraphedDenoiser:
             self._bank_body()
         n1 = ops.launch_count()
         self.g_step = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_step, pool=self.g_bank.pool()):
+        with torch.cuda.graph(self.g_step, **({} if self.overlap else {"pool": self.g_bank.pool()})):
             self._step_body()
         torch.cuda.synchronize()
         # kernels of OUR library inside each graph (the C ABI counts launches at capture time only)
@@ -273,8 +292,28 @@ class GraphedDenoiser:
         self.replayed_launches += self.bank_launches
         out_slots.copy_(self.bank_built[:n])
 
-    def step(self, index, bank_flat):
-        """one DDIM step on self.x in place (result also in self.x_prev / self.pred_x0)"""
+    def build_bank_overlapped(self, indices, ref_latent, out_slots):
+        """Like build_bank for a whole sequence, but on the bank stream and chunk by chunk in the order the steps
+        will need them: returns {ddim index: (flat slot, event)}; a step waits for its own event only
+        (step(..., ready=event)), so denoising starts as soon as the first chunk exists."""
+        assert self.overlap, "construct the GraphedDenoiser with MDB_BANK_OVERLAP=1"
+        main, bs = torch.cuda.current_stream(), self.bank_stream
+        bs.wait_stream(main)  # the reference latent is uploaded; earlier readers of out_slots have been issued
+        table = {}
+        with torch.cuda.stream(bs):
+            for s0, part in plan_bank_chunks(indices, self.bank_chunk):
+                self.build_bank(part, ref_latent, out_slots[s0:s0 + len(part)])
+                ev = torch.cuda.Event()
+                ev.record(bs)
+                for j, ix in enumerate(part):
+                    table[ix] = (out_slots[s0 + j], ev)
+        return table
+
+    def step(self, index, bank_flat, ready=None):
+        """one DDIM step on self.x in place (result also in self.x_prev / self.pred_x0); `ready`: event after which
+        bank_flat is valid (overlapped bank build)"""
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready)
         self.t_cur.copy_(self.pipe.t_dev[index:index + 1])
         self.coef_cur.copy_(self.pipe.coef[index])
         self.bank_cur.copy_(bank_flat)

@@ -32,3 +32,7 @@ timeout 100 python scripts/gpu_diag.py --group pending --pending-filter MDB_GN_F
 timeout 100 python scripts/gpu_microbench.py misc > gpurun_out/pending_microbench_misc.log 2>&1; echo "rc=$?"
 MDB_GN_FUSED=1 timeout 100 python scripts/gpu_microbench.py misc > gpurun_out/pending_microbench_misc_gnfused.log 2>&1; echo "rc=$?"
 MDB_GN_FUSED=1 timeout 90 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b1_gnfused.json 2> gpurun_out/pending_b1_gnfused.err; echo "rc=$? (124 = hung)"
+echo "== bank build overlapped with the first steps (MDB_BANK_OVERLAP=1, one frame); compare value AND the final latent checksum with the default run"
+timeout 120 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b1_default.json 2> gpurun_out/pending_b1_default.err; echo "rc=$?"
+MDB_BANK_OVERLAP=1 timeout 120 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b1_overlap.json 2> gpurun_out/pending_b1_overlap.err; echo "rc=$? (124 = hung)"
+MDB_BANK_OVERLAP=1 MDB_BANK_CHUNK=5 timeout 120 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b1_overlap5.json 2> gpurun_out/pending_b1_overlap5.err; echo "rc=$? (124 = hung)"

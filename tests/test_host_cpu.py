@@ -113,6 +113,12 @@ def test_sharding_helpers():
         for w in (1, 2, 3, 8):
             c, share = P.bank_chunk_size(n, w), (n + w - 1) // w
             assert 1 <= c <= 25 and -(-share // c) == -(-share // 25)
+    # overlapped bank build: chunks follow the order in which the steps consume the timesteps, slots are contiguous
+    from magicdance_b200.pipeline import plan_bank_chunks
+    plan = plan_bank_chunks(idx, 10)
+    assert [s0 for s0, _ in plan] == [0, 10, 20, 30, 40] and plan[0][1] == list(range(49, 39, -1))
+    assert sum((part for _, part in plan), []) == idx
+    assert plan_bank_chunks([49, 48, 49, 47], 2) == [(0, [49, 48]), (2, [47])]  # repeated steps share one slot
 
 
 def test_header_is_plain_c_and_matches_the_ctypes_structs(tmp_path):
