@@ -1009,6 +1009,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_pairs_kernel(const __gri
   const uint32_t crank = cluster_ctarank();     // x + 2 * z inside the (2, 1, S) cluster
   const uint32_t pair_rank = crank & 1u;        // 0 = leader of its pair (issues the MMAs)
   const uint32_t leader = crank & ~1u;
+  // the pairing and the reduction below rely on the x-major linearisation of the cluster rank: fail loudly otherwise
+  if (pair_rank != (blockIdx.x & 1u) || (crank >> 1) != blockIdx.z) __trap();
   pdl_wait();  // a no-op unless launched with programmatic serialization
 
   if (warp == 0) {
@@ -1163,6 +1165,221 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_pairs_kernel(const __gri
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gemm_tc_kernel's plain path (one 128 x BN tile per CTA, no split-K, no cluster) with the TMA-store epilogue
+// of gemm_pairq_kernel (MDB_GEMM_TMAST=1) — NOT YET RUN ON A GPU, opt-in.  The main loop, the barriers and the
+// operand prefetches are those of the validated kernel; only the way the tile leaves the SM differs: each
+// epilogue warp packs 32 rows x 32 columns of fp16 into the (by then idle) operand ring and one lane issues a
+// cp.async.bulk.tensor store, instead of every lane writing 16-byte pieces one row pitch apart.  Aimed at the
+// short-K layers of the eight-frame regime (q/k/v/out projections, 1x1 convs, GEGLU: K = 320 ... 1280), where
+// the default epilogue takes longer than the main loop.
+// ------------------------------------------------------------------------------------------------
+template <int BN, bool GEGLU, int kStages>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+    gemm_ts_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ CUtensorMap tmD) {
+  using S = GemmSmem<BN, kStages, false>;
+  static_assert(kStages * S::kStageBytes >= 4 * 2 * kOutBufBytes, "the staging buffers live in the operand ring");
+  static_assert(BN % 32 == 0, "every 32-column store box must lie inside the tile");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_bias[BN];
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM;
+  const int n0 = blockIdx.y * BN;
+  const int n_iter = p.k_chunks;
+  constexpr uint32_t kTmemCols = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&tmD);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
+  const bool bias_in_smem = (p.bias != nullptr) && (p.bias_batch_stride == 0);
+  if (bias_in_smem && warp >= 2) {
+    for (int j = threadIdx.x - 64; j < BN; j += 128) s_bias[j] = (n0 + j < p.n) ? p.bias[n0 + j] : 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int b0 = 0, y0 = 0;
+      if (p.conv) {
+        b0 = m0 / p.hw;
+        y0 = (p.hw >= kBM) ? (m0 % p.hw) / p.w : 0;
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::kStageBytes;
+        uint8_t* sb = sa + S::kABytes;
+        mbar_expect_tx(&full_bar[s], S::kStageBytes);
+        if (p.conv) {
+          const int tap = it / p.chunks_per_tap;
+          const int cc = it - tap * p.chunks_per_tap;
+          const int kh = tap / 3, kw = tap - kh * 3;
+          tma_load_4d(sa, &p.tmA, &full_bar[s], cc * kBK, kw - 1, y0 + kh - 1, b0);
+        } else if (it < p.k1_chunks) {
+          tma_load_2d(sa, &p.tmA, &full_bar[s], it * kBK, m0);
+        } else {
+          tma_load_2d(sa, &p.tmA2, &full_bar[s], (it - p.k1_chunks) * kBK, m0);
+        }
+        tma_load_2d(sb, &p.tmB, &full_bar[s], it * kBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
+        const uint32_t b_addr = a_addr + S::kABytes;
+        const uint64_t da = umma_desc_k_sw128(a_addr);
+        const uint64_t db = umma_desc_k_sw128(b_addr);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&acc_bar);
+    }
+  } else {
+    // ---------------- epilogue warps 2..5 ----------------
+    const int g = warp & 3;
+    const int row0 = m0 + g * 32;
+    const long long row = static_cast<long long>(row0) + lane;
+    const bool row_ok = row < p.m;
+    constexpr int kResVecs = (GEGLU ? 0 : ((BN + 31) / 32) * 4);
+    uint4 res_pref[kResVecs > 0 ? kResVecs : 1];
+    const bool have_res = !GEGLU && (p.residual != nullptr);
+    if constexpr (!GEGLU) {
+      if (have_res) {
+        const __half* rrow = p.residual + row * p.ldr + n0;
+#pragma unroll
+        for (int q = 0; q < kResVecs; ++q) {
+          if (row_ok && q * 8 + 8 <= BN && n0 + q * 8 + 8 <= p.n) res_pref[q] = *reinterpret_cast<const uint4*>(rrow + q * 8);
+          else res_pref[q] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
+    const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
+    mbar_wait(&acc_bar, 0);  // every MMA has completed: the operand ring is idle and becomes the staging area
+    tc_fence_after_sync();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
+    uint8_t* obuf = smem + (warp - 2) * (2 * kOutBufBytes);
+    uint32_t ob = 0;
+    constexpr int kUnits = GEGLU ? BN / 64 : (BN + 31) / 32;
+#pragma unroll
+    for (int u = 0; u < kUnits; ++u) {
+      const int col0 = n0 + u * (GEGLU ? 64 : 32);
+      if (col0 >= p.n) break;  // warp-uniform
+      uint4 o4[4];
+      if constexpr (!GEGLU) {
+        uint32_t r[32];
+        tmem_ld_x32(taddr + u * 32, r);
+        tmem_wait_ld();
+        const int ncols = min(32, p.n - col0);
+        const float* bp = nullptr;
+        if (bias_in_smem) bp = s_bias + u * 32;
+        else if (p.bias != nullptr && row_ok) bp = p.bias + brow * p.bias_batch_stride + col0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[q * 8 + e]);
+          if (bp != nullptr && q * 8 + 8 <= ncols) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bp + q * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bp + q * 8 + 4);
+            o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+            o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+          }
+          if (have_res) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&res_pref[u * 4 + q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(h2[e]);
+              o[2 * e] += f.x;
+              o[2 * e + 1] += f.y;
+            }
+          }
+          o4[q].x = pack_half2(o[0], o[1]);
+          o4[q].y = pack_half2(o[2], o[3]);
+          o4[q].z = pack_half2(o[4], o[5]);
+          o4[q].w = pack_half2(o[6], o[7]);
+        }
+      } else {
+        uint32_t rv[32], rg[32];
+        tmem_ld_x32(taddr + u * 64, rv);
+        tmem_ld_x32(taddr + u * 64 + 32, rg);
+        tmem_wait_ld();
+        const float* bp = nullptr;
+        if (bias_in_smem) bp = s_bias + u * 64;
+        else if (p.bias != nullptr && row_ok) bp = p.bias + brow * p.bias_batch_stride + col0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = q * 8 + e;
+            float a = __uint_as_float(rv[j]);
+            float gt = __uint_as_float(rg[j]);
+            if (bp != nullptr) {
+              a += bp[j];
+              gt += bp[32 + j];
+            }
+            o[e] = a * gelu_erf_f(gt);
+          }
+          o4[q].x = pack_half2(o[0], o[1]);
+          o4[q].y = pack_half2(o[2], o[3]);
+          o4[q].z = pack_half2(o[4], o[5]);
+          o4[q].w = pack_half2(o[6], o[7]);
+        }
+      }
+      uint8_t* sbuf = obuf + ob * kOutBufBytes;
+      if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago has finished reading this buffer
+      __syncwarp();
+      uint4* srow = reinterpret_cast<uint4*>(sbuf + lane * (kOutBox * 2));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) srow[q] = o4[q];
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && row0 < p.m) {
+        tma_store_2d(&tmD, sbuf, GEGLU ? (col0 >> 1) : col0, row0);
+        tma_store_commit();
+      }
+      ob ^= 1u;
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -1356,6 +1573,20 @@ static int launch_gemm_pairq(const GemmKParams& kp, const CUtensorMap& tmD, int 
   void* args[2] = {const_cast<GemmKParams*>(&kp), const_cast<CUtensorMap*>(&tmD)};
   return launch_cluster_nopdl(reinterpret_cast<const void*>(kern), dim3(2 * clusters), dim3(kPairqThreads), kSmem, st, 2u,
                               1u, args);
+}
+
+template <int BN, bool GEGLU, int STAGES>
+static int launch_gemm_ts(const GemmKParams& kp, const CUtensorMap& tmD, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = gemm_ts_kernel<BN, GEGLU, STAGES>;
+  constexpr int kSmem = GemmSmem<BN, STAGES, false>::kTotal;
+  if (!attr_set) {
+    MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_set = true;
+  }
+  MDB_CHECK_CUDA(launch_pdl(kern, grid, dim3(kGemmThreads), kSmem, st, kp, tmD));
+  count_launch();
+  return MDB_OK;
 }
 
 template <int BN, int STAGES>
@@ -1578,6 +1809,19 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     else if (bn == 160) rc = deep ? launch_gemm<160, false, 8, true>(kp, grid, st) : launch_gemm<160, false, 4, true>(kp, grid, st);
     else if (bn == 256) rc = deep ? launch_gemm<256, false, 6, true>(kp, grid, st) : launch_gemm<256, false, 3, true>(kp, grid, st);
     else rc = deep ? launch_gemm<128, false, 8, true>(kp, grid, st) : launch_gemm<128, false, 4, true>(kp, grid, st);
+  } else if (getenv("MDB_GEMM_TMAST") != nullptr && getenv("MDB_GEMM_TMAST")[0] == '1' && splits == 1 && !deep &&
+             g->n % 8 == 0 && bn != 80) {  // 80-wide tiles end in a 16-column chunk: a 32-wide box would spill
+                                           // into the neighbouring tile
+    // opt-in, not yet run on a GPU: same tiles, output through shared memory + TMA (gemm_ts_kernel)
+    CUtensorMap tmD;
+    uint32_t boxd[2] = {(uint32_t)kOutBox, (uint32_t)kOutBox};
+    uint64_t dimsd[2] = {(uint64_t)(geglu ? g->n / 2 : g->n), (uint64_t)g->m};
+    uint64_t strd[1] = {(uint64_t)g->ldd * 2};
+    rc = make_tmap_f16_plain(&tmD, g->d, 2, dimsd, strd, boxd);
+    if (rc) return rc;
+    if (geglu) rc = launch_gemm_ts<128, true, 3>(kp, tmD, grid, st);
+    else if (bn == 160) rc = launch_gemm_ts<160, false, 3>(kp, tmD, grid, st);
+    else rc = launch_gemm_ts<128, false, 3>(kp, tmD, grid, st);
   } else if (geglu) rc = launch_gemm<128, true, 3>(kp, grid, st);
   else if (bn == 160) rc = deep ? launch_gemm<160, false, 6>(kp, grid, st) : launch_gemm<160, false, 3>(kp, grid, st);
   else if (bn == 80) rc = deep ? launch_gemm<80, false, 8>(kp, grid, st) : launch_gemm<80, false, 3>(kp, grid, st);

@@ -36,3 +36,7 @@ echo "== bank build overlapped with the first steps (MDB_BANK_OVERLAP=1, one fra
 timeout 120 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b1_default.json 2> gpurun_out/pending_b1_default.err; echo "rc=$?"
 MDB_BANK_OVERLAP=1 timeout 120 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b1_overlap.json 2> gpurun_out/pending_b1_overlap.err; echo "rc=$? (124 = hung)"
 MDB_BANK_OVERLAP=1 MDB_BANK_CHUNK=5 timeout 120 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b1_overlap5.json 2> gpurun_out/pending_b1_overlap5.err; echo "rc=$? (124 = hung)"
+echo "== default GEMM tiles with the TMA-store epilogue (MDB_GEMM_TMAST=1): numerics, per-shape time at eight frames, full step"
+timeout 120 python scripts/gpu_diag.py --group pending --pending-filter MDB_GEMM_TMAST > gpurun_out/pending_tmast.log 2>&1; echo "rc=$? (124 = hung)"; tail -n 3 gpurun_out/pending_tmast.log
+MDB_GEMM_TMAST=1 timeout 200 python scripts/gpu_microbench.py pair 0 > gpurun_out/pending_microbench_tmast.log 2>&1; echo "rc=$?"
+MDB_GEMM_TMAST=1 timeout 90 python bench.py --batch 8 --steps 20 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/pending_b8_tmast.json 2> gpurun_out/pending_b8_tmast.err; echo "rc=$? (124 = hung)"

@@ -377,8 +377,19 @@ ALL_CASES = [
 # by one under the caller's timeout (scripts/gpu_pending_checks.sh).  Move a case to ALL_CASES once it is green.
 _PAIRQ = (("MDB_GEMM_PAIR", "3"), ("MDB_GEMM_PAIR_MIN", "1"))     # persistent pair GEMM, TMA-store epilogue
 _PAIRS = (("MDB_GEMM_PAIR_SPLITK", "1"),)                         # pair tiles + split-K inside the cluster
+_TMAST = (("MDB_GEMM_TMAST", "1"),)                              # default tiles, TMA-store epilogue (gemm_ts_kernel)
 _GNF = (("MDB_GN_FUSED", "1"),)                                   # single-launch GroupNorm (cluster per batch x group)
 PENDING_CASES = [
+    (case_env, (_TMAST, case_gemm, 8192, 320, 320, True, True)),          # 160-wide tiles, K = 5 chunks
+    (case_env, (_TMAST, case_gemm, 16384, 640, 640, True, True)),
+    (case_env, (_TMAST, case_gemm, 1000, 384, 192, True, True)),          # 128-wide tiles, ragged M
+    (case_env, (_TMAST, case_gemm, 520, 200, 128, True, True)),           # N = 200: last box clipped by the tensor map
+    (case_env, (_TMAST, case_gemm_batch_bias, 8, 1024, 640, 320)),
+    (case_env, (_TMAST, case_gemm_dual, 8192, 640, 640, 320)),
+    (case_env, (_TMAST, case_gemm_strided_out, 320, 80, 768)),            # row pitch > N: columns beyond N stay untouched
+    (case_env, (_TMAST, case_geglu, 4096, 320)),
+    (case_env, (_TMAST, case_geglu, 64, 1280)),
+    (case_env, (_TMAST, case_conv, 8, 32, 32, 640, 640, True, True)),
     (case_env, (_GNF, case_groupnorm, 2, 4096, 320, 0, 1e-5, True)),      # cluster of 4, 5 words per pixel
     (case_env, (_GNF, case_groupnorm, 1, 1024, 640, 320, 1e-5, True)),    # concat: groups straddle the two sources
     (case_env, (_GNF, case_groupnorm, 2, 64, 1280, 1280, 1e-5, True)),    # 8x8 level: one CTA per group
