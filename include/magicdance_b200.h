@@ -148,6 +148,12 @@ int mdb_conv3x3_direct_f16(const void* x, const void* wt, const float* bias, con
 int mdb_im2col3x3_f16(const void* x, void* col, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t stride,
                       mdb_stream_t stream);
 
+/* The same gather for a window anchored at the output pixel with ONE padding row / column at the bottom / right
+ * only: ho = (h + 1 - 3)/stride + 1.  Replaces F.pad(x, (0,1,0,1)) + Conv2d(k=3, stride=2, padding=0) of the
+ * first-stage VAE encoder's Downsample (ldm/modules/diffusionmodules/model.py:71-90) together with mdb_gemm_f16. */
+int mdb_im2col3x3_br_f16(const void* x, void* col, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t stride,
+                         mdb_stream_t stream);
+
 /* nearest x2 upsample (Upsample.forward, openaimodel.py:129-139): NHWC [B][h][w][c] -> [B][2h][2w][c] */
 int mdb_upsample2x_f16(const void* x, void* y, int32_t batch, int32_t h, int32_t w, int32_t c, mdb_stream_t stream);
 

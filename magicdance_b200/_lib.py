@@ -53,6 +53,7 @@ SIGNATURES = {
     "mdb_conv3x3_direct_f16": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mdb_im2col3x3_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "mdb_im2col3x3_br_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mdb_upsample2x_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mdb_add_f16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "mdb_timestep_embedding_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),

@@ -270,6 +270,32 @@ __global__ void im2col3x3_kernel(const __half* __restrict__ x, __half* __restric
   }
 }
 
+// Same gather with the window anchored at the output pixel (no top/left halo) and zero fill past the bottom /
+// right edge: the first-stage VAE encoder's Downsample pads (0,1,0,1) and convolves with stride 2, padding 0
+// (ldm/modules/diffusionmodules/model.py:82-84).  Not yet run on a GPU (VAE encoder, opt-in).
+__global__ void im2col3x3_br_kernel(const __half* __restrict__ x, __half* __restrict__ col, int batch, int h, int w,
+                                    int c, int stride, int ho, int wo) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int vecs = c / 8;
+  const long long total = static_cast<long long>(batch) * ho * wo * 9 * vecs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vecs);
+    long long r = i / vecs;
+    const int t = static_cast<int>(r % 9);
+    r /= 9;  // output pixel index
+    const int ox = static_cast<int>(r % wo);
+    const int oy = static_cast<int>((r / wo) % ho);
+    const int b = static_cast<int>(r / (static_cast<long long>(wo) * ho));
+    const int yy = oy * stride + t / 3, xx = ox * stride + t % 3;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (yy < h && xx < w)
+      val = *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * h + yy) * w + xx) * c + v * 8);
+    *reinterpret_cast<uint4*>(col + (r * 9 + t) * c + v * 8) = val;
+  }
+}
+
 __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ y, int batch, int h, int w, int c) {
   pdl_launch_dependents();
   pdl_wait();
@@ -620,6 +646,20 @@ extern "C" int mdb_im2col3x3_f16(const void* x, void* col, int32_t batch, int32_
   const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
   const long long total = static_cast<long long>(batch) * ho * wo * 9 * (c / 8);
   MDB_CHECK_CUDA(launch_pdl(im2col3x3_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                            static_cast<const __half*>(x), static_cast<__half*>(col), batch, h, w, c, stride, ho, wo));
+  count_launch();
+  return MDB_OK;
+}
+
+extern "C" int mdb_im2col3x3_br_f16(const void* x, void* col, int32_t batch, int32_t h, int32_t w, int32_t c,
+                                    int32_t stride, mdb_stream_t stream) {
+  MDB_REQUIRE(x && col, "mdb_im2col3x3_br_f16: null pointer");
+  MDB_REQUIRE(c % 8 == 0 && (stride == 1 || stride == 2), "mdb_im2col3x3_br_f16: need c %% 8 == 0 and stride 1 or 2");
+  MDB_REQUIRE(h >= 2 && w >= 2, "mdb_im2col3x3_br_f16: image too small");
+  // input padded by one row / column at the bottom / right, 3x3 window, no other padding
+  const int ho = (h + 1 - 3) / stride + 1, wo = (w + 1 - 3) / stride + 1;
+  const long long total = static_cast<long long>(batch) * ho * wo * 9 * (c / 8);
+  MDB_CHECK_CUDA(launch_pdl(im2col3x3_br_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream),
                             static_cast<const __half*>(x), static_cast<__half*>(col), batch, h, w, c, stride, ho, wo));
   count_launch();
   return MDB_OK;

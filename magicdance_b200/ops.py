@@ -292,9 +292,18 @@ def conv3x3_direct(x, wt, bias, *, batch, h, w, cin, cout, stride=1, silu=False,
     return out
 
 
-def im2col3x3(x, *, batch, h, w, c, stride):
+def im2col3x3(x, *, batch, h, w, c, stride, pad="same"):
+    """pad='same': one halo pixel on every side (the UNet's convolutions); pad='br': one padding row / column
+    at the bottom / right only (the VAE encoder's Downsample, model.py:82-84)"""
     lib = _lib.load()
     _chk(x, torch.float16, "x")
+    if pad == "br":
+        ho, wo = (h + 1 - 3) // stride + 1, (w + 1 - 3) // stride + 1
+        col = torch.empty((batch * ho * wo, 9 * c), dtype=torch.float16, device=x.device)
+        _lib.check(lib.mdb_im2col3x3_br_f16(x.data_ptr(), col.data_ptr(), batch, h, w, c, stride, _stream()),
+                   "im2col3x3_br_f16")
+        return col
+    assert pad == "same"
     ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
     col = torch.empty((batch * ho * wo, 9 * c), dtype=torch.float16, device=x.device)
     _lib.check(lib.mdb_im2col3x3_f16(x.data_ptr(), col.data_ptr(), batch, h, w, c, stride, _stream()), "im2col3x3_f16")

@@ -162,3 +162,132 @@ class VaeDecoder:
         h = ops.groupnorm(a.data, *p.out_gn, batch=a.b, hw=a.hw, eps=GN_EPS, silu=True)
         y = ops.conv3x3_direct(h, p.out_w, p.out_b, batch=a.b, h=a.h, w=a.w, cin=a.c, cout=p.c_out)
         return ops.nhwc_f16_to_nchw_f32(y, batch=a.b, c=p.c_out, h=a.h, w=a.w)
+
+
+# =====================================================================================================================
+# Encoder (encode_first_stage: ddpm.py:2109-2117 -> autoencoder.py:82-86 -> model.py:518-543) — the reference image is
+# encoded once per sequence (1116.7 GFLOP at 512x512).  Same kernels as the decoder plus ops.im2col3x3(pad="br") for the
+# Downsample's bottom/right padding.  NOT YET VALIDATED ON A GPU, opt-in like the decoder.
+# =====================================================================================================================
+def _center_tap(w1x1, scale=1.0):
+    """[O, I, 1, 1] -> a 3x3 kernel whose only non-zero tap is the centre (a 1x1 conv on the direct-conv kernel)"""
+    o, i = w1x1.shape[:2]
+    w3 = torch.zeros(o, i, 3, 3)
+    w3[:, :, 1, 1] = w1x1[:, :, 0, 0] * scale
+    return w3
+
+
+class _Attn:
+    """single-head attention over all channels (model.py:152-203): scale folded into q, v bias into proj_out"""
+
+    def __init__(self, take, a, c, device):
+        self.gn = (_f32(take(a + ".norm.weight"), device), _f32(take(a + ".norm.bias"), device))
+        s = float(c) ** -0.5
+        self.wq = _f16(take(a + ".q.weight").reshape(c, c) * s, device)
+        self.bq = _f32(take(a + ".q.bias") * s, device)
+        self.wk, self.bk = pack_conv1x1(take(a + ".k.weight"), device), _f32(take(a + ".k.bias"), device)
+        self.wv = pack_conv1x1(take(a + ".v.weight"), device)
+        bv = take(a + ".v.bias")
+        wp = take(a + ".proj_out.weight").reshape(c, c)
+        self.wp = _f16(wp, device)
+        self.bp = _f32(take(a + ".proj_out.bias") + wp @ bv, device)
+
+
+class PackedVaeEncoder:
+    """fp16 repack of `first_stage_model.{encoder.*, quant_conv}`; `consumed` lists the keys read."""
+
+    def __init__(self, state_dict, device="cuda"):
+        self.device = torch.device(device)
+        self.consumed = []
+        dev = self.device
+
+        def take(name):
+            key = PREFIX + name
+            self.consumed.append(key)
+            return state_dict[key].detach().float()
+
+        self.in_w = pack_conv3x3(take("encoder.conv_in.weight"), dev)                # [128, 27]
+        self.in_b = _f32(take("encoder.conv_in.bias"), dev)
+        self.c0 = self.in_w.shape[0]
+        self.down = []
+        for lvl in range(len(CH_MULT)):
+            blocks = [_Res(take, f"encoder.down.{lvl}.block.{i}", dev) for i in range(NUM_RES_BLOCKS)]
+            ds = None
+            if lvl != len(CH_MULT) - 1:
+                ds = (pack_conv3x3(take(f"encoder.down.{lvl}.downsample.conv.weight"), dev),
+                      _f32(take(f"encoder.down.{lvl}.downsample.conv.bias"), dev))
+            self.down.append((blocks, ds))
+        self.mid1 = _Res(take, "encoder.mid.block_1", dev)
+        self.c_mid = self.mid1.cout
+        self.attn = _Attn(take, "encoder.mid.attn_1", self.c_mid, dev)
+        self.mid2 = _Res(take, "encoder.mid.block_2", dev)
+        self.out_gn = (_f32(take("encoder.norm_out.weight"), dev), _f32(take("encoder.norm_out.bias"), dev))
+        self.out_w = pack_conv3x3(take("encoder.conv_out.weight"), dev)              # [8, 9*512]
+        self.out_b = _f32(take("encoder.conv_out.bias"), dev)
+        self.c_out = self.out_w.shape[0]
+        self.q_w = pack_conv3x3(_center_tap(take("quant_conv.weight")), dev)         # 1x1 conv, autoencoder.py:33,84
+        self.q_b = _f32(take("quant_conv.bias"), dev)
+
+
+class VaeEncoder:
+    """encode(x): image [B, 3, H, W] fp32 in [-1, 1] -> the posterior's moments [B, 8, H/8, W/8] fp32 (mean | logvar),
+    i.e. what AutoencoderKL.encode wraps in DiagonalGaussianDistribution (autoencoder.py:82-86)."""
+
+    def __init__(self, packed: PackedVaeEncoder):
+        ops.ensure_device()
+        self.p = packed
+
+    _res = VaeDecoder._res
+
+    def _attn(self, x: Act) -> Act:
+        a, n = self.p.attn, x.hw
+        assert n % 64 == 0, "the P V product runs as a GEMM over the token axis: h*w must be a multiple of 64"
+        h = ops.groupnorm(x.data, *a.gn, batch=x.b, hw=n, eps=GN_EPS, silu=False)
+        q = ops.gemm(h, a.wq, bias=a.bq)
+        k = ops.gemm(h, a.wk, bias=a.bk)
+        o = torch.empty_like(q)
+        for b in range(x.b):
+            rows = slice(b * n, (b + 1) * n)
+            vt = ops.gemm(a.wv, h[rows])
+            s = ops.gemm(q[rows], k[rows])
+            ops.softmax_rows(s)
+            ops.gemm(s, vt, out=o[rows])
+        return Act(ops.gemm(o, a.wp, bias=a.bp, residual=x.data), x.b, x.h, x.w)
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("magicdance_b200.vae: the encoder runs on CUDA kernels only (no CPU fallback)")
+        return self._encode(x)
+
+    def _encode(self, x: torch.Tensor) -> torch.Tensor:
+        p = self.p
+        assert x.dim() == 4 and x.shape[1] == 3 and x.shape[2] % 8 == 0 and x.shape[3] % 8 == 0, "image must be [B, 3, 8h, 8w]"
+        b, _, hh, ww = x.shape
+        t = ops.nchw_f32_to_nhwc_f16(x.float())                                         # [b*H*W, 3]
+        t = ops.conv3x3_direct(t, p.in_w, p.in_b, batch=b, h=hh, w=ww, cin=3, cout=p.c0)
+        a = Act(t, b, hh, ww)
+        for blocks, ds in p.down:
+            for r in blocks:
+                a = self._res(r, a)
+            if ds is not None:  # F.pad(x, (0,1,0,1)) + conv(k=3, s=2, p=0)  (model.py:82-84)
+                col = ops.im2col3x3(a.data, batch=a.b, h=a.h, w=a.w, c=a.c, stride=2, pad="br")
+                a = Act(ops.gemm(col, ds[0], bias=ds[1]), a.b, a.h // 2, a.w // 2)
+        a = self._res(p.mid1, a)
+        a = self._attn(a)
+        a = self._res(p.mid2, a)
+        h = ops.groupnorm(a.data, *p.out_gn, batch=a.b, hw=a.hw, eps=GN_EPS, silu=True)
+        y = ops.conv3x3_direct(h, p.out_w, p.out_b, batch=a.b, h=a.h, w=a.w, cin=a.c, cout=p.c_out)
+        y = ops.conv3x3_direct(y, p.q_w, p.q_b, batch=a.b, h=a.h, w=a.w, cin=p.c_out, cout=p.c_out)   # quant_conv
+        return ops.nhwc_f16_to_nchw_f32(y, batch=a.b, c=p.c_out, h=a.h, w=a.w)
+
+
+def posterior_sample(moments: torch.Tensor, noise: torch.Tensor | None = None) -> torch.Tensor:
+    """DiagonalGaussianDistribution.sample / .mode (distributions.py:27-37,59-60) on the [B, 8, h, w] moments: a
+    few elementwise operations on a 128 KB tensor, done with torch on the device the moments live on (off the hot
+    path; the reference does the same arithmetic in torch)."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    if noise is None:
+        return mean
+    return mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise
+

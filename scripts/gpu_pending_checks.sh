@@ -95,6 +95,6 @@ if want baseline; then
 fi
 
 if want vae; then
-  echo "== VAE decoder (softmax kernel, GroupNorm with 4 channels/group, 128-pixel-row implicit GEMM, im2col at 256/512)"
-  timeout 200 python scripts/gpu_vae_parity.py > gpurun_out/pending_vae.log 2>&1; echo "vae rc=$?"; tail -n 12 gpurun_out/pending_vae.log
+  echo "== VAE decoder + encoder (softmax kernel, br-padded im2col, GroupNorm with 4 channels/group, 128-pixel-row implicit GEMM, im2col at 256/512)"
+  timeout 400 python scripts/gpu_vae_parity.py > gpurun_out/pending_vae.log 2>&1; echo "vae rc=$?"; tail -n 12 gpurun_out/pending_vae.log
 fi

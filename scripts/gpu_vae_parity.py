@@ -1,4 +1,4 @@
-"""GPU parity of the (not yet validated) VAE decoder in magicdance_b200/vae.py against the pinned CPU oracle and
+"""GPU parity of the (not yet validated) VAE decoder and encoder in magicdance_b200/vae.py against the pinned CPU oracle and
 the reference goldens.  Run on a B200:
 
     python scripts/gpu_vae_parity.py            # latent 16 (B=2) and latent 64 (B=1)
@@ -18,7 +18,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from magicdance_b200 import ops, synth  # noqa: E402
-from magicdance_b200.vae import PackedVaeDecoder, VaeDecoder  # noqa: E402
+from magicdance_b200.vae import PackedVaeDecoder, PackedVaeEncoder, VaeDecoder, VaeEncoder  # noqa: E402
 from oracle import vae_restatement as V  # noqa: E402  (checker only)
 
 TOL = 5e-3
@@ -80,6 +80,31 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
             print(f"   decode 64x64 -> 512x512: {ms:.2f} ms/frame = {2514.5 / ms:.1f} TFLOP/s (2514.5 GFLOP per frame)")
+    # ---- encoder (encode_first_stage): the br-padded im2col, then the whole stack against the golden moments ----
+    xi = torch.randn(2 * 16 * 16, 64, device="cuda").half()
+    col = ops.im2col3x3(xi, batch=2, h=16, w=16, c=64, stride=2, pad="br").float()
+    xp = torch.nn.functional.pad(xi.float().reshape(2, 16, 16, 64).permute(0, 3, 1, 2), (0, 1, 0, 1))
+    rc = torch.nn.functional.unfold(xp, 3, padding=0, stride=2).reshape(2, 64, 9, 64).permute(0, 3, 2, 1).reshape(128, 576)
+    e = rel(col, rc)
+    print(f"im2col3x3 pad=br stride 2: rel-L2 {e:.2e}")
+    bad += e > 1e-6
+    enc = VaeEncoder(PackedVaeEncoder(sd, "cuda"))
+    for batch, latent, gname in ((2, 16, "vae16"), (1, 64, None)):
+        _, img_in, noise = V.vae_inputs(batch, latent)
+        t0 = time.time()
+        mom = enc.encode(img_in.cuda())
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        oracle = V.vae_encode_moments(sd, img_in)
+        e = rel(mom, oracle)
+        print(f"encode {latent * 8}x{latent * 8} B={batch}: moments rel-L2 vs CPU oracle {e:.3e} (first call {dt * 1e3:.1f} ms, "
+              f"finite={bool(torch.isfinite(mom).all())})")
+        bad += not (e <= TOL)
+        if gname:
+            g = np.load(os.path.join(REPO, "tests", "golden", gname + ".npz"))
+            e2 = rel(mom, torch.from_numpy(g[gname + "/moments"]))
+            print(f"   vs reference golden moments: {e2:.3e}")
+            bad += not (e2 <= TOL)
     print("FAILED" if bad else "OK")
     return 1 if bad else 0
 

@@ -126,10 +126,14 @@ def nhwc_f16_to_nchw_f32(x, *, batch, c, h, w, out=None):
     return x.float().reshape(batch, h, w, c).permute(0, 3, 1, 2).contiguous()
 
 
-def im2col3x3(x, *, batch, h, w, c, stride):
+def im2col3x3(x, *, batch, h, w, c, stride, pad="same"):
     xi = x.float().reshape(batch, h, w, c).permute(0, 3, 1, 2)
-    cols = F.unfold(xi, 3, padding=1, stride=stride)                      # [b, c*9, L], channel-major
-    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    if pad == "br":  # one padding row / column at the bottom / right only
+        cols = F.unfold(F.pad(xi, (0, 1, 0, 1)), 3, padding=0, stride=stride)
+        ho, wo = (h + 1 - 3) // stride + 1, (w + 1 - 3) // stride + 1
+    else:
+        cols = F.unfold(xi, 3, padding=1, stride=stride)                  # [b, c*9, L], channel-major
+        ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
     cols = cols.reshape(batch, c, 9, ho * wo).permute(0, 3, 2, 1)         # -> tap-major, channel-minor
     return _h(cols.reshape(batch * ho * wo, 9 * c)).contiguous()
 

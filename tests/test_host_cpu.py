@@ -205,3 +205,48 @@ def test_vae_decoder_orchestration_matches_the_oracle_with_cpu_test_doubles(monk
     assert tuple(img.shape) == (2, 3, 128, 128) and err <= 5e-3, err
     with __import__("pytest").raises(RuntimeError, match="no CPU fallback"):
         dec.decode(z)  # the public entry refuses CPU tensors
+
+
+def test_vae_encoder_orchestration_matches_the_reference_golden_with_cpu_test_doubles(monkeypatch):
+    """The VAE encoder's host logic (magicdance_b200/vae.py: the bottom/right-padded stride-2 downsample as
+    im2col(pad="br") + GEMM, ResnetBlocks, the single-head attention, quant_conv as a centre-tap conv) on the CPU test
+    doubles must reproduce the moments and the scaled posterior sample the UNMODIFIED reference produced
+    (tests/golden/vae16.npz), and its repack must read every encoder / quant_conv tensor exactly once."""
+    import json
+    import os
+    import numpy as np
+    import torch
+    from magicdance_b200 import ops, synth, vae
+    from oracle import vae_restatement as V
+    from tests import fake_ops
+    for name in ("gemm", "conv3x3_direct", "groupnorm", "softmax_rows", "nchw_f32_to_nhwc_f16", "nhwc_f16_to_nchw_f32",
+                 "im2col3x3"):
+        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(here, "magicdance_b200", "vae_manifest.json")) as f:
+        manifest = json.load(f)
+    torch.set_grad_enabled(False)
+    sd = synth.synth_state_dict(manifest, seed=0)
+    enc = vae.VaeEncoder.__new__(vae.VaeEncoder)  # no device check: the test doubles run on the CPU
+    enc.p = vae.PackedVaeEncoder(sd, "cpu")
+    want = {k for k in manifest if k.startswith(vae.PREFIX + "encoder.") or k.startswith(vae.PREFIX + "quant_conv.")}
+    assert sorted(enc.p.consumed) == sorted(want) and len(set(enc.p.consumed)) == len(enc.p.consumed)
+    # decoder + encoder + post_quant_conv + quant_conv = the whole first_stage_model
+    dec = vae.PackedVaeDecoder(sd, "cpu")
+    assert set(enc.p.consumed) | set(dec.consumed) == {k for k in manifest if k.startswith(vae.PREFIX)}
+    _, img, noise = V.vae_inputs(2, 16)
+    mom = enc._encode(img)
+    gold = np.load(os.path.join(here, "tests", "golden", "vae16.npz"))
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    assert tuple(mom.shape) == (2, 8, 16, 16) and rel(mom, torch.from_numpy(gold["vae16/moments"])) <= 5e-3
+    z = vae.SCALE_FACTOR * vae.posterior_sample(mom, noise)      # get_first_stage_encoding, ddpm.py:1936-1942
+    assert rel(z, torch.from_numpy(gold["vae16/encoding"])) <= 5e-3
+    assert torch.equal(vae.posterior_sample(mom), mom[:, :4])    # .mode()
+    # the double of the br-padded gather is the reference's own F.pad(x, (0,1,0,1)) + unfold(padding=0)
+    x = torch.randn(2 * 6 * 6, 8).half()
+    col = fake_ops.im2col3x3(x, batch=2, h=6, w=6, c=8, stride=2, pad="br")
+    assert tuple(col.shape) == (2 * 3 * 3, 72)
+    assert torch.equal(col[0, :8], x[0]) and torch.equal(col[2, 2 * 8:3 * 8], torch.zeros(8).half())  # right edge pad
+    with __import__("pytest").raises(RuntimeError, match="no CPU fallback"):
+        enc.encode(img)
+
