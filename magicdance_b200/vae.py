@@ -55,7 +55,9 @@ class PackedVaeDecoder:
     """fp16 repack of `first_stage_model.{post_quant_conv, decoder.*}` (PyTorch-native layouts in, kernel layouts
     out).  `consumed` lists the state-dict keys read, so a test can check nothing is silently ignored."""
 
-    def __init__(self, state_dict, device="cuda"):
+    def __init__(self, state_dict, device="cuda", scale_factor=SCALE_FACTOR):
+        """scale_factor: decode() takes the latent as the sampler returns it and divides by this first
+        (decode_first_stage, ddpm.py:2107); pass 1.0 to get AutoencoderKL.decode (autoencoder.py:88-91)."""
         self.device = torch.device(device)
         self.consumed = []
         dev = self.device
@@ -66,7 +68,7 @@ class PackedVaeDecoder:
             return state_dict[key].detach().float()
 
         # post_quant_conv (autoencoder.py:34,89) on z / scale_factor (ddpm.py:2107): centre tap of a 3x3
-        wpq = take("post_quant_conv.weight")[:, :, 0, 0] / SCALE_FACTOR            # [4, 4]
+        wpq = take("post_quant_conv.weight")[:, :, 0, 0] / float(scale_factor)      # [4, 4]
         w3 = torch.zeros(4, 4, 3, 3)
         w3[:, :, 1, 1] = wpq
         self.pq_w, self.pq_b = pack_conv3x3(w3, dev), _f32(take("post_quant_conv.bias"), dev)

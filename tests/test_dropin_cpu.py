@@ -108,3 +108,52 @@ def test_dropin_apply_model_orchestration_matches_reference_small32(model, monke
     assert len(res) == 13
     for i, r in enumerate(res):
         G.check_summary(g, f"small32/pose{i}", r, 5e-3)
+
+
+def test_autoencoder_dropin_has_the_reference_keys_and_decodes_through_the_test_doubles(monkeypatch):
+    """magicdance_b200.dropin.autoencoder.AutoencoderKL (opt-in first_stage target): the reference's constructor
+    kwargs (yaml:93-114), exactly its 248 state-dict keys / shapes (manifest recorded from the unmodified reference),
+    strict load, loud failure on the CPU, and — through the CPU test doubles — decode(z / scale_factor) equal to the
+    reference's golden image and encode(x).mode() equal to its golden moments' mean."""
+    import json
+    import os
+    import numpy as np
+    import pytest
+    from magicdance_b200 import ops, synth, vae
+    from magicdance_b200.dropin.autoencoder import AutoencoderKL, DiagonalGaussianDistribution
+    from oracle import vae_restatement as V
+    from tests import fake_ops
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(here, "magicdance_b200", "vae_manifest.json")) as f:
+        manifest = json.load(f)
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    m = AutoencoderKL(ddconfig=dd, lossconfig={"target": "torch.nn.Identity"}, embed_dim=4, monitor="val/rec_loss")
+    want = {k[len(vae.PREFIX):]: tuple(v) for k, v in manifest.items()}
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == want and len(want) == 248
+    sd = synth.synth_state_dict(manifest, seed=0)
+    m.load_state_dict({k[len(vae.PREFIX):]: v for k, v in sd.items()}, strict=True)
+    with pytest.raises(NotImplementedError):
+        AutoencoderKL(ddconfig=dict(dd, ch=64), lossconfig=None, embed_dim=4)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m.decode(torch.zeros(1, 4, 16, 16))
+    for name in ("gemm", "conv3x3_direct", "groupnorm", "upsample2x", "softmax_rows", "nchw_f32_to_nhwc_f16",
+                 "nhwc_f16_to_nchw_f32", "im2col3x3"):
+        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    torch.set_grad_enabled(False)
+    try:
+        dec = vae.VaeDecoder.__new__(vae.VaeDecoder)
+        dec.p = vae.PackedVaeDecoder(m._prefixed_state(), "cpu", scale_factor=1.0)   # what decoder_engine() packs
+        enc = vae.VaeEncoder.__new__(vae.VaeEncoder)
+        enc.p = vae.PackedVaeEncoder(m._prefixed_state(), "cpu")
+        z, img, noise = V.vae_inputs(2, 16)
+        gold = np.load(os.path.join(here, "tests", "golden", "vae16.npz"))
+        rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+        assert rel(dec._decode(z / vae.SCALE_FACTOR), torch.from_numpy(gold["vae16/decoded"])) <= 5e-3
+        post = DiagonalGaussianDistribution(enc._encode(img))
+        gm = torch.from_numpy(gold["vae16/moments"])
+        assert rel(post.mode(), gm[:, :4]) <= 5e-3 and post.sample().shape == (2, 4, 16, 16)
+        assert torch.allclose(post.std, torch.exp(0.5 * torch.clamp(post.parameters[:, 4:], -30, 20)))
+    finally:
+        torch.set_grad_enabled(True)
+
