@@ -1698,7 +1698,11 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   {
     const char* ps_env = getenv("MDB_GEMM_PAIR_SPLITK");
     const int mt = (g->m + kBM - 1) / kBM;
-    if (ps_env != nullptr && ps_env[0] == '1' && !geglu && mt >= 2 && g->n % 8 == 0) {
+    // long-K layers only (3x3 convs, the 4C -> C feed-forward): with a handful of K chunks the park-and-reduce
+    // epilogue costs more than the operand traffic it saves.  MDB_GEMM_PAIR_SPLITK_MINK overrides the threshold.
+    const char* mink_env = getenv("MDB_GEMM_PAIR_SPLITK_MINK");
+    const int min_chunks = mink_env ? atoi(mink_env) : 16;
+    if (ps_env != nullptr && ps_env[0] == '1' && !geglu && mt >= 2 && g->n % 8 == 0 && kp.k_chunks >= min_chunks) {
       const int bnp = (g->n % 160 == 0) ? 160 : 128;
       const int m_pairs = (mt + 1) / 2;
       const int n_tiles = (g->n + bnp - 1) / bnp;

@@ -127,6 +127,7 @@ def main():
         from magicdance_b200.engine import _auto_splits
         for mode in ("0", "1"):
             os.environ["MDB_GEMM_PAIR_SPLITK"] = mode
+            os.environ["MDB_GEMM_PAIR_SPLITK_MINK"] = "1"  # every eligible shape, also the short-K ones, to find the threshold
             print(f"--- MDB_GEMM_PAIR_SPLITK={mode}", flush=True)
             for (hh, cin, cout) in ((64, 320, 320), (64, 640, 320), (32, 640, 640), (32, 1280, 640), (16, 1280, 1280),
                                     (16, 2560, 1280), (8, 1280, 1280), (8, 2560, 1280)):
@@ -135,6 +136,7 @@ def main():
                               (512, 1280, 1280), (512, 1280, 5120), (512, 2560, 1280)):
                 gemm_case(m, n, k, _auto_splits(m, n, k))
         os.environ.pop("MDB_GEMM_PAIR_SPLITK", None)
+        os.environ.pop("MDB_GEMM_PAIR_SPLITK_MINK", None)
         return
     if which in ("all", "attn"):
         attn_case(1, 40, 4096, 4096)

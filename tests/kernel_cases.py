@@ -376,7 +376,7 @@ ALL_CASES = [
 # -m gpu suite must not depend on unvalidated code); `python scripts/gpu_diag.py --group pending` runs them one
 # by one under the caller's timeout (scripts/gpu_pending_checks.sh).  Move a case to ALL_CASES once it is green.
 _PAIRQ = (("MDB_GEMM_PAIR", "3"), ("MDB_GEMM_PAIR_MIN", "1"))     # persistent pair GEMM, TMA-store epilogue
-_PAIRS = (("MDB_GEMM_PAIR_SPLITK", "1"),)                         # pair tiles + split-K inside the cluster
+_PAIRS = (("MDB_GEMM_PAIR_SPLITK", "1"), ("MDB_GEMM_PAIR_SPLITK_MINK", "1"))                         # pair tiles + split-K inside the cluster
 _TMAST = (("MDB_GEMM_TMAST", "1"),)                              # default tiles, TMA-store epilogue (gemm_ts_kernel)
 _GNF = (("MDB_GN_FUSED", "1"),)                                   # single-launch GroupNorm (cluster per batch x group)
 PENDING_CASES = [
