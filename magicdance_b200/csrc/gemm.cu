@@ -1761,6 +1761,13 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   } else {
     bn = 128;
   }
+  // per-shape overrides for the tuner (scripts/gpu_tune_gemm.py -> magicdance_b200/gemm_plan.json -> ops.gemm):
+  // MDB_GEMM_BN = 80 | 128 | 160 forces the tile width of the single-CTA kernel, MDB_GEMM_DEEP = 0 | 1 the ring depth
+  const char* bn_env = getenv("MDB_GEMM_BN");
+  if (bn_env != nullptr && !pair && !geglu) {
+    const int fb = atoi(bn_env);
+    if (fb == 80 || fb == 128 || fb == 160) bn = fb;
+  }
   {
     uint32_t box[2] = {kBK, (uint32_t)(pair ? bn / 2 : bn)};  // a pair CTA stages half of the B rows
     uint64_t dims[2] = {(uint64_t)g->k, (uint64_t)g->n};
@@ -1785,7 +1792,11 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   }
 
   dim3 grid(pair ? 2 * ((m_tiles + 1) / 2) : m_tiles, (g->n + bn - 1) / bn, splits);
-  const bool deep = (long long)grid.x * grid.y * grid.z <= 148 && kp.chunks_per_split >= 12;
+  bool deep = (long long)grid.x * grid.y * grid.z <= 148 && kp.chunks_per_split >= 12;
+  if (const char* deep_env = getenv("MDB_GEMM_DEEP")) {
+    if (deep_env[0] == '0') deep = false;
+    else if (deep_env[0] == '1') deep = true;
+  }
   if (pair) {
     // MDB_GEMM_PAIR=2: the persistent one-pair-per-TPC kernel (owns the SMs and all of their tensor memory)
     if (pairq) {

@@ -18,6 +18,47 @@ _GEMM_DEBUG = os.environ.get("MDB_GEMM_DEBUG", "0") == "1"
 TRACE = None  # set to a list to record (m, n, k, conv, epilogue, splits, k2) of every gemm() call (bench.py)
 
 
+# Per-shape launch choices measured on the target GPU by scripts/gpu_tune_gemm.py: key (gemm_plan_key) ->
+# {"splits": int, "env": {switch: value}}.  Empty unless magicdance_b200/gemm_plan.json exists (none is committed
+# until the tuner has run on a B200) and MDB_GEMM_PLAN != 0; with an empty plan gemm() behaves exactly as before.
+GEMM_PLAN = {}
+_PLAN_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gemm_plan.json")
+
+
+def gemm_plan_key(m, n, k, conv, epilogue, a2_cols):
+    return f"{m}x{n}x{k}|conv{int(conv is not None)}|epi{int(epilogue)}|a2_{int(a2_cols)}"
+
+
+def load_gemm_plan(path=None):
+    """(Re)loads the plan; returns the number of entries.  A missing file clears the plan."""
+    import json
+    GEMM_PLAN.clear()
+    path = _PLAN_PATH if path is None else path
+    if os.environ.get("MDB_GEMM_PLAN", "1") != "0" and os.path.isfile(path):
+        with open(path) as f:
+            for key, ent in json.load(f).get("plan", {}).items():
+                GEMM_PLAN[key] = {"splits": int(ent.get("splits", 0)), "env": {str(a): str(b) for a, b in ent.get("env", {}).items()}}
+    return len(GEMM_PLAN)
+
+
+class _env_switches:
+    """sets library switches (read by the C entry on every call) for the duration of one launch"""
+
+    def __init__(self, env):
+        self.env = env
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.env}
+        os.environ.update(self.env)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -175,6 +216,9 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
     if TRACE is not None:
         TRACE.append((m, n, k, tuple(conv) if conv is not None else None, epilogue, splits,
                       a2.shape[1] if a2 is not None else 0))
+    plan = GEMM_PLAN.get(gemm_plan_key(m, n, k, conv, epilogue, a2.shape[1] if a2 is not None else 0)) if GEMM_PLAN else None
+    if plan is not None and plan["splits"] > 0 and epilogue != EPI_GEGLU:
+        splits = plan["splits"]
     if splits > 1:
         ws = _workspace("splitk", splits * m * n, torch.float32, a.device)
         g.splits, g.splitk_ws = splits, ws.data_ptr()
@@ -187,7 +231,11 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
         print(f"gemm m={m} n={n} k={k} conv={conv} epi={epilogue} splits={g.splits} a2={a2 is not None} lda={g.lda} "
               f"ldd={g.ldd} bias={bias is not None} bbs={g.bias_batch_stride} res={residual is not None}",
               file=sys.stderr, flush=True)
-    _lib.check(lib.mdb_gemm_f16(C.byref(g), _stream()), "gemm_f16")
+    if plan is not None and plan["env"]:
+        with _env_switches(plan["env"]):
+            _lib.check(lib.mdb_gemm_f16(C.byref(g), _stream()), "gemm_f16")
+    else:
+        _lib.check(lib.mdb_gemm_f16(C.byref(g), _stream()), "gemm_f16")
     if _GEMM_DEBUG:
         torch.cuda.synchronize()
     return out
@@ -402,3 +450,6 @@ def cfg_ddim_update(x, eps_c, eps_u, coef, noise=None, x_prev=None, pred_x0=None
                                            x_prev.data_ptr(), pred_x0.data_ptr(), x.numel(), coef.data_ptr(), _stream()),
                "cfg_ddim_update_f32")
     return x_prev, pred_x0
+
+
+load_gemm_plan()

@@ -250,3 +250,42 @@ def test_vae_encoder_orchestration_matches_the_reference_golden_with_cpu_test_do
     with __import__("pytest").raises(RuntimeError, match="no CPU fallback"):
         enc.encode(img)
 
+
+def test_gemm_plan_plumbing_and_tuner_candidates(tmp_path, monkeypatch):
+    """The per-shape launch plan (scripts/gpu_tune_gemm.py -> magicdance_b200/gemm_plan.json -> ops.gemm): no plan file
+    is committed, so the library starts with an empty plan; a plan file is keyed by shape, can be disabled with
+    MDB_GEMM_PLAN=0; the switches it carries are set only around one launch; the tuner's candidate list starts with the
+    engine's own choice and never proposes more splits than K chunks allow."""
+    import importlib.util
+    import json
+    import os
+    from magicdance_b200 import ops
+    assert not os.path.exists(ops._PLAN_PATH) and ops.load_gemm_plan() == 0 and ops.GEMM_PLAN == {}
+    key = ops.gemm_plan_key(512, 1280, 11520, (2, 16, 16, 1280), 0, 0)
+    assert key == "512x1280x11520|conv1|epi0|a2_0" and key != ops.gemm_plan_key(512, 1280, 11520, None, 0, 0)
+    path = tmp_path / "plan.json"
+    path.write_text(json.dumps({"plan": {key: {"splits": 4, "env": {"MDB_GEMM_BN": 160}, "us": 1.0}}}))
+    try:
+        assert ops.load_gemm_plan(str(path)) == 1 and ops.GEMM_PLAN[key] == {"splits": 4, "env": {"MDB_GEMM_BN": "160"}}
+        monkeypatch.setenv("MDB_GEMM_PLAN", "0")
+        assert ops.load_gemm_plan(str(path)) == 0
+    finally:
+        monkeypatch.delenv("MDB_GEMM_PLAN", raising=False)
+        ops.load_gemm_plan()
+    monkeypatch.delenv("MDB_X_TEST", raising=False)
+    with ops._env_switches({"MDB_X_TEST": "1"}):
+        assert os.environ["MDB_X_TEST"] == "1"
+    assert "MDB_X_TEST" not in os.environ
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gpu_tune_gemm", os.path.join(here, "scripts", "gpu_tune_gemm.py"))
+    tune = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tune)
+    cands = tune.candidates(8192, 320, 320, None, 0, 1, ["tmast", "pairs"])
+    assert cands[0] == ("base", 1, {}) and all(s == 1 for _, s, _ in cands)          # 5 K chunks: no split is proposed
+    assert {"tmast", "pairs"} <= {label for label, _, _ in cands}
+    cands = tune.candidates(128, 1280, 11520, (2, 8, 8, 1280), 0, 8, ["pairs"])
+    assert cands[0] == ("base", 8, {}) and "pairs" not in {label for label, _, _ in cands}   # one M tile: no pair
+    assert {s for _, s, _ in cands} == {1, 2, 4, 8}
+    assert all(env == {} or set(env) <= {"MDB_GEMM_BN", "MDB_GEMM_DEEP"} for _, _, env in cands)
+    assert [c for c in tune.candidates(4096, 2560, 320, None, ops.EPI_GEGLU, 1, [])] == [("base", 1, {})]
+
