@@ -50,8 +50,7 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_bank_allgather_world2_gloo():
-    world = 2
+def _run(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -61,5 +60,18 @@ def test_bank_allgather_world2_gloo():
     res = sorted(q.get(timeout=120) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
+    return res
+
+
+def test_bank_allgather_world2_gloo():
+    res = _run(2)
     assert [r[1] for r in res] == [True, True]
     assert [r[2] for r in res] == [5, 5]  # each rank built exactly its half of the timesteps
+
+
+def test_bank_allgather_uneven_world3_gloo():
+    """10 timesteps over 3 ranks -> 4, 3, 3: the short ranks' last slot is padding that nobody reads — the shape of
+    the 8-GPU split of the 50 DDIM steps (7, 7, 6, 6, 6, 6, 6, 6)."""
+    res = _run(3)
+    assert [r[1] for r in res] == [True, True, True]
+    assert [r[2] for r in res] == [4, 3, 3]
