@@ -289,3 +289,42 @@ def test_gemm_plan_plumbing_and_tuner_candidates(tmp_path, monkeypatch):
     assert all(env == {} or set(env) <= {"MDB_GEMM_BN", "MDB_GEMM_DEEP"} for _, _, env in cands)
     assert [c for c in tune.candidates(4096, 2560, 320, None, ops.EPI_GEGLU, 1, [])] == [("base", 1, {})]
 
+
+def test_gpu_case_lists_and_scripts_are_well_formed():
+    """The GPU-side case lists are data that only runs on the GPU box: check here that every (function, args) pair of
+    ALL_CASES and PENDING_CASES binds to its function's signature (wrappers are followed to the wrapped case), that the
+    pending switches are ones the library reads, and that every GPU script at least compiles — a typo must not cost
+    GPU minutes."""
+    import inspect
+    import os
+    import py_compile
+    from tests import kernel_cases as K
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def bind(fn, args):
+        if fn is K.case_pair:
+            return bind(args[0], args[1:])
+        if fn is K.case_env:
+            env, inner = args[0], args[1]
+            assert all(isinstance(a, str) and isinstance(b, str) for a, b in env)
+            return bind(inner, args[2:])
+        inspect.signature(fn).bind(*args)
+        return fn
+
+    for fn, args in K.ALL_CASES + K.PENDING_CASES:
+        assert callable(bind(fn, args))
+    src = ""
+    for f in ("gemm.cu", "attention.cu", "norm.cu", "misc.cu"):
+        with open(os.path.join(here, "magicdance_b200", "csrc", f)) as fh:
+            src += fh.read()
+    with open(os.path.join(here, "magicdance_b200", "ops.py")) as fh:
+        src += fh.read()
+    switches = {a for fn, args in K.PENDING_CASES if fn is K.case_env for a, _ in args[0]}
+    assert switches and all(f'"{sw}"' in src for sw in switches), switches
+    assert not any(c in K.ALL_CASES for c in K.PENDING_CASES)  # unvalidated kernels stay out of the -m gpu suite
+    for f in sorted(os.listdir(os.path.join(here, "scripts"))):
+        if f.endswith(".py"):
+            py_compile.compile(os.path.join(here, "scripts", f), doraise=True)
+    py_compile.compile(os.path.join(here, "tests", "torch_gpu_baseline.py"), doraise=True)
+    py_compile.compile(os.path.join(here, "bench.py"), doraise=True)
+
