@@ -328,3 +328,23 @@ def test_gpu_case_lists_and_scripts_are_well_formed():
     py_compile.compile(os.path.join(here, "tests", "torch_gpu_baseline.py"), doraise=True)
     py_compile.compile(os.path.join(here, "bench.py"), doraise=True)
 
+
+def test_switch_defaults_file_is_absent_and_would_not_override_the_environment(tmp_path, monkeypatch):
+    """No opt-in is the default yet: magicdance_b200/switch_defaults.json does not exist.  When it does, its MDB_*
+    entries are applied with setdefault (an explicit environment variable wins, other keys are ignored)."""
+    import json
+    import os
+    import magicdance_b200 as M
+    pkg = os.path.dirname(os.path.abspath(M.__file__))
+    assert not os.path.exists(os.path.join(pkg, "switch_defaults.json")) and M.SWITCH_DEFAULTS == {}
+    fake_pkg = tmp_path / "pkg"
+    fake_pkg.mkdir()
+    (fake_pkg / "switch_defaults.json").write_text(json.dumps({"MDB_T_A": 1, "MDB_T_B": "x", "PATH": "/nope"}))
+    monkeypatch.setenv("MDB_T_B", "explicit")
+    monkeypatch.delenv("MDB_T_A", raising=False)
+    monkeypatch.setattr(M._os.path, "abspath", lambda p: str(fake_pkg / "__init__.py"))
+    cfg = M._apply_switch_defaults()
+    assert cfg == {"MDB_T_A": "1", "MDB_T_B": "x"}
+    assert os.environ["MDB_T_A"] == "1" and os.environ["MDB_T_B"] == "explicit" and os.environ["PATH"] != "/nope"
+    monkeypatch.delenv("MDB_T_A", raising=False)
+
