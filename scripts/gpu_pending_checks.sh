@@ -8,7 +8,9 @@
 #
 # Reading the results: a feature becomes the default when (1) its numerics leg is all "ok", (2) its bench line
 # has "finite": true and an "x_final_fingerprint" equal (to ~1e-3) to pending_b1_default.json / pending_b8_default.json,
-# and (3) its "value" is higher.  Then move its cases from PENDING_CASES to ALL_CASES (tests/kernel_cases.py).
+# and (3) its "value" is higher — `python scripts/decide_defaults.py [--write]` applies exactly these rules to
+# gpurun_out/ and writes magicdance_b200/switch_defaults.json.  Then move the green cases from PENDING_CASES to
+# ALL_CASES (tests/kernel_cases.py).
 mkdir -p gpurun_out
 want() { for s in $SECTIONS; do [ "$s" = "$1" ] || [ "$s" = all ] && return 0; done; return 1; }
 SECTIONS="${*:-all}"

@@ -348,3 +348,43 @@ def test_switch_defaults_file_is_absent_and_would_not_override_the_environment(t
     assert os.environ["MDB_T_A"] == "1" and os.environ["MDB_T_B"] == "explicit" and os.environ["PATH"] != "/nope"
     monkeypatch.delenv("MDB_T_A", raising=False)
 
+
+def test_decide_defaults_rules(tmp_path):
+    """scripts/decide_defaults.py: a switch is enabled only with green numerics AND a finite bench line whose final
+    latent agrees with the default run AND a gain; a hung numerics log, a diverging latent or a slowdown keep it off;
+    of two variants claiming the same slot the faster survives."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("decide_defaults", os.path.join(here, "scripts", "decide_defaults.py"))
+    dd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(dd)
+    d = tmp_path
+
+    def bench(name, value, fp=(0.5, 12.0), finite=True):
+        (d / name).write_text(json.dumps({"value": value, "unit": "frame-steps/s", "finite": finite,
+                                          "x_final_fingerprint": list(fp)}))
+
+    def log(name, failing, total, extra=""):
+        (d / name).write_text(f"device: B200\nok   case: err=1e-4\n{extra}group pending: {failing} failing of {total}\n")
+
+    bench("pending_b1_default.json", 117.0)
+    bench("pending_b8_default.json", 240.0)
+    log("pending_pairq.log", 0, 17); bench("pending_b8_pair3.json", 262.0, fp=(0.5002, 12.004))     # green, +9 %
+    log("pending_pairp.log", 0, 14); bench("pending_b8_pair2.json", 250.0)                          # green, +4 %: superseded
+    log("pending_tmast.log", 1, 10, "FAIL gemm m=8192: err=3e-1\n"); bench("pending_b8_tmast.json", 300.0)  # wrong numerics
+    (d / "pending_pairs.log").write_text("device: B200\nok   case\n")                            # hung: no summary line
+    bench("pending_b1_pairs.json", 130.0)
+    log("pending_attn4.log", 0, 12); bench("pending_b8_attn4.json", 250.0); bench("pending_b1_attn4.json", 110.0)  # slower at B=1
+    log("pending_gnfused.log", 0, 7); bench("pending_b1_gnfused.json", 124.0, fp=(0.9, 30.0))      # latent differs
+    bench("pending_b1_overlap.json", 126.0)                                                          # host-side, +7.7 %
+    report, enabled = dd.judge(str(d), 2e-3, 0.01)
+    assert set(enabled) == {"MDB_GEMM_PAIR=3", "MDB_BANK_OVERLAP=1"}, (enabled, report)
+    cfg = {}
+    for env in enabled.values():
+        cfg.update(env)
+    assert cfg == {"MDB_GEMM_PAIR": "3", "MDB_BANK_OVERLAP": "1"}
+    assert dd.numerics_ok(str(d / "missing.log")) == (False, "numerics log missing")
+    assert not dd.fp_close([1.0, 2.0], [1.0, 2.1], 2e-3) and dd.fp_close([1.0, 2.0], [1.001, 2.001], 2e-3)
+
