@@ -696,7 +696,14 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
     gemm_pairq_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ CUtensorMap tmD) {
   using S = GemmSmem<BN, kStages, true>;
   using Q = PairqSmem<BN, kStages>;
-  static_assert(BN % 32 == 0 && BN <= 256, "cta_group::2 UMMA: N <= 256; the epilogue works in 32-column chunks");
+  // UMMA N <= 256: a 320-wide tile (BN = 320, the full width of the 64x64 level: every A tile is loaded exactly once)
+  // is TWO 160-wide MMAs per K step into adjacent accumulator columns.  320 columns leave no room for a second
+  // accumulator buffer, so that tile is single-buffered (the epilogue of a long-K tile is a few % of its main loop).
+  constexpr int kParts = (BN > 256) ? 2 : 1;
+  constexpr int kPartN = BN / kParts;
+  constexpr int kBufs = (BN > 256) ? 1 : 2;
+  static_assert(BN % 32 == 0 && kPartN <= 256 && kPartN % 16 == 0 && BN <= 512, "tile width");
+  static_assert(((kPartN / 2) * 128) % 1024 == 0, "each part's B rows start on a swizzle-atom boundary");
   static_assert(!GEGLU || BN % 64 == 0, "GEGLU tiles hold (value, gate) chunk pairs");
   static_assert(Q::kRing % 1024 == 0, "the staging buffers follow the ring and need 128-byte alignment");
   extern __shared__ uint8_t smem_raw[];
@@ -768,18 +775,21 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
           } else {
             tma_load_2d_pair(sa, &p.tmA2, fb, (kc - p.k1_chunks) * kBK, m0);
           }
-          tma_load_2d_pair(sb, &p.tmB, fb, kc * kBK, n0 + static_cast<int>(pair_rank) * S::kBRows);
+#pragma unroll
+          for (int h = 0; h < kParts; ++h)  // this CTA's half of each part's B rows (tmB's box is kPartN / 2 rows)
+            tma_load_2d_pair(sb + h * (kPartN / 2) * 128, &p.tmB, fb, kc * kBK,
+                             n0 + h * kPartN + static_cast<int>(pair_rank) * (kPartN / 2));
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && pair_rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(2 * kBM, BN);
+      constexpr uint32_t idesc = umma_idesc_f16(2 * kBM, kPartN);
       uint32_t g = 0;
       int i = 0;
       for (int t = cluster_id; t < total_tiles; t += n_clusters, ++i) {
-        const int buf = i & 1;
-        mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);  // all 16 epilogue warps of the pair have drained this buffer
+        const int buf = i % kBufs;
+        mbar_wait(&acc_empty[buf], ((i / kBufs) & 1) ^ 1);  // all 16 epilogue warps of the pair have drained this buffer
         tc_fence_after_sync();
         const uint32_t tacc = tmem_base + buf * kAccStride;
         for (int kc = 0; kc < p.k_chunks; ++kc, ++g) {
@@ -792,7 +802,12 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
           const uint64_t da = umma_desc_k_sw128(a_addr);
           const uint64_t db = umma_desc_k_sw128(b_addr);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) umma_f16_ss_pair(tacc, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+#pragma unroll
+            for (int h = 0; h < kParts; ++h)
+              umma_f16_ss_pair(tacc + h * kPartN, da + 2 * k, db + h * (((kPartN / 2) * 128) >> 4) + 2 * k, idesc,
+                               (kc | k) != 0 ? 1u : 0u);
+          }
           umma_commit_pair(&empty_bar[s]);
         }
         umma_commit_pair(&acc_full[buf]);
@@ -823,7 +838,7 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
     }
     int i = 0;
     for (int t = cluster_id; t < total_tiles; t += n_clusters, ++i) {
-      const int buf = i & 1;
+      const int buf = i % kBufs;
       const int mp = t % m_pairs, nt = t / m_pairs;
       const int m0 = (2 * mp + static_cast<int>(pair_rank)) * kBM;
       const int n0 = nt * BN;
@@ -831,7 +846,7 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
       const long long row = static_cast<long long>(row0) + lane;
       const bool row_ok = row < p.m;
       const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
-      mbar_wait(&acc_full[buf], (i >> 1) & 1);
+      mbar_wait(&acc_full[buf], (i / kBufs) & 1);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + buf * kAccStride + (static_cast<uint32_t>(gq * 32) << 16);
       bool arrived = false;
@@ -1743,6 +1758,7 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   int bn;
   if (pair) {
     if (geglu) bn = (g->n % 256 == 0) ? 256 : 0;
+    else if (pairq && g->n % 320 == 0 && kp.k_chunks >= 16) bn = 320;  // full-width tiles of the long-K layers
     else if (pairq && g->n % 256 == 0) bn = 256;  // widest tile first: fewest L2 -> SM bytes per flop
     else if (g->n % 160 == 0) bn = 160;
     else if (g->n % 256 == 0) bn = 256;
@@ -1769,7 +1785,8 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     if (fb == 80 || fb == 128 || fb == 160) bn = fb;
   }
   {
-    uint32_t box[2] = {kBK, (uint32_t)(pair ? bn / 2 : bn)};  // a pair CTA stages half of the B rows
+    // a pair CTA stages half of the B rows (of each 160-wide part of a 320-wide tile)
+    uint32_t box[2] = {kBK, (uint32_t)(pair ? (bn == 320 ? 80 : bn / 2) : bn)};
     uint64_t dims[2] = {(uint64_t)g->k, (uint64_t)g->n};
     uint64_t str[1] = {(uint64_t)g->ldb * 2};
     rc = make_tmap_f16(&kp.tmB, g->b, 2, dims, str, box);
@@ -1809,6 +1826,7 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
       if (rc) return rc;
       const int total_tiles = ((m_tiles + 1) / 2) * (int)grid.y;
       if (geglu) return launch_gemm_pairq<256, true, 5>(kp, tmD, total_tiles, st);
+      if (bn == 320) return launch_gemm_pairq<320, false, 5>(kp, tmD, total_tiles, st);
       if (bn == 160) return launch_gemm_pairq<160, false, 6>(kp, tmD, total_tiles, st);
       if (bn == 256) return launch_gemm_pairq<256, false, 5>(kp, tmD, total_tiles, st);
       return launch_gemm_pairq<128, false, 6>(kp, tmD, total_tiles, st);

@@ -401,9 +401,12 @@ PENDING_CASES = [
     (case_env, (_PAIRQ, case_gemm, 384, 320, 320, True, True)),           # odd M tiles: last pair half empty; bias+residual
     (case_env, (_PAIRQ, case_gemm, 1000, 640, 1280, True, False)),        # ragged M (TMA store clips rows)
     (case_env, (_PAIRQ, case_gemm, 300, 384, 192, True, True)),           # 128-wide tiles
-    (case_env, (_PAIRQ, case_gemm, 4096, 320, 2880, True, True)),         # long K: ring wraps; 16 M pairs x 2 N tiles
+    (case_env, (_PAIRQ, case_gemm, 4096, 320, 2880, True, True)),         # long K: ring wraps; 320-wide tile = full N
     (case_env, (_PAIRQ, case_gemm, 65536, 320, 320, True, True)),         # 512 tiles over 74 pairs: 7 rounds, both buffers
-    (case_env, (_PAIRQ, case_gemm, 4096, 1280, 1280, True, True)),        # 256-wide tiles, 5 N tiles
+    (case_env, (_PAIRQ, case_gemm, 4096, 1280, 640, True, True)),         # 256-wide tiles, 5 N tiles (K too short for 320)
+    (case_env, (_PAIRQ, case_gemm, 4096, 1280, 1280, True, True)),        # 320-wide tiles (2 x 160 MMAs, one accumulator)
+    (case_env, (_PAIRQ, case_gemm, 1000, 640, 2560, True, True)),         # 320-wide, ragged M, 2 N tiles
+    (case_env, (_PAIRQ, case_conv, 8, 64, 64, 320, 320, True, True)),     # full-width conv tile: 128 pairs over 74 clusters
     (case_env, (_PAIRQ, case_gemm, 520, 200, 128, True, True)),           # N = 200: last chunk 8 columns wide, 2nd half empty
     (case_env, (_PAIRQ, case_gemm_batch_bias, 2, 1024, 640, 320)),
     (case_env, (_PAIRQ, case_gemm_dual, 1024, 640, 640, 320)),
