@@ -986,7 +986,11 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
 template <int BN, int kStages>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_pairs_kernel(const __grid_constant__ GemmKParams p) {
   using S = GemmSmem<BN, kStages, true>;
-  static_assert(BN % 16 == 0 && BN <= 256, "cta_group::2 UMMA: N must be a multiple of 16, at most 256");
+  // BN = 320: two 160-wide MMAs per K step into one 320-column accumulator (see gemm_pairq_kernel)
+  constexpr int kParts = (BN > 256) ? 2 : 1;
+  constexpr int kPartN = BN / kParts;
+  static_assert(BN % 32 == 0 && kPartN % 16 == 0 && kPartN <= 256 && BN <= 512, "tile width");
+  static_assert(((kPartN / 2) * 128) % 1024 == 0, "each part's B rows start on a swizzle-atom boundary");
   constexpr int kRedLd = BN + 4;  // fp32 row pitch of the parked partial tile
   static_assert(kBM * kRedLd * 4 <= kStages * S::kStageBytes, "partial tile must fit in the operand ring");
   extern __shared__ uint8_t smem_raw[];
@@ -1004,7 +1008,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_pairs_kernel(const __gri
   const int kc_begin = split * p.chunks_per_split;
   const int kc_end = min(p.k_chunks, kc_begin + p.chunks_per_split);
   const int n_iter = kc_end - kc_begin;  // > 0: the host never creates an empty split
-  constexpr uint32_t kTmemCols = (BN <= 128) ? 128 : 256;
+  constexpr uint32_t kTmemCols = (BN <= 128) ? 128 : (BN <= 256 ? 256 : 512);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -1054,12 +1058,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_pairs_kernel(const __gri
         } else {
           tma_load_2d_pair(sa, &p.tmA2, fb, (kc - p.k1_chunks) * kBK, m0);
         }
-        tma_load_2d_pair(sb, &p.tmB, fb, kc * kBK, n0 + static_cast<int>(pair_rank) * S::kBRows);
+#pragma unroll
+        for (int h = 0; h < kParts; ++h)  // this CTA's half of each part's B rows (tmB's box is kPartN / 2 rows)
+          tma_load_2d_pair(sb + h * (kPartN / 2) * 128, &p.tmB, fb, kc * kBK,
+                           n0 + h * kPartN + static_cast<int>(pair_rank) * (kPartN / 2));
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && pair_rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(2 * kBM, BN);
+      constexpr uint32_t idesc = umma_idesc_f16(2 * kBM, kPartN);
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
@@ -1070,7 +1077,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_pairs_kernel(const __gri
         const uint64_t da = umma_desc_k_sw128(a_addr);
         const uint64_t db = umma_desc_k_sw128(b_addr);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) umma_f16_ss_pair(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < kBK / 16; ++k) {
+#pragma unroll
+          for (int h = 0; h < kParts; ++h)
+            umma_f16_ss_pair(tmem_base + h * kPartN, da + 2 * k, db + h * (((kPartN / 2) * 128) >> 4) + 2 * k, idesc,
+                             (it | k) != 0 ? 1u : 0u);
+        }
         umma_commit_pair_at(&empty_bar[s], leader);  // frees the stage in both CTAs of THIS pair
       }
       umma_commit_pair_at(&acc_bar, leader);
@@ -1609,7 +1621,8 @@ static int launch_gemm_pairs(const GemmKParams& kp, dim3 grid, cudaStream_t st) 
   static bool attr_set = false;
   auto kern = gemm_pairs_kernel<BN, STAGES>;
   constexpr int kSmem = GemmSmem<BN, STAGES, true>::kTotal;
-  static_assert(kSmem <= 227 * 1024 && kSmem >= 190 * 1024, "one CTA per SM, nothing else with tensor memory beside it");
+  // one CTA per SM and less than the smallest tensor-memory kernel's footprint (78 KB) left beside it
+  static_assert(kSmem <= 227 * 1024 && kSmem >= 180 * 1024, "one CTA per SM, nothing else with tensor memory beside it");
   if (!attr_set) {
     MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
@@ -1718,17 +1731,34 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     const char* mink_env = getenv("MDB_GEMM_PAIR_SPLITK_MINK");
     const int min_chunks = mink_env ? atoi(mink_env) : 16;
     if (ps_env != nullptr && ps_env[0] == '1' && !geglu && mt >= 2 && g->n % 8 == 0 && kp.k_chunks >= min_chunks) {
-      const int bnp = (g->n % 160 == 0) ? 160 : 128;
+      // Tile width and split count: what bounds these layers is the bytes ONE SM pulls through the L2 -> SM fabric,
+      // chunks/S x (16 KB of A + 64 B x BN of B) — so take the (BN, S) that minimises it.  Co-resident CTAs at one
+      // ~200 KB CTA per SM: 148 in clusters of 2, 132 in clusters of 4, 128 in clusters of 8 (8 GPCs of 16/18/20
+      // SMs, a cluster never straddles a GPC).  MDB_GEMM_PAIR_SPLITK_BN forces the width (tuner / tests).
       const int m_pairs = (mt + 1) / 2;
-      const int n_tiles = (g->n + bnp - 1) / bnp;
-      const int ctas = 2 * m_pairs * n_tiles;
-      if (ctas <= 148) {
-        // co-resident CTAs at one 200 KB CTA per SM: 148 in clusters of 2, 132 in clusters of 4, 128 in clusters of 8
-        // (8 GPCs of 16/18/20 SMs, a cluster never straddles a GPC)
-        int S_ = 1;
-        if (ctas * 4 <= 128 && kp.k_chunks >= 16) S_ = 4;
-        else if (ctas * 2 <= 132 && kp.k_chunks >= 8) S_ = 2;
-        uint32_t boxb[2] = {kBK, (uint32_t)(bnp / 2)};  // each CTA of a pair stages half of the B rows
+      const char* pbn_env = getenv("MDB_GEMM_PAIR_SPLITK_BN");
+      const int forced_bn = pbn_env ? atoi(pbn_env) : 0;
+      int bnp = 0, S_ = 1, ctas = 0;
+      long long best_cost = -1;
+      const int widths[3] = {320, 160, 128};
+      for (int wi = 0; wi < 3; ++wi) {
+        const int w = widths[wi];
+        if (forced_bn ? (w != forced_bn) : ((w != 128 && g->n % w != 0) || (w == 128 && g->n % 160 == 0))) continue;
+        const int nt = (g->n + w - 1) / w;
+        const int c = 2 * m_pairs * nt;
+        if (c > 148) continue;
+        int sp = 1;
+        if (c * 4 <= 128 && kp.k_chunks >= 16) sp = 4;
+        else if (c * 2 <= 132 && kp.k_chunks >= 8) sp = 2;
+        const long long cost = (long long)((kp.k_chunks + sp - 1) / sp) * (16384 + 64 * w);
+        if (best_cost < 0 || cost < best_cost) {
+          best_cost = cost; bnp = w; S_ = sp; ctas = c;
+        }
+      }
+      const int n_tiles = bnp ? (g->n + bnp - 1) / bnp : 0;
+      if (bnp != 0 && ctas <= 148) {
+        // each CTA of a pair stages half of the B rows (of each 160-wide part of a 320-wide tile)
+        uint32_t boxb[2] = {kBK, (uint32_t)(bnp == 320 ? 80 : bnp / 2)};
         uint64_t dimsb[2] = {(uint64_t)g->k, (uint64_t)g->n};
         uint64_t strb[1] = {(uint64_t)g->ldb * 2};
         rc = make_tmap_f16(&kp.tmB, g->b, 2, dimsb, strb, boxb);
@@ -1742,6 +1772,7 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
         kp.splits = S_;
         kp.cluster_reduce = 1;
         dim3 gridp(2 * m_pairs, n_tiles, S_);
+        if (bnp == 320) return launch_gemm_pairs<320, 5>(kp, gridp, st);
         if (bnp == 160) return launch_gemm_pairs<160, 8>(kp, gridp, st);
         return launch_gemm_pairs<128, 8>(kp, gridp, st);
       }

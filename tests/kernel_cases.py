@@ -426,8 +426,11 @@ PENDING_CASES = [
     (case_env, (_PAIRS, case_gemm_batch_bias, 2, 1024, 640, 320)),
     (case_env, (_PAIRS, case_gemm_dual, 1024, 640, 640, 320)),
     (case_env, (_PAIRS, case_conv, 2, 16, 16, 1280, 1280, True, True)),   # the 16x16 level of one frame (cond+uncond)
-    (case_env, (_PAIRS, case_conv, 2, 32, 32, 640, 640, True, True)),
-    (case_env, (_PAIRS, case_conv, 2, 64, 64, 320, 320, True, True)),
+    (case_env, (_PAIRS, case_conv, 2, 32, 32, 640, 640, True, True)),     # -> 320-wide tiles, S = 4
+    (case_env, (_PAIRS, case_conv, 2, 64, 64, 320, 320, True, True)),     # -> 320-wide tile = full N, S = 2
     (case_env, (_PAIRS, case_conv, 4, 8, 8, 1280, 1280, True, True)),     # 8x8 level: two images per 128-row tile
     (case_env, (_PAIRS, case_conv, 3, 8, 8, 2560, 1280, True, False)),    # 192 rows: second CTA half out of range
+    (case_env, (_PAIRS + (("MDB_GEMM_PAIR_SPLITK_BN", "320"),), case_gemm, 384, 640, 1280, True, True)),   # 320-wide, odd M tiles
+    (case_env, (_PAIRS + (("MDB_GEMM_PAIR_SPLITK_BN", "320"),), case_gemm, 8192, 320, 320, True, True)),   # 320-wide, S = 1
+    (case_env, (_PAIRS + (("MDB_GEMM_PAIR_SPLITK_BN", "128"),), case_gemm, 512, 1280, 1280, True, True)),  # 128-wide forced
 ]
