@@ -920,7 +920,7 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
                 a += bp[j];
                 gt += bp[32 + j];
               }
-              o[e] = a * gelu_erf_f(gt);
+              o[e] = a * gelu_erf_poly_f(gt);
             }
             o4[q].x = pack_half2(o[0], o[1]);
             o4[q].y = pack_half2(o[2], o[3]);
@@ -1377,7 +1377,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
               a += bp[j];
               gt += bp[32 + j];
             }
-            o[e] = a * gelu_erf_f(gt);
+            o[e] = a * gelu_erf_poly_f(gt);
           }
           o4[q].x = pack_half2(o[0], o[1]);
           o4[q].y = pack_half2(o[2], o[3]);

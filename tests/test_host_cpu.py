@@ -388,3 +388,37 @@ def test_decide_defaults_rules(tmp_path):
     assert dd.numerics_ok(str(d / "missing.log")) == (False, "numerics log missing")
     assert not dd.fp_close([1.0, 2.0], [1.0, 2.1], 2e-3) and dd.fp_close([1.0, 2.0], [1.001, 2.001], 2e-3)
 
+
+def test_polynomial_gelu_constants_in_the_kernel_source_are_accurate():
+    """gelu_erf_poly_f (common.cuh, used by the opt-in GEGLU epilogues): the constants in the source, evaluated in
+    float32 Horner arithmetic exactly as the kernel does, reproduce exact-erf GELU (attention.py:57) to 1e-4 absolute
+    over [-12, 12] — far below the fp16 rounding of the result — and the fit script regenerates the same constants."""
+    import importlib.util
+    import os
+    import re
+    import numpy as np
+    from scipy.special import erf
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(here, "magicdance_b200", "csrc", "common.cuh")) as f:
+        src = f.read()
+    body = src[src.index("float gelu_erf_poly_f(float x)"):]
+    body = body[:body.index("return fmaf(hx")]
+    first = float(re.search(r"float p = ([-0-9.e+]+)f;", body).group(1))
+    rest = [float(m) for m in re.findall(r"p = fmaf\(p, u, ([-0-9.e+]+)f\);", body)]
+    assert len(rest) == 8
+    x = np.linspace(-12, 12, 200001).astype(np.float32)
+    z = np.clip(x * np.float32(0.70710678118654752), np.float32(-3), np.float32(3)).astype(np.float32)
+    u = (z * z).astype(np.float32)
+    p = np.full_like(u, np.float32(first))
+    for c in rest:
+        p = (p * u + np.float32(c)).astype(np.float32)
+    hx = (np.float32(0.5) * x).astype(np.float32)
+    got = (hx * (p * z).astype(np.float32) + hx).astype(np.float32)
+    ref = 0.5 * x.astype(np.float64) * (1 + erf(x.astype(np.float64) * 0.70710678118654752))
+    assert np.abs(got - ref).max() < 1e-4
+    spec = importlib.util.spec_from_file_location("fit_erf_poly", os.path.join(here, "scripts", "fit_erf_poly.py"))
+    fit = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fit)
+    coef = fit.fit(3.0, 8)
+    assert np.allclose(coef[::-1], [first] + rest, rtol=1e-6, atol=1e-12)
+
