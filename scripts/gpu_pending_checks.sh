@@ -18,7 +18,7 @@ B1="--steps 50 --warmup 3 --no-cpu-baseline --no-roofline"
 B8="--batch 8 --steps 20 --warmup 3 --no-cpu-baseline --no-roofline"
 bench() {  # bench <name> <timeout> <bench args...>   (environment switches are inherited from the caller)
   local name=$1 t=$2; shift 2
-  timeout "$t" python bench.py "$@" > "gpurun_out/$name.json" 2> "gpurun_out/$name.err"
+  timeout -k 10 "$t" python bench.py "$@" > "gpurun_out/$name.json" 2> "gpurun_out/$name.err"
   echo "$name rc=$? $(python - "$name" <<'EOF'
 import json, sys
 try:
@@ -31,7 +31,7 @@ EOF
 }
 diag() {  # diag <log name> <timeout> <gpu_diag args...>
   local name=$1 t=$2; shift 2
-  timeout "$t" python scripts/gpu_diag.py "$@" > "gpurun_out/$name.log" 2>&1
+  timeout -k 10 "$t" python scripts/gpu_diag.py "$@" > "gpurun_out/$name.log" 2>&1
   echo "$name rc=$? $(tail -n 1 gpurun_out/$name.log)"; grep -E "^(FAIL|EXC)" "gpurun_out/$name.log" | head -n 8
 }
 
@@ -47,8 +47,8 @@ fi
 
 if want gemm8; then
   echo "== GEMM variants at eight frames: shape by shape (warm L2, graph replay), then the full step"
-  timeout 250 python scripts/gpu_microbench.py pair 0,1,2,3 > gpurun_out/pending_microbench_pair.log 2>&1; echo "microbench pair rc=$?"
-  MDB_GEMM_TMAST=1 timeout 200 python scripts/gpu_microbench.py pair 0 > gpurun_out/pending_microbench_tmast.log 2>&1; echo "microbench tmast rc=$?"
+  timeout -k 10 250 python scripts/gpu_microbench.py pair 0,1,2,3 > gpurun_out/pending_microbench_pair.log 2>&1; echo "microbench pair rc=$?"
+  MDB_GEMM_TMAST=1 timeout -k 10 200 python scripts/gpu_microbench.py pair 0 > gpurun_out/pending_microbench_tmast.log 2>&1; echo "microbench tmast rc=$?"
   bench pending_b8_default 120 $B8
   MDB_GEMM_PAIR=2 bench pending_b8_pair2 90 $B8
   MDB_GEMM_PAIR=3 bench pending_b8_pair3 90 $B8
@@ -57,7 +57,7 @@ fi
 
 if want gemm1; then
   echo "== one frame: pair tiles + cluster split-K on the weight-streaming layers"
-  timeout 200 python scripts/gpu_microbench.py pairs > gpurun_out/pending_microbench_pairs.log 2>&1; echo "microbench pairs rc=$?"
+  timeout -k 10 200 python scripts/gpu_microbench.py pairs > gpurun_out/pending_microbench_pairs.log 2>&1; echo "microbench pairs rc=$?"
   bench pending_b1_default 120 $B1
   MDB_GEMM_PAIR_SPLITK=1 bench pending_b1_pairs 90 $B1
   MDB_GEMM_PAIR=3 MDB_GEMM_PAIR_SPLITK=1 bench pending_b1_pair3_pairs 90 $B1   # + persistent pair for the bank build
@@ -65,16 +65,16 @@ fi
 
 if want attn; then
   echo "== attention d=40 on the two-Q-tile kernel at two CTAs per SM (MDB_ATTN=4) against the default (v3)"
-  timeout 100 python scripts/gpu_microbench.py attn > gpurun_out/pending_microbench_attn3.log 2>&1; echo "microbench attn v3 rc=$?"
-  MDB_ATTN=4 timeout 100 python scripts/gpu_microbench.py attn > gpurun_out/pending_microbench_attn4.log 2>&1; echo "microbench attn v4 rc=$?"
+  timeout -k 10 100 python scripts/gpu_microbench.py attn > gpurun_out/pending_microbench_attn3.log 2>&1; echo "microbench attn v3 rc=$?"
+  MDB_ATTN=4 timeout -k 10 100 python scripts/gpu_microbench.py attn > gpurun_out/pending_microbench_attn4.log 2>&1; echo "microbench attn v4 rc=$?"
   MDB_ATTN=4 bench pending_b8_attn4 90 $B8
   MDB_ATTN=4 bench pending_b1_attn4 90 $B1
 fi
 
 if want gn; then
   echo "== single-launch GroupNorm for small batches (MDB_GN_FUSED=1)"
-  timeout 100 python scripts/gpu_microbench.py misc > gpurun_out/pending_microbench_misc.log 2>&1; echo "microbench misc rc=$?"
-  MDB_GN_FUSED=1 timeout 100 python scripts/gpu_microbench.py misc > gpurun_out/pending_microbench_misc_gnfused.log 2>&1; echo "microbench misc fused rc=$?"
+  timeout -k 10 100 python scripts/gpu_microbench.py misc > gpurun_out/pending_microbench_misc.log 2>&1; echo "microbench misc rc=$?"
+  MDB_GN_FUSED=1 timeout -k 10 100 python scripts/gpu_microbench.py misc > gpurun_out/pending_microbench_misc_gnfused.log 2>&1; echo "microbench misc fused rc=$?"
   MDB_GN_FUSED=1 bench pending_b1_gnfused 90 $B1
 fi
 
@@ -91,17 +91,17 @@ if want baseline; then
   echo "== secondary baseline: the reference's path as eager PyTorch (cuDNN/cuBLAS/SDPA, fp16 autocast) on this GPU"
   for cfg in "b1 --batch 1 --steps 10 --warmup 2" "b1_alg --batch 1 --steps 10 --warmup 2 --algorithmic" "b8_alg --batch 8 --steps 5 --warmup 1 --algorithmic"; do
     set -- $cfg; name=$1; shift
-    timeout 150 python tests/torch_gpu_baseline.py "$@" > "gpurun_out/torch_gpu_baseline_$name.json" 2> "gpurun_out/torch_gpu_baseline_$name.err"
+    timeout -k 10 150 python tests/torch_gpu_baseline.py "$@" > "gpurun_out/torch_gpu_baseline_$name.json" 2> "gpurun_out/torch_gpu_baseline_$name.err"
     echo "torch baseline $name rc=$?"; cat "gpurun_out/torch_gpu_baseline_$name.json"
   done
 fi
 
 if want vae; then
   echo "== VAE decoder + encoder (softmax kernel, br-padded im2col, GroupNorm with 4 channels/group, 128-pixel-row implicit GEMM, im2col at 256/512)"
-  timeout 400 python scripts/gpu_vae_parity.py > gpurun_out/pending_vae.log 2>&1; echo "vae rc=$?"; tail -n 12 gpurun_out/pending_vae.log
+  timeout -k 10 400 python scripts/gpu_vae_parity.py > gpurun_out/pending_vae.log 2>&1; echo "vae rc=$?"; tail -n 12 gpurun_out/pending_vae.log
 fi
 
 if want tune; then
   echo "== per-shape GEMM launch plan (scripts/gpu_tune_gemm.py): dry run with the validated kernels only; add --variants for the green opt-ins"
-  timeout 600 python scripts/gpu_tune_gemm.py --frames 1,8 --dry-run > gpurun_out/tune_gemm.log 2>&1; echo "tune rc=$?"; tail -n 6 gpurun_out/tune_gemm.log
+  timeout -k 10 600 python scripts/gpu_tune_gemm.py --frames 1,8 --dry-run > gpurun_out/tune_gemm.log 2>&1; echo "tune rc=$?"; tail -n 6 gpurun_out/tune_gemm.log
 fi
