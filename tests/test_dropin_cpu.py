@@ -71,9 +71,14 @@ def test_strict_load_of_a_reference_checkpoint_layout(model):
     from magicdance_b200 import synth
     manifest = synth.load_manifest()
     sd = {k: torch.zeros(v) for k, v in manifest.items()}  # a checkpoint with exactly the reference's keys
-    missing, unexpected = model.load_state_dict(sd, strict=True)
-    assert not missing and not unexpected
-    assert model.model.diffusion_model._packed is None  # packed fp16 copies are invalidated by a load
+    schedule = {k: v.clone() for k, v in model.state_dict().items() if k in synth.SCHEDULE_KEYS}
+    try:
+        missing, unexpected = model.load_state_dict(sd, strict=True)
+        assert not missing and not unexpected
+        assert model.model.diffusion_model._packed is None  # packed fp16 copies are invalidated by a load
+    finally:  # the module-scoped model keeps its derived schedule buffers for the tests below
+        model.load_state_dict(schedule, strict=False)
+        model._test_loaded_seed = None
 
 
 def test_dropin_apply_model_orchestration_matches_reference_small32(model, monkeypatch):
@@ -91,6 +96,7 @@ def test_dropin_apply_model_orchestration_matches_reference_small32(model, monke
     sd.update({k: own[k] for k in synth.SCHEDULE_KEYS})  # the 13 schedule buffers are derived, not synthesised
     missing, unexpected = model.load_state_dict(sd, strict=True)
     assert not missing and not unexpected
+    model._test_loaded_seed = 0
     g = G.load("small32")
     inp = G.small32_inputs()
     cond = {"c_concat": [inp["pose"]], "c_crossattn": [inp["context"]]}
@@ -108,6 +114,47 @@ def test_dropin_apply_model_orchestration_matches_reference_small32(model, monke
     assert len(res) == 13
     for i, r in enumerate(res):
         G.check_summary(g, f"small32/pose{i}", r, 5e-3)
+
+
+def test_sample_log_four_step_chain_matches_the_oracle(model, monkeypatch):
+    """The sampler's host loop end to end on the CPU (kernels = layout-faithful test doubles): sample_log ->
+    DDIMSampler_ReferenceOnly.sample -> ddim_sampling -> p_sample_ddim for a 4-step DDIM schedule (timesteps 751, 501, 251, 1)
+    from a given x_T — schedule construction, index order, the per-timestep bank cache, the cached hint features, CFG
+    with the 'controlnet is more important' branch — against the oracle's chain of p_sample_ddim (ddim.py:460-645)."""
+    import numpy as np
+    from magicdance_b200 import ops, synth
+    from oracle import restatement as R
+    from tests import fake_ops, golden_util as G
+    from tests.test_engine_cpu import _PATCHED
+    for name in _PATCHED + ("cfg_ddim_update",):
+        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    torch.set_grad_enabled(False)
+    try:
+        sd = synth.synth_state_dict(seed=0)
+        if getattr(model, "_test_loaded_seed", None) != 0:  # the apply_model test above leaves these weights loaded and packed
+            own = model.state_dict()
+            sd.update({k: own[k] for k in synth.SCHEDULE_KEYS})
+            model.load_state_dict(sd, strict=True)
+            model._test_loaded_seed = 0
+        inp = synth.synth_inputs(1, 16, seed=5, shared_reference=True)  # 128x128 image: the host loop is size-independent
+        uc_ctx = torch.randn(1, 77, 768, generator=torch.Generator().manual_seed(9))  # must be ignored (ddim.py:599-604)
+        cond = {"c_concat": [inp["pose"]], "c_crossattn": [inp["context"]], "image_control": [inp["ref"]], "wonoise": True}
+        uc = {"c_concat": [inp["pose"]], "c_crossattn": [uc_ctx]}
+        seen = []
+        x0, inter = model.sample_log(cond, 1, ddim=True, ddim_steps=4, eta=0.0, unconditional_guidance_scale=7.0,
+                                     unconditional_conditioning=uc, x_T=inp["x"], callback=seen.append)
+        assert seen == [0, 1, 2, 3] and len(inter["x_inter"]) >= 2
+        sched = R.ddim_schedule(R.make_schedule()["alphas_cumprod"].astype(np.float32).astype(np.float64), num_ddim_steps=4)
+        assert [int(t) for t in sched["timesteps"]] == [1, 251, 501, 751]
+        x = inp["x"]
+        for index in (3, 2, 1, 0):
+            t = torch.full((1,), int(sched["timesteps"][index]), dtype=torch.long)
+            x = R.p_sample_ddim(sd, x, t, index, inp["context"], inp["pose"], inp["ref"], sched, scale=7.0)[0]
+        err = G.rel_l2(x0, x)
+        assert tuple(x0.shape) == (1, 4, 16, 16) and err <= 3e-2, err
+    finally:
+        model.__dict__.pop("_mdb_pipelines", None)
+        torch.set_grad_enabled(True)
 
 
 def test_autoencoder_dropin_has_the_reference_keys_and_decodes_through_the_test_doubles(monkeypatch):
