@@ -157,6 +157,45 @@ def test_sample_log_four_step_chain_matches_the_oracle(model, monkeypatch):
         torch.set_grad_enabled(True)
 
 
+def test_p_losses_forward_value_matches_the_oracle(model, monkeypatch):
+    """The training caller's forward (ddpm.py:2165-2212, q_sample ddpm.py:356-359) under no_grad:
+    x_noisy = sqrt(acp_t) x0 + sqrt(1 - acp_t) eps, apply_model with the CLEAN reference latent (wonoise), and
+    loss = mean((eps_pred - eps)^2) (l_simple_weight 1, logvar 0, original_elbo_weight 0) — against the same arithmetic
+    on the oracle's apply_model.  Gradients stay refused (test above); this pins the value and the loss_dict keys."""
+    from magicdance_b200 import ops, synth
+    from oracle import restatement as R
+    from tests import fake_ops
+    from tests.test_engine_cpu import _PATCHED
+    for name in _PATCHED:
+        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    torch.set_grad_enabled(False)
+    try:
+        sd = synth.synth_state_dict(seed=0)
+        if getattr(model, "_test_loaded_seed", None) != 0:
+            own = model.state_dict()
+            sd.update({k: own[k] for k in synth.SCHEDULE_KEYS})
+            model.load_state_dict(sd, strict=True)
+            model._test_loaded_seed = 0
+        inp = synth.synth_inputs(2, 16, seed=11, shared_reference=False)
+        g = torch.Generator().manual_seed(3)
+        x0 = torch.randn(2, 4, 16, 16, generator=g) * 0.8
+        noise = torch.randn(2, 4, 16, 16, generator=g)
+        t = torch.tensor([700, 35], dtype=torch.long)
+        cond = {"c_concat": [inp["pose"]], "c_crossattn": [inp["context"]], "image_control": [inp["ref"]], "wonoise": True}
+        model.eval()
+        loss, ld = model.p_losses(x0, cond, t, noise=noise)
+        assert set(ld) == {"val/loss_simple", "val/loss_vlb", "val/loss"}
+        acp = R.make_schedule()["alphas_cumprod"]
+        a = torch.tensor(acp[t.numpy()], dtype=torch.float32).reshape(2, 1, 1, 1)
+        x_noisy = a.sqrt() * x0 + (1 - a).sqrt() * noise
+        eps = R.apply_model(sd, x_noisy, t, inp["context"], inp["pose"], inp["ref"], uc=False)
+        want = ((eps - noise) ** 2).mean(dim=(1, 2, 3)).mean()
+        assert abs(float(loss) - float(want)) <= 2e-2 * float(want), (float(loss), float(want))
+        assert abs(float(ld["val/loss_simple"]) - float(want)) <= 2e-2 * float(want)
+    finally:
+        torch.set_grad_enabled(True)
+
+
 def test_autoencoder_dropin_has_the_reference_keys_and_decodes_through_the_test_doubles(monkeypatch):
     """magicdance_b200.dropin.autoencoder.AutoencoderKL (opt-in first_stage target): the reference's constructor
     kwargs (yaml:93-114), exactly its 248 state-dict keys / shapes (manifest recorded from the unmodified reference),
