@@ -422,3 +422,54 @@ def test_polynomial_gelu_constants_in_the_kernel_source_are_accurate():
     coef = fit.fit(3.0, 8)
     assert np.allclose(coef[::-1], [first] + rest, rtol=1e-6, atol=1e-12)
 
+
+def test_pipeline_caches_are_keyed_on_tensor_identity_and_version():
+    """DenoisePipeline's per-sequence caches (a stale appearance bank would silently render the previous reference
+    image): the bank is cached per (reference tensor, its in-place version, ddim index) and dropped as a whole when a
+    different reference shows up; hint features are cached per caller-supplied frame key only."""
+    import torch
+    from magicdance_b200.pipeline import DenoisePipeline
+
+    class Eng:
+        device = torch.device("cpu")
+        calls = {"app": 0, "proj": 0, "hint": 0}
+
+        def appearance_write(self, ref, t, ctx):
+            self.calls["app"] += 1
+            return [ref.clone(), t.clone()]
+
+        def project_bank(self, bank, batches):
+            self.calls["proj"] += 1
+            return ("kv", float(bank[0].sum()), int(bank[1][0]), batches)
+
+        def hint_features(self, pose):
+            self.calls["hint"] += 1
+            return pose * 2
+
+    eng = Eng()
+    pipe = DenoisePipeline(eng, ddim_steps=50, scale=7.0, eta=0.0)
+    ref, ctx = torch.ones(1, 4, 8, 8), torch.zeros(1, 77, 768)
+    a = pipe.reference_bank(ref, ctx, 49)
+    assert pipe.reference_bank(ref, ctx, 49) is a and eng.calls["app"] == 1          # hit
+    b = pipe.reference_bank(ref, ctx, 48)
+    assert eng.calls["app"] == 2 and b[2] == int(pipe.timesteps[48]) and a[2] == int(pipe.timesteps[49]) == 981
+    ref.add_(1.0)                                                                    # same storage, new content
+    c = pipe.reference_bank(ref, ctx, 49)
+    assert eng.calls["app"] == 3 and c[1] == float(ref.sum()) != a[1]
+    assert len(pipe._bank_cache) == 1                                                # the old sequence's banks are gone
+    other = torch.ones(1, 4, 8, 8)
+    pipe.reference_bank(other, ctx, 49)
+    assert eng.calls["app"] == 4 and len(pipe._bank_cache) == 1
+    two = torch.stack([other[0], other[0]])                                          # all rows the same image: row 0 only
+    d = pipe.reference_bank(two, ctx, 49, first_only=True)
+    assert d[3] == 1 and eng.calls["app"] == 5
+    pose = torch.ones(1, 3, 16, 16)
+    h1 = pipe.hint(pose, frame_key="f0")
+    assert pipe.hint(pose, frame_key="f0") is h1 and eng.calls["hint"] == 1
+    pipe.hint(pose, frame_key="f1")
+    pipe.hint(pose)                                                                  # no key: never cached
+    pipe.hint(pose)
+    assert eng.calls["hint"] == 4
+    pipe.clear_caches()
+    assert not pipe._bank_cache and not pipe._hint_cache
+
