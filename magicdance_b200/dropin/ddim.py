@@ -119,9 +119,10 @@ class DDIMSampler_ReferenceOnly(object):
         pipe = self._pipeline(unconditional_guidance_scale)
         dev = pipe.device
         x = x.to(device=dev, dtype=torch.float32)
-        ref = torch.cat(c["image_control"], 1)
-        ctx = torch.cat(c["c_crossattn"], 1)
-        pose_map = torch.cat(c["c_concat"], 1)
+        # one-element lists (every released script) are used as they are: torch.cat would hand the engine a fresh
+        # copy every step, and the caches below are keyed on tensor identity
+        one = lambda lst: lst[0] if len(lst) == 1 else torch.cat(lst, 1)
+        ref, ctx, pose_map = one(c["image_control"]), one(c["c_crossattn"]), one(c["c_concat"])
         if c["wonoise"]:
             # the clean reference latent feeds the appearance net (ddim.py:532-533): the bank depends on
             # (reference, t) only.  One reference for the whole batch (the scripts repeat it per sample) is
@@ -137,7 +138,8 @@ class DDIMSampler_ReferenceOnly(object):
             ref_n = self.model.q_sample(ref, t.to(ref.device))
             tt = pipe.t_dev[index].expand(ref.shape[0]).contiguous()
             bank_kv = pipe.engine.project_bank(pipe.engine.appearance_write(ref_n, tt, ctx), ref.shape[0])
-        hint = pipe.hint(pose_map.to(dev), frame_key=(pose_map.data_ptr(), pose_map._version, tuple(pose_map.shape)))
+        hint = pipe.hint(pose_map.to(dev), frame_key=(pose_map.data_ptr(), pose_map._version, tuple(pose_map.shape)),
+                         keep_alive=pose_map)
         noise = None
         if float(self.ddim_sigmas[index]) != 0.0:
             noise = torch.randn_like(x)

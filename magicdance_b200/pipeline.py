@@ -93,14 +93,22 @@ class DenoisePipeline:
         self._bank_cache.clear()
         self._hint_cache.clear()
 
-    def hint(self, pose_map, frame_key=None):
+    HINT_CACHE_FRAMES = 8
+
+    def hint(self, pose_map, frame_key=None, keep_alive=None):
+        """Hint-encoder features of a pose map, cached per caller-supplied frame key.  When the key is derived from
+        a tensor's address (the drop-in sampler keys on the caller's pose tensor), pass that tensor as `keep_alive`:
+        the entry then holds a strong reference, so the storage cannot be freed and its address handed to the NEXT
+        frame's pose map while the entry exists (a recycled address would be a silent stale hit)."""
         if frame_key is None:
             return self.engine.hint_features(pose_map)
         hit = self._hint_cache.get(frame_key)
         if hit is None:
-            hit = self.engine.hint_features(pose_map)
+            while len(self._hint_cache) >= self.HINT_CACHE_FRAMES:  # oldest first (dicts keep insertion order)
+                self._hint_cache.pop(next(iter(self._hint_cache)))
+            hit = (self.engine.hint_features(pose_map), keep_alive)
             self._hint_cache[frame_key] = hit
-        return hit
+        return hit[0]
 
     # ---- one DDIM step ---------------------------------------------------------------------------
     def step(self, x, index, context, hint_feat, bank_kv, noise=None):

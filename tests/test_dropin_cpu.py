@@ -144,6 +144,11 @@ def test_sample_log_four_step_chain_matches_the_oracle(model, monkeypatch):
         x0, inter = model.sample_log(cond, 1, ddim=True, ddim_steps=4, eta=0.0, unconditional_guidance_scale=7.0,
                                      unconditional_conditioning=uc, x_T=inp["x"], callback=seen.append)
         assert seen == [0, 1, 2, 3] and len(inter["x_inter"]) >= 2
+        # the caller's tensors reach the engine as they are: one text-K/V entry per network pass kind for the whole
+        # chain (a fresh torch.cat copy per step would miss every step), one hint entry, one bank entry per timestep
+        pipe = next(iter(model._mdb_pipelines.values()))
+        mine = [k for k in model.engine()._ctx_cache if tuple(k[3][:3]) == (1, 77, 768)]  # (net, storage, version, shape)
+        assert 1 <= len(mine) <= 4 and len(pipe._hint_cache) == 1 and len(pipe._bank_cache) == 4
         sched = R.ddim_schedule(R.make_schedule()["alphas_cumprod"].astype(np.float32).astype(np.float64), num_ddim_steps=4)
         assert [int(t) for t in sched["timesteps"]] == [1, 251, 501, 751]
         x = inp["x"]

@@ -472,4 +472,17 @@ def test_pipeline_caches_are_keyed_on_tensor_identity_and_version():
     assert eng.calls["hint"] == 4
     pipe.clear_caches()
     assert not pipe._bank_cache and not pipe._hint_cache
+    # keyed on a tensor's address (the drop-in sampler): the entry keeps that tensor alive, so the next frame's pose map
+    # cannot be allocated at the same address and hit the previous frame's features
+    pose_a = torch.ones(1, 3, 16, 16)
+    ptr = pose_a.data_ptr()
+    fa = pipe.hint(pose_a, frame_key=(ptr, pose_a._version, tuple(pose_a.shape)), keep_alive=pose_a)
+    del pose_a
+    pose_b = torch.zeros(1, 3, 16, 16)
+    assert pose_b.data_ptr() != ptr
+    fb = pipe.hint(pose_b, frame_key=(pose_b.data_ptr(), pose_b._version, tuple(pose_b.shape)), keep_alive=pose_b)
+    assert float(fa.sum()) != float(fb.sum())
+    for i in range(20):  # bounded: the oldest frames leave
+        pipe.hint(pose_b, frame_key=("k", i))
+    assert len(pipe._hint_cache) == pipe.HINT_CACHE_FRAMES
 
