@@ -108,11 +108,14 @@ class ControlLDMReferenceOnlyPose(LatentDiffusionReferenceOnly):
         """cldm.py:1099-1117 — same arguments, returns eps (B,4,h,w) fp32."""
         assert isinstance(cond, dict)
         assert not self.only_mid_control
-        cond_txt = torch.cat(cond["c_crossattn"], 1)
+        # a one-element list (every released script) is passed on as the caller's tensor: the engine caches the text
+        # keys/values per tensor identity, and torch.cat would hand it a fresh copy on every call
+        one = lambda lst: lst[0] if len(lst) == 1 else torch.cat(lst, 1)
+        cond_txt = one(cond["c_crossattn"])
         if self.control_enabled and cond.get("c_crossattn_void") is not None:
             raise NotImplementedError("c_crossattn_void is never passed by the MagicPose scripts")
         assert self.control_enabled and cond.get("c_concat") is not None, "the pose map (c_concat) is required"
-        cond_hint = torch.cat(cond["c_concat"], 1)
+        cond_hint = one(cond["c_concat"])
         eng = self.engine(x_noisy.device)
         return eng.apply_model(x_noisy, t, cond_txt, cond_hint, reference_image_noisy, uc=uc)
 
