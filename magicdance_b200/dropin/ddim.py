@@ -10,6 +10,8 @@ the frames of a video — the reference recomputes all of them for every frame a
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -79,6 +81,12 @@ class DDIMSampler_ReferenceOnly(object):
         img = torch.randn(shape, device=device) if x_T is None else x_T.to(device)
         intermediates = {"x_inter": [img], "pred_x0": [img]}
         total = self.ddim_timesteps.shape[0]
+        if (os.environ.get("MDB_DROPIN_GRAPH", "0") == "1" and not quantize_denoised and temperature == 1.
+                and noise_dropout == 0. and score_corrector is None and dynamic_threshold is None and inpaint is None):
+            out = self._ddim_sampling_graphed(cond, img, unconditional_guidance_scale, unconditional_conditioning,
+                                              callback, img_callback, log_every_t, intermediates)
+            if out is not None:
+                return out
         for i, step in enumerate(np.flip(self.ddim_timesteps)):
             index = total - i - 1
             ts = torch.full((b,), int(step), device=device, dtype=torch.long)
@@ -96,6 +104,60 @@ class DDIMSampler_ReferenceOnly(object):
                 intermediates["x_inter"].append(img)
                 intermediates["pred_x0"].append(pred_x0)
         return img, intermediates
+
+    @torch.no_grad()
+    def _ddim_sampling_graphed(self, c, img, scale, uc, callback, img_callback, log_every_t, intermediates):
+        """OPT-IN (MDB_DROPIN_GRAPH=1; not yet run on a GPU): the same chain as the loop above, but every step is
+        one replay of pipeline.GraphedDenoiser's captured step graph and the appearance bank of the reference is built
+        by its timestep-batched bank graph — what bench.py times — instead of ~650 eager launches per step driven from
+        Python.  Returns None (the caller falls back to the eager loop) for anything the graphs do not cover: eta != 0,
+        a noised or per-sample reference, no classifier-free guidance, CPU tensors."""
+        from .. import parallel
+        from ..pipeline import GraphedDenoiser, plan_bank_chunks
+        if not (isinstance(c, dict) and c.get("image_control") is not None and c.get("wonoise") and uc is not None
+                and uc.get("image_control") is None and scale != 1.0 and not c.get("overlap_sampling")
+                and not np.any(self.ddim_sigmas) and img.is_cuda):
+            return None
+        one = lambda lst: lst[0] if len(lst) == 1 else torch.cat(lst, 1)
+        ref, ctx, pose_map = one(c["image_control"]), one(c["c_crossattn"]), one(c["c_concat"])
+        if ref.shape[0] > 1 and not bool((ref[1:] == ref[:1]).all()):
+            return None  # one reference image per batch only (the scripts repeat it per sample)
+        pipe = self._pipeline(scale)
+        b, _, h, w = img.shape
+        total = int(self.ddim_timesteps.shape[0])
+        graphs = self.model.__dict__.setdefault("_mdb_graphs", {})
+        gkey = (id(pipe), b, h, w, ctx.data_ptr(), ctx._version, tuple(ctx.shape))
+        ent = graphs.get(gkey)
+        if ent is None:
+            graphs.clear()  # one captured configuration at a time: each owns gigabytes of graph memory
+            gd = GraphedDenoiser(pipe, b, (h, w), ctx.to(pipe.device), bank_chunk=parallel.bank_chunk_size(total, 1))
+            gd.capture()
+            ent = {"gd": gd, "ctx": ctx, "bank_key": None,
+                   "slots": torch.empty((total, gd.layout.numel), dtype=torch.float16, device=pipe.device)}
+            graphs[gkey] = ent
+        gd = ent["gd"]
+        bkey = (ref.data_ptr(), ref._version)
+        if ent["bank_key"] != bkey:  # a new reference image: one batched appearance pass per chunk of timesteps
+            order = list(range(total - 1, -1, -1))
+            ent["slot_of"] = {ix: s for s, ix in enumerate(order)}
+            for s0, part in plan_bank_chunks(order, gd.bank_chunk):
+                gd.build_bank(part, ref.to(pipe.device), ent["slots"][s0:s0 + len(part)])
+            ent["bank_key"], ent["ref"] = bkey, ref  # the strong reference keeps the address from being recycled
+        gd.hint.copy_(pipe.hint(pose_map.to(pipe.device),
+                                frame_key=(pose_map.data_ptr(), pose_map._version, tuple(pose_map.shape)),
+                                keep_alive=pose_map))
+        gd.x.copy_(img.to(device=pipe.device, dtype=torch.float32))
+        for i in range(total):
+            index = total - i - 1
+            gd.step(index, ent["slots"][ent["slot_of"][index]])
+            if callback:
+                callback(i)
+            if img_callback:
+                img_callback(gd.pred_x0.clone(), i)
+            if index % log_every_t == 0 or index == total - 1:
+                intermediates["x_inter"].append(gd.x_prev.clone())
+                intermediates["pred_x0"].append(gd.pred_x0.clone())
+        return gd.x_prev.clone(), intermediates
 
     @torch.no_grad()
     def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,

@@ -4,7 +4,7 @@
 #
 #   gpurun --timeout 900 -- 'bash scripts/gpu_pending_checks.sh numerics'          # first: ~4 min, decides the rest
 #   gpurun --timeout 900 -- 'bash scripts/gpu_pending_checks.sh gemm8 gemm1'       # then the timing legs that matter
-#   sections: numerics gemm8 gemm1 attn gn overlap baseline vae tune all
+#   sections: numerics gemm8 gemm1 attn gn overlap baseline vae tune dropin all
 #
 # Reading the results: a feature becomes the default when (1) its numerics leg is all "ok", (2) its bench line
 # has "finite": true and an "x_final_fingerprint" equal (to ~1e-3) to pending_b1_default.json / pending_b8_default.json,
@@ -104,4 +104,9 @@ fi
 if want tune; then
   echo "== per-shape GEMM launch plan (scripts/gpu_tune_gemm.py): dry run with the validated kernels only; add --variants for the green opt-ins"
   timeout -k 10 600 python scripts/gpu_tune_gemm.py --frames 1,8 --dry-run > gpurun_out/tune_gemm.log 2>&1; echo "tune rc=$?"; tail -n 6 gpurun_out/tune_gemm.log
+fi
+
+if want dropin; then
+  echo "== drop-in sampler through CUDA graphs (MDB_DROPIN_GRAPH=1): same result as the eager loop, time per step of both"
+  timeout -k 10 300 python scripts/gpu_dropin_graph_check.py > gpurun_out/pending_dropin_graph.log 2>&1; echo "dropin rc=$?"; tail -n 6 gpurun_out/pending_dropin_graph.log
 fi
