@@ -99,6 +99,22 @@ def judge(dirname, fp_tol, min_gain):
         report.append((name, take, notes))
         if take:
             enabled[name] = env
+    # the drop-in sampler's graph path has its own gate script (result check + both timings in one log)
+    name, path = "MDB_DROPIN_GRAPH=1", os.path.join(dirname, "pending_dropin_graph.log")
+    if os.path.isfile(path):
+        with open(path) as f:
+            text = f.read()
+        t = {tag: float(v) for tag, v in re.findall(r"^(eager loop|graph replay)\s*: ([0-9.]+) ms/step", text, re.M)}
+        ok = text.strip().endswith("OK") and "eager loop" in t and "graph replay" in t
+        gain = (t["eager loop"] / t["graph replay"] - 1.0) if ok else -1.0
+        take = ok and gain > min_gain
+        report.append((name, take, [f"gate script: {'OK' if ok else 'not OK'}"] +
+                       ([f"eager {t['eager loop']:.2f} ms/step, graph {t['graph replay']:.2f} ms/step ({gain * 100:+.1f} %)"] if ok else [])))
+        gains[name] = gain
+        if take:
+            enabled[name] = {"MDB_DROPIN_GRAPH": "1"}
+    else:
+        report.append((name, False, ["gate log missing"]))
     for group in EXCLUSIVE:
         live = [n for n in group if n in enabled]
         for n in sorted(live, key=lambda x: -gains[x])[1:]:

@@ -381,6 +381,13 @@ def test_decide_defaults_rules(tmp_path):
     bench("pending_b1_overlap.json", 126.0)                                                          # host-side, +7.7 %
     report, enabled = dd.judge(str(d), 2e-3, 0.01)
     assert set(enabled) == {"MDB_GEMM_PAIR=3", "MDB_BANK_OVERLAP=1"}, (enabled, report)
+    (d / "pending_dropin_graph.log").write_text("eager loop : 21.500 ms/step (46.5 steps/s), finite=True\n"
+                                                "graph replay: 7.100 ms/step (140.8 steps/s), finite=True\n"
+                                                "eager vs eager (atomics order) 1.0e-03; graph vs eager 1.2e-03\nOK\n")
+    assert "MDB_DROPIN_GRAPH=1" in dd.judge(str(d), 2e-3, 0.01)[1]
+    (d / "pending_dropin_graph.log").write_text("eager loop : 21.5 ms/step\ngraph replay: 7.1 ms/step\nFAILED\n")
+    assert "MDB_DROPIN_GRAPH=1" not in dd.judge(str(d), 2e-3, 0.01)[1]
+    (d / "pending_dropin_graph.log").unlink()
     cfg = {}
     for env in enabled.values():
         cfg.update(env)
