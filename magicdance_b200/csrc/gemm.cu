@@ -1783,7 +1783,9 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   const char* pair_min_env = getenv("MDB_GEMM_PAIR_MIN");
   const bool pairq = (pair_env != nullptr && pair_env[0] == '3');  // gemm_pairq_kernel: see its header comment
   const bool pair_ok = (pair_env != nullptr && (pair_env[0] == '1' || pair_env[0] == '2')) || (pairq && g->n % 8 == 0);
-  const long long pair_min = pair_min_env ? atoll(pair_min_env) : 256ll;
+  // smallest grid (in single-CTA-tile equivalents) that is worth a pair launch: 256 for the one-tile pair mode
+  // (measured), 128 for the persistent kernels' second cut (one round of 64 pair tiles already fills 128 SMs)
+  const long long pair_min = pair_min_env ? atoll(pair_min_env) : (pairq ? 128ll : 256ll);
   const int m_tiles = (g->m + kBM - 1) / kBM;
   bool pair = pair_ok && g->splits <= 1 && m_tiles >= 2;
   int bn;

@@ -53,6 +53,7 @@ if want gemm8; then
   MDB_GEMM_PAIR=2 bench pending_b8_pair2 90 $B8
   MDB_GEMM_PAIR=3 bench pending_b8_pair3 90 $B8
   MDB_GEMM_TMAST=1 bench pending_b8_tmast 90 $B8
+  MDB_GEMM_PAIR=3 MDB_GEMM_PAIR_SPLITK=1 bench pending_b8_pair3_pairs 90 $B8   # + pair split-K for the one-wave layers
 fi
 
 if want gemm1; then
