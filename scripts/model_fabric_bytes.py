@@ -80,7 +80,7 @@ def default_choice(m, n, k, geglu):
 
 
 def pair_choice(m, n, k, geglu):
-    """the opt-in pair kernels: pairs (<= 148 CTAs, long K) else pairq (>= 256 CTAs); None if neither takes it"""
+    """the opt-in pair kernels: pairs (<= 148 CTAs, long K) else pairq (>= 128 tile-equivalents); None if neither takes it"""
     mt, chunks = -(-m // 128), k // 64
     if mt < 2:
         return None
@@ -108,7 +108,7 @@ def pair_choice(m, n, k, geglu):
             w = 160
         else:
             w = 128
-        if w and 2 * m_pairs * -(-n // w) >= 256:
+        if w and 2 * m_pairs * -(-n // w) >= 128:
             tiles = m_pairs * -(-n // w)
             rounds = -(-tiles // 74)
             best = (148, rounds * chunks * (A_TILE + 64 * w), f"pairq bn{w} x{rounds}")
