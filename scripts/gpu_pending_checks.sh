@@ -77,6 +77,10 @@ if want gn; then
   timeout -k 10 100 python scripts/gpu_microbench.py misc > gpurun_out/pending_microbench_misc.log 2>&1; echo "microbench misc rc=$?"
   MDB_GN_FUSED=1 timeout -k 10 100 python scripts/gpu_microbench.py misc > gpurun_out/pending_microbench_misc_gnfused.log 2>&1; echo "microbench misc fused rc=$?"
   MDB_GN_FUSED=1 bench pending_b1_gnfused 90 $B1
+  # does the single launch also pay at eight frames (cond+uncond batch 16, bank build batch 25)?
+  MDB_GN_FUSED=1 MDB_GN_FUSED_MAX_BATCH=64 timeout -k 10 100 python scripts/gpu_microbench.py misc > gpurun_out/pending_microbench_misc_gnfused64.log 2>&1; echo "microbench misc fused(all batches) rc=$?"
+  [ -f gpurun_out/pending_b8_default.json ] || bench pending_b8_default 120 $B8
+  MDB_GN_FUSED=1 MDB_GN_FUSED_MAX_BATCH=64 bench pending_b8_gnfused64 90 $B8
 fi
 
 if want overlap; then
