@@ -111,20 +111,19 @@ int mdb_attention_f16(const mdb_attn_desc* desc, mdb_stream_t stream);
  * cldm.py:104).  Replaces GroupNorm32 (ldm/modules/diffusionmodules/util.py:252-254) + nn.SiLU in
  * ResBlock.in_layers/out_layers and UNet.out (openaimodel.py:222-226,246-248,744-748), and
  * Normalize (attention.py:89-90, eps 1e-6) in SpatialTransformer.
- *   x1 [B][hw][c1], x2 [B][hw][c2] (x2 NULL => c2 = 0), y [B][hw][c1+c2];  stats: fp32 [B][32][2]
- *   scratch; stats_prezeroed != 0 promises it is already zero (callers that hand every call its own slot
- *   of a ring they clear once per network pass save one memset node per GroupNorm).
+ *   x1 [B][hw][c1], x2 [B][hw][c2] (x2 NULL => c2 = 0), y [B][hw][c1+c2].
+ * Deterministic (fixed-order reductions, no atomics on data) and pivot-shifted (sums of x - x[b,0,first channel of
+ * the group]), so large-mean activations do not cancel.  Two paths, chosen by batch size (mode 0), or forced
+ * (mode 1 = two kernels, mode 2 = cluster):
+ *   - ONE launch: a thread-block cluster per (batch element, group) exchanges its partial sums through
+ *     distributed shared memory (channels per group even, i.e. c a multiple of 64); ws may be NULL;
+ *   - stats (+ last-CTA fold) -> apply: needs ws of mdb_groupnorm_ws_floats(c, batch, hw) floats that were ZERO
+ *     when first used (self-resetting tickets; calls of any shape on one stream may share one workspace).
  * ---------------------------------------------------------------------------------------------- */
 int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* gamma, const float* beta,
-                      void* y, float* stats_ws, int32_t batch, int32_t hw, float eps, int32_t silu,
-                      int32_t stats_prezeroed, mdb_stream_t stream);
-
-/* Same operation in ONE launch for small batches (single-frame latency): a thread-block cluster per (batch
- * element, group) reads its slice twice and exchanges the partial sums through distributed shared memory; no
- * statistics scratch.  Channels per group must be even (c a multiple of 64); same references as above. */
-int mdb_groupnorm_fused_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* gamma,
-                            const float* beta, void* y, int32_t batch, int32_t hw, float eps, int32_t silu,
-                            mdb_stream_t stream);
+                      void* y, float* ws, int32_t batch, int32_t hw, float eps, int32_t silu, int32_t mode,
+                      mdb_stream_t stream);
+int64_t mdb_groupnorm_ws_floats(int32_t c, int32_t batch, int32_t hw);
 
 /* LayerNorm over the last dim (eps 1e-5), fp16 [rows][c] -> fp16; replaces nn.LayerNorm norm1/2/3 of
  * BasicTransformerBlock (attention.py:270-272). */

@@ -47,8 +47,7 @@ SIGNATURES = {
     "mdb_attention_f16": (c_int32, [C.POINTER(AttnDesc), c_void_p]),
     "mdb_groupnorm_f16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int32, c_int32, c_float, c_int32, c_int32, c_void_p]),
-    "mdb_groupnorm_fused_f16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
-                                          c_int32, c_int32, c_float, c_int32, c_void_p]),
+    "mdb_groupnorm_ws_floats": (c_int64, [c_int32, c_int32, c_int32]),
     "mdb_layernorm_f16": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),
     "mdb_conv3x3_direct_f16": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_int32, c_int32, c_void_p]),
@@ -84,6 +83,11 @@ def load():
         raise RuntimeError(
             f"magicdance_b200: kernel library {path} is missing — run `python -m magicdance_b200.build` "
             "(there is no CPU/PyTorch fallback for the hot path)")
+    if path == _build.LIB_PATH and os.path.isdir(_build.CSRC) and not _build.is_fresh():
+        # the descriptor structs below mirror the sources next to the library: a library built from other sources
+        # would be called with mismatched layouts (memory corruption, not an error) — refuse it
+        raise RuntimeError(f"magicdance_b200: {path} was not built from the sources in {_build.CSRC} "
+                           "(stamp mismatch) — run `python -m magicdance_b200.build`")
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol

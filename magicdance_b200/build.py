@@ -46,17 +46,48 @@ def is_fresh() -> bool:
         return f.read().strip() == _digest()
 
 
+def _file_digest(src: str) -> str:
+    h = hashlib.sha256()
+    for rel in [src] + HEADERS:
+        with open(os.path.join(CSRC, rel), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into lib/libmagicdance_b200.so; returns the library path."""
+    """Compile csrc/*.cu into lib/libmagicdance_b200.so; returns the library path.  Translation units are
+    compiled in parallel and cached per source digest (lib/obj/*.o), then linked."""
     if not force and is_fresh():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        stamp = obj + ".stamp"
+        dig = _file_digest(src)
+        if not force and os.path.isfile(obj) and os.path.isfile(stamp) and open(stamp).read().strip() == dig:
+            return obj, ""
+        cmd = [_nvcc()] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed ({' '.join(cmd)}):\n{proc.stdout}\n{proc.stderr}")
+        with open(stamp, "w") as f:
+            f.write(dig)
+        return obj, proc.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    if verbose:
+        for _, err in results:
+            print(err)
+    cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + [o for o, _ in results]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({' '.join(cmd)}):\n{proc.stdout}\n{proc.stderr}")
-    if verbose:
-        print(proc.stderr)
+        raise RuntimeError(f"link failed ({' '.join(cmd)}):\n{proc.stdout}\n{proc.stderr}")
     with open(STAMP, "w") as f:
         f.write(_digest())
     return LIB_PATH

@@ -1,12 +1,19 @@
-// GroupNorm(32) [+SiLU] and LayerNorm over channels-last fp16 activations (HBM-bound kernels).
+// GroupNorm(32) [+SiLU] and LayerNorm over channels-last fp16 activations (HBM/L2-bound kernels).
 //
-// GroupNorm runs as (memset) -> stats -> apply:
-//   stats : each CTA owns a slab of rows of one batch element, threads own 8 consecutive channels
-//           (one 16-byte load per row), per-channel partial sums are folded to per-group sums with
-//           warp shuffles / shared atomics and added to stats[b][32][{sum,sumsq}] (fp32).
-//   apply : y = (x - mean) * rstd * gamma + beta, optional SiLU, 8 channels per thread; the input
-//           may be the channel concatenation of two tensors, which is how torch.cat([h, skip], 1)
-//           (cldm.py:104) disappears: the normalised copy is the only concatenated buffer.
+// GroupNorm32 / Normalize (util.py:252-254, attention.py:89-90): fp32 statistics, two eps values.  Both paths below
+// are DETERMINISTIC (no atomics on data: fixed-order warp-shuffle / shared-memory / DSMEM reductions) and use
+// PIVOT-SHIFTED sums: with K = x[b, pixel 0, first channel of the group] every partial accumulates
+// S = sum(x - K), Q = sum((x - K)^2); mean = K + S/n, var = Q/n - (S/n)^2.  K is a sample of the data, so
+// |mean - K| is of the order of the standard deviation and the subtraction loses a few bits at most — unlike
+// E[x^2] - mean^2, which cancels catastrophically for activations whose mean is large against their spread.
+//
+//   small batches  gn_cluster_kernel : ONE launch; a thread-block cluster per (batch element, group) splits the
+//                  pixels, warp shuffles -> shared memory -> DSMEM exchange of (S, Q), second pass from L1/L2.
+//   large batches  gn_stats_kernel   : coalesced full-row reads, per-CTA (S, Q) partials to a workspace, the LAST
+//                  CTA of a batch element (ticket) folds them in slot order -> (mean, var)
+//                  gn_apply_kernel   : y = x * a_c + b_c [+ SiLU], 8 channels per thread.
+// The input may be the channel concatenation of two tensors, which is how torch.cat([h, skip], 1) (cldm.py:104)
+// disappears: the normalised copy is the only concatenated buffer.
 #include "common.cuh"
 
 namespace mdb {
@@ -20,11 +27,24 @@ __device__ __forceinline__ const uint4* gn_src(const __half* x1, int c1, const _
                    : reinterpret_cast<const uint4*>(x2 + row * c2 + (ch - c1));
 }
 
+// pivot of group g of batch element b: the group's first channel at pixel 0
+__device__ __forceinline__ float gn_pivot(const __half* x1, int c1, const __half* x2, int c2, int b, int hw, int ch) {
+  return (ch < c1) ? __half2float(x1[static_cast<long long>(b) * hw * c1 + ch])
+                   : __half2float(x2[static_cast<long long>(b) * hw * c2 + (ch - c1)]);
+}
+
+constexpr int kGnMaxBatch = 1024;     // batch elements of the two-kernel path (size of the ticket region)
+constexpr int kGnFinalThreads = 256;  // threads of the last CTA that fold the partials (4 slices x 64 entries)
+
+// ws layout (floats): [kGnMaxBatch] tickets (uint, zero at first use, self-resetting; a FIXED region so that calls
+//                     with different batch sizes can share one workspace) | [batch][64] final (mean, var) per group |
+//                     [batch][gridDim.x][64] partials (S_0..S_31, Q_0..Q_31)
 // rows_per_cta is chosen by the launcher so that ~2 waves of CTAs cover the tensor and every thread
 // owns at most a handful of rows (loads of one thread are independent and unrolled).
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
-                                float* __restrict__ stats, int hw, int rows_per_cta) {
-  extern __shared__ float sh[];  // [2][32] group sums
+                                float* __restrict__ ws, int batch, int hw, int rows_per_cta) {
+  extern __shared__ float sh[];  // [2][rstride][c] per-thread channel sums, reused as [4][64] by the final fold
+  __shared__ int s_last;
   pdl_launch_dependents();
   const int c = c1 + c2;
   const int cg = c / 32;
@@ -32,15 +52,24 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __h
   const int row0 = blockIdx.x * rows_per_cta;
   const int rows = min(rows_per_cta, hw - row0);
   const int vecs = c / 8;
-  if (threadIdx.x < 64) sh[threadIdx.x] = 0.f;
-  __syncthreads();
-  pdl_wait();
   const int v = threadIdx.x % vecs;
   const int rphase = threadIdx.x / vecs;
   const int rstride = blockDim.x / vecs;
-  float s[8], q[8];
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws) + b;
+  float* stats = ws + kGnMaxBatch + static_cast<long long>(b) * 64;
+  float* pbase = ws + kGnMaxBatch + static_cast<long long>(batch) * 64;
+  float* partial = pbase + (static_cast<long long>(b) * gridDim.x + blockIdx.x) * 64;
+  pdl_wait();
+  // this thread's 8 channels lie in at most two groups (cg >= 8, or cg == 4 where a vector is two whole groups)
+  const int g_first = (v * 8) / cg;
+  const float ka = gn_pivot(x1, c1, x2, c2, b, hw, g_first * cg);
+  const float kb = (g_first + 1 < 32) ? gn_pivot(x1, c1, x2, c2, b, hw, (g_first + 1) * cg) : 0.f;
+  float piv[8], s[8], q[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  for (int i = 0; i < 8; ++i) {
+    piv[i] = ((v * 8 + i) / cg == g_first) ? ka : kb;
+    s[i] = q[i] = 0.f;
+  }
 #pragma unroll 4
   for (int r = rphase; r < rows; r += rstride) {
     const long long row = static_cast<long long>(b) * hw + row0 + r;
@@ -49,31 +78,57 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __h
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float2 f = __half22float2(h2[e]);
-      s[2 * e] += f.x; q[2 * e] += f.x * f.x;
-      s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
+      const float d0 = f.x - piv[2 * e], d1 = f.y - piv[2 * e + 1];
+      s[2 * e] += d0; q[2 * e] = fmaf(d0, d0, q[2 * e]);
+      s[2 * e + 1] += d1; q[2 * e + 1] = fmaf(d1, d1, q[2 * e + 1]);
     }
   }
-  if (rphase < rows) {
-    // fold the 8 channels into (at most two) groups
-    const int g_first = (v * 8) / cg;
-    float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+  // per-thread channel sums -> shared memory, then thread (g, which) folds its group in a fixed order
+  float* sh_s = sh;
+  float* sh_q = sh + rstride * c;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = (v * 8 + i) / cg;
-      if (g == g_first) { sa += s[i]; qa += q[i]; } else { sb += s[i]; qb += q[i]; }
-    }
-    atomicAdd(&sh[g_first], sa);
-    atomicAdd(&sh[32 + g_first], qa);
-    if ((v * 8 + 7) / cg != g_first) {  // cg >= 8 or cg == 4: a vector spans at most two groups
-      atomicAdd(&sh[g_first + 1], sb);
-      atomicAdd(&sh[32 + g_first + 1], qb);
-    }
+  for (int i = 0; i < 8; ++i) {
+    sh_s[rphase * c + v * 8 + i] = s[i];
+    sh_q[rphase * c + v * 8 + i] = q[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x & 31;
+    const float* src = (threadIdx.x < 32) ? sh_s : sh_q;
+    float acc = 0.f;
+    for (int r = 0; r < rstride; ++r)
+      for (int j = 0; j < cg; ++j) acc += src[r * c + g * cg + j];
+    partial[threadIdx.x] = acc;
+  }
+  // ---- ticket: the last CTA of this batch element folds all partials in slot order ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* pall = pbase + static_cast<long long>(b) * gridDim.x * 64;
+  const int nblk = gridDim.x;
+  if (threadIdx.x < kGnFinalThreads) {
+    const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    const int per = (nblk + 3) / 4;
+    const int i0 = sl * per, i1 = min(nblk, i0 + per);
+    float acc = 0.f;
+    for (int i = i0; i < i1; ++i) acc += __ldcg(pall + static_cast<long long>(i) * 64 + e);
+    sh[sl * 64 + e] = acc;
   }
   __syncthreads();
   if (threadIdx.x < 32) {
-    atomicAdd(&stats[(b * 32 + threadIdx.x) * 2 + 0], sh[threadIdx.x]);
-    atomicAdd(&stats[(b * 32 + threadIdx.x) * 2 + 1], sh[32 + threadIdx.x]);
+    const int g = threadIdx.x;
+    const float S = ((sh[g] + sh[64 + g]) + sh[128 + g]) + sh[192 + g];
+    const float Q = ((sh[32 + g] + sh[96 + g]) + sh[160 + g]) + sh[224 + g];
+    const float inv_n = 1.0f / (static_cast<float>(cg) * hw);
+    const float k = gn_pivot(x1, c1, x2, c2, b, hw, g * cg);
+    const float ms = S * inv_n;
+    stats[2 * g] = k + ms;
+    stats[2 * g + 1] = fmaxf(fmaf(-ms, ms, Q * inv_n), 0.f);
   }
+  if (threadIdx.x == 0) *ticket = 0u;  // self-resetting: the next call on this workspace starts from zero
 }
 
 // apply: every CTA first turns the 32 group statistics of its batch element into per-channel
@@ -89,7 +144,6 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __h
   const int cg = c / 32;
   const int vecs = c / 8;
   const int b = blockIdx.y;
-  const float inv_n = 1.0f / (static_cast<float>(cg) * hw);
   // gamma / beta are constants: park them in shared memory before the PDL wait, combine with the statistics after
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     s_ab[ch] = gamma[ch];
@@ -98,8 +152,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __h
   pdl_wait();
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {  // same thread owns the same channels: no sync needed
     const int g = ch / cg;
-    const float mean = stats[(b * 32 + g) * 2] * inv_n;
-    const float var = fmaxf(stats[(b * 32 + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+    const float mean = stats[(b * 32 + g) * 2];
+    const float var = stats[(b * 32 + g) * 2 + 1];
     const float a = rsqrtf(var + eps) * s_ab[ch];
     s_ab[ch] = a;
     s_ab[c + ch] = s_ab[c + ch] - mean * a;
@@ -138,25 +192,23 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __h
 }
 
 // ------------------------------------------------------------------------------------------------
-// Single-launch GroupNorm for small batches (mdb_groupnorm_fused_f16) — written after the round-1 GPU budget
-// was spent, NOT YET RUN ON A GPU, opt-in (MDB_GN_FUSED=1 in magicdance_b200/ops.py).
-// At one frame the stats -> apply pair above costs two dependent launches (~7 + ~9 us, 88 pairs per step) for
-// tensors of 0.1 ... 8 MB.  Here one CLUSTER owns one (batch element, group): its CTAs split the pixels, each
-// reads its hw/CS x cg slice twice (the second pass hits L1/L2), the partial (sum, sum of squares) pairs are
-// exchanged through distributed shared memory — no atomics, no statistics buffer, no second kernel.
+// Single-launch GroupNorm for small batches.  At one frame a stats -> apply pair costs two dependent launches
+// (~7 + ~9 us, 88 pairs per step) for tensors of 0.1 ... 8 MB.  Here one CLUSTER owns one (batch element, group):
+// its CTAs split the pixels, each reads its hw/CS x cg slice twice (the second pass hits L1/L2), the partial
+// (S, Q) pairs are exchanged through distributed shared memory — no atomics, no workspace, no second kernel.
 // Thread layout: a group is cg = C/32 consecutive channels = cg/2 half2 words per pixel; thread t owns word
 // t % (cg/2) of pixels t / (cg/2), + rows_per_iter, ... so a warp reads whole pixels' slices back to back and
-// there is no division in the loops.  Numerics as above: fp32 sums, var = E[x^2] - mean^2 clamped at 0.
+// there is no division in the loops.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGnFusedThreads = 512;
 
-__global__ void __launch_bounds__(kGnFusedThreads) gn_fused_kernel(const __half* __restrict__ x1, int c1,
-                                                                    const __half* __restrict__ x2, int c2,
-                                                                    const float* __restrict__ gamma,
-                                                                    const float* __restrict__ beta, __half* __restrict__ y,
-                                                                    int hw, float eps, int silu) {
+__global__ void __launch_bounds__(kGnFusedThreads) gn_cluster_kernel(const __half* __restrict__ x1, int c1,
+                                                                      const __half* __restrict__ x2, int c2,
+                                                                      const float* __restrict__ gamma,
+                                                                      const float* __restrict__ beta, __half* __restrict__ y,
+                                                                      int hw, float eps, int silu) {
   __shared__ float s_warp[2][kGnFusedThreads / 32];
-  __shared__ __align__(8) float s_part[2];  // this CTA's (sum, sumsq): read by the cluster partners
+  __shared__ __align__(8) float s_part[2];  // this CTA's (S, Q): read by the cluster partners
   pdl_launch_dependents();
   const int c = c1 + c2;
   const int cg = c / 32;
@@ -180,14 +232,16 @@ __global__ void __launch_bounds__(kGnFusedThreads) gn_fused_kernel(const __half*
   const int p_end = min(hw, p_begin + per);
   const float ga0 = gamma[ch], ga1 = gamma[ch + 1], be0 = beta[ch], be1 = beta[ch + 1];  // constants: before the wait
   pdl_wait();
+  const float piv = gn_pivot(x1, c1, x2, c2, b, hw, g * cg);  // the same value in every CTA of the cluster
 
   float s = 0.f, q = 0.f;
   if (active) {
 #pragma unroll 8
     for (int pix = p_begin + r0; pix < p_end; pix += rows_per_iter) {
       const float2 f = __half22float2(*reinterpret_cast<const __half2*>(src + static_cast<long long>(pix) * pitch));
-      s += f.x + f.y;
-      q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
+      const float d0 = f.x - piv, d1 = f.y - piv;
+      s += d0 + d1;
+      q = fmaf(d0, d0, fmaf(d1, d1, q));
     }
   }
 #pragma unroll
@@ -231,8 +285,9 @@ __global__ void __launch_bounds__(kGnFusedThreads) gn_fused_kernel(const __half*
     tot_q = s_part[1];
   }
   const float inv_n = 1.0f / (static_cast<float>(cg) * hw);
-  const float mean = tot_s * inv_n;
-  const float var = fmaxf(tot_q * inv_n - mean * mean, 0.f);
+  const float ms = tot_s * inv_n;
+  const float mean = piv + ms;
+  const float var = fmaxf(fmaf(-ms, ms, tot_q * inv_n), 0.f);
   const float rstd = rsqrtf(var + eps);
   const float a0 = rstd * ga0, a1 = rstd * ga1;
   const float b0 = be0 - mean * a0, b1 = be1 - mean * a1;
@@ -295,32 +350,75 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, const float* __re
 
 using namespace mdb;
 
+// rows per stats CTA / stats grid: ~296 CTAs (2 per SM) in total, whole multiples of the row-phase count,
+// at most 8 rows per thread
+static void gn_stats_geometry(int c, int batch, int hw, int* threads_out, int* rows_per_cta_out, int* nblk_out) {
+  const int vecs = c / 8;
+  int threads = ((512 / vecs) * vecs);  // whole number of row phases
+  if (threads < vecs) threads = vecs;
+  const int rstride = threads / vecs;
+  int per = (batch * hw + 295) / 296;
+  int rows_per_cta = ((per + rstride - 1) / rstride) * rstride;
+  if (rows_per_cta > 8 * rstride) rows_per_cta = 8 * rstride;
+  if (rows_per_cta < rstride) rows_per_cta = rstride;
+  *threads_out = threads;
+  *rows_per_cta_out = rows_per_cta;
+  *nblk_out = (hw + rows_per_cta - 1) / rows_per_cta;
+}
+
+// floats of workspace mdb_groupnorm_f16 needs for the two-kernel path (0 when the call takes the single-launch
+// cluster path).  The workspace must be ZERO when first used (tickets); the kernels leave it reusable.
+extern "C" int64_t mdb_groupnorm_ws_floats(int32_t c, int32_t batch, int32_t hw) {
+  if (c <= 0 || batch <= 0 || hw <= 0 || c % 8 != 0) return 0;
+  int threads, rows_per_cta, nblk;
+  gn_stats_geometry(c, batch, hw, &threads, &rows_per_cta, &nblk);
+  return kGnMaxBatch + static_cast<int64_t>(batch) * 64 + static_cast<int64_t>(batch) * nblk * 64;
+}
+
+// single-launch cluster path: even channels per group and small enough a batch that 32 x batch x (<= 8) CTAs is
+// about two waves; mode: 0 = automatic, 1 = force the two-kernel path, 2 = force the cluster path (tests)
+static bool gn_use_cluster(int c, int c1, int c2, int batch, int mode) {
+  const bool ok = (c % 64 == 0) && (c1 % 2 == 0) && (c2 % 2 == 0) && (c / 64 <= kGnFusedThreads);
+  if (mode == 1 || !ok) return false;
+  if (mode == 2) return true;
+  return batch <= 4;
+}
+
 extern "C" int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* gamma,
-                                 const float* beta, void* y, float* stats_ws, int32_t batch, int32_t hw, float eps,
-                                 int32_t silu, int32_t stats_prezeroed, mdb_stream_t stream) {
+                                 const float* beta, void* y, float* ws, int32_t batch, int32_t hw, float eps,
+                                 int32_t silu, int32_t mode, mdb_stream_t stream) {
   const int c = c1 + (x2 ? c2 : 0);
   if (!x2) c2 = 0;
-  MDB_REQUIRE(x1 && y && gamma && beta && stats_ws, "mdb_groupnorm_f16: null pointer");
+  MDB_REQUIRE(x1 && y && gamma && beta, "mdb_groupnorm_f16: null pointer");
+  MDB_REQUIRE(batch > 0 && hw > 0 && batch <= 65535, "mdb_groupnorm_f16: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gn_use_cluster(c, c1, c2, batch, mode)) {
+    // cluster size: enough CTAs to cover the SMs about twice, at least ~64 pixels per CTA, at most 8 (portable)
+    int cs = 1;
+    while (cs < 8 && 32 * batch * cs * 2 <= 320 && hw / (cs * 2) >= 64) cs *= 2;
+    MDB_CHECK_CUDA(launch_pdl_cluster(gn_cluster_kernel, dim3(32, batch, cs), dim3(kGnFusedThreads), 0, st,
+                                      static_cast<unsigned>(cs), static_cast<const __half*>(x1), c1,
+                                      static_cast<const __half*>(x2), c2, gamma, beta, static_cast<__half*>(y), hw, eps,
+                                      silu));
+    count_launch(1);
+    return MDB_OK;
+  }
+  MDB_REQUIRE(ws != nullptr, "mdb_groupnorm_f16: the two-kernel path needs a workspace (mdb_groupnorm_ws_floats)");
   // a thread's 8-channel vector may straddle at most two groups: 8 or more channels per group, or exactly 4
   // (the first-stage VAE's 128-channel level), where every vector is exactly two whole groups
   MDB_REQUIRE(c % 32 == 0 && c1 % 8 == 0 && c2 % 8 == 0 && (c / 32 >= 8 || c / 32 == 4),
               "mdb_groupnorm_f16: channels must be multiples of 8, c %% 32 == 0 and c/32 >= 8 or == 4 (c1=%d c2=%d)", c1, c2);
   MDB_REQUIRE(c / 8 <= 512, "mdb_groupnorm_f16: too many channels (%d)", c);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!stats_prezeroed) MDB_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * batch * 64, st));
-  const int vecs = c / 8;
-  int threads = ((512 / vecs) * vecs);  // whole number of row phases
-  if (threads < vecs) threads = vecs;
-  const int rstride = threads / vecs;
-  // ~296 CTAs (2 per SM) in total, whole multiples of the row-phase count, at most 8 rows per thread
-  int per = (batch * hw + 295) / 296;
-  int rows_per_cta = ((per + rstride - 1) / rstride) * rstride;
-  if (rows_per_cta > 8 * rstride) rows_per_cta = 8 * rstride;
-  if (rows_per_cta < rstride) rows_per_cta = rstride;
-  dim3 grid((hw + rows_per_cta - 1) / rows_per_cta, batch);
-  MDB_CHECK_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), 64 * sizeof(float), st,
-                            static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2, stats_ws, hw,
-                            rows_per_cta));
+  int threads, rows_per_cta, nblk;
+  gn_stats_geometry(c, batch, hw, &threads, &rows_per_cta, &nblk);
+  const int rstride = threads / (c / 8);
+  size_t smem_stats = static_cast<size_t>(2) * rstride * c * sizeof(float);
+  if (smem_stats < 256 * sizeof(float)) smem_stats = 256 * sizeof(float);
+  MDB_REQUIRE(threads >= kGnFinalThreads && smem_stats <= 48 * 1024, "mdb_groupnorm_f16: unsupported width %d", c);
+  MDB_REQUIRE(batch <= kGnMaxBatch, "mdb_groupnorm_f16: batch %d > %d", batch, kGnMaxBatch);
+  dim3 grid(nblk, batch);
+  MDB_CHECK_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), smem_stats, st, static_cast<const __half*>(x1), c1,
+                            static_cast<const __half*>(x2), c2, ws, batch, hw, rows_per_cta));
   {
     // ~2-4 CTAs per SM; each CTA pays a c-element (scale, shift) setup, so rows per CTA grow with c
     int rows_apply = (batch * hw + 443) / 444;
@@ -330,31 +428,10 @@ extern "C" int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int
     dim3 agrid((hw + rows_apply - 1) / rows_apply, batch);
     MDB_CHECK_CUDA(launch_pdl(gn_apply_kernel, agrid, dim3(256), 2 * c * sizeof(float), st,
                               static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2, gamma, beta,
-                              static_cast<const float*>(stats_ws), static_cast<__half*>(y), hw, rows_apply, eps, silu));
+                              static_cast<const float*>(ws + kGnMaxBatch), static_cast<__half*>(y), hw, rows_apply, eps,
+                              silu));
   }
   count_launch(2);
-  return MDB_OK;
-}
-
-extern "C" int mdb_groupnorm_fused_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* gamma,
-                                       const float* beta, void* y, int32_t batch, int32_t hw, float eps, int32_t silu,
-                                       mdb_stream_t stream) {
-  const int c = c1 + (x2 ? c2 : 0);
-  if (!x2) c2 = 0;
-  MDB_REQUIRE(x1 && y && gamma && beta, "mdb_groupnorm_fused_f16: null pointer");
-  MDB_REQUIRE(c > 0 && c % 64 == 0 && c1 % 2 == 0 && c2 % 2 == 0 && c / 64 <= kGnFusedThreads,
-              "mdb_groupnorm_fused_f16: c must be a multiple of 64 (even channels per group), sources even (c1=%d c2=%d)",
-              c1, c2);
-  MDB_REQUIRE(batch > 0 && hw > 0 && batch <= 65535, "mdb_groupnorm_fused_f16: bad shape");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // cluster size: enough CTAs to cover the SMs about twice, at least ~64 pixels per CTA, at most 8 (portable)
-  int cs = 1;
-  while (cs < 8 && 32 * batch * cs * 2 <= 320 && hw / (cs * 2) >= 64) cs *= 2;
-  MDB_CHECK_CUDA(launch_pdl_cluster(gn_fused_kernel, dim3(32, batch, cs), dim3(kGnFusedThreads), 0, st,
-                                    static_cast<unsigned>(cs), static_cast<const __half*>(x1), c1,
-                                    static_cast<const __half*>(x2), c2, gamma, beta, static_cast<__half*>(y), hw, eps,
-                                    silu));
-  count_launch(1);
   return MDB_OK;
 }
 

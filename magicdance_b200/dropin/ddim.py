@@ -19,6 +19,10 @@ from ..pipeline import DenoisePipeline, ddim_parameters, ddim_timesteps_uniform
 
 
 class DDIMSampler_ReferenceOnly(object):
+    # ddim_sampling replays the captured step / bank-build CUDA graphs (pipeline.GraphedDenoiser — the code bench.py
+    # times) whenever the call is the one the MagicPose scripts make; False forces the eager per-step loop.
+    use_graphs = True
+
     def __init__(self, model, schedule="linear", **kwargs):
         super().__init__()
         self.model = model
@@ -81,7 +85,7 @@ class DDIMSampler_ReferenceOnly(object):
         img = torch.randn(shape, device=device) if x_T is None else x_T.to(device)
         intermediates = {"x_inter": [img], "pred_x0": [img]}
         total = self.ddim_timesteps.shape[0]
-        if (os.environ.get("MDB_DROPIN_GRAPH", "0") == "1" and not quantize_denoised and temperature == 1.
+        if (self.use_graphs and not quantize_denoised and temperature == 1.
                 and noise_dropout == 0. and score_corrector is None and dynamic_threshold is None and inpaint is None):
             out = self._ddim_sampling_graphed(cond, img, unconditional_guidance_scale, unconditional_conditioning,
                                               callback, img_callback, log_every_t, intermediates)
@@ -107,7 +111,7 @@ class DDIMSampler_ReferenceOnly(object):
 
     @torch.no_grad()
     def _ddim_sampling_graphed(self, c, img, scale, uc, callback, img_callback, log_every_t, intermediates):
-        """OPT-IN (MDB_DROPIN_GRAPH=1; not yet run on a GPU): the same chain as the loop above, but every step is
+        """The same chain as the loop above, but every step is
         one replay of pipeline.GraphedDenoiser's captured step graph and the appearance bank of the reference is built
         by its timestep-batched bank graph — what bench.py times — instead of ~650 eager launches per step driven from
         Python.  Returns None (the caller falls back to the eager loop) for anything the graphs do not cover: eta != 0,
@@ -120,8 +124,8 @@ class DDIMSampler_ReferenceOnly(object):
             return None
         one = lambda lst: lst[0] if len(lst) == 1 else torch.cat(lst, 1)
         ref, ctx, pose_map = one(c["image_control"]), one(c["c_crossattn"]), one(c["c_concat"])
-        if ref.shape[0] > 1 and not bool((ref[1:] == ref[:1]).all()):
-            return None  # one reference image per batch only (the scripts repeat it per sample)
+        if not (self._rows_identical(ref) and self._rows_identical(ctx)):
+            return None  # one reference image and one prompt per batch only (the scripts repeat them per sample)
         pipe = self._pipeline(scale)
         b, _, h, w = img.shape
         total = int(self.ddim_timesteps.shape[0])
@@ -129,34 +133,44 @@ class DDIMSampler_ReferenceOnly(object):
         # belong to one reference image.  The scripts build NEW tensors with the SAME content for every frame
         # (get_learned_conditioning([""] * N), the encoded reference image), so both are recognised by content
         # (torch.equal against the copy kept with the graphs), not by identity.
+        # Sequence-parallel bank: when the caller has set model.bank_process_group (all ranks of that group
+        # sample frames of the SAME reference image in lock-step, e.g. bench.py's config 4), the timesteps of the
+        # appearance pass are dealt over the ranks and exchanged once per reference (parallel.build_and_gather_bank).
+        group = getattr(self.model, "bank_process_group", None)
+        world, rank = 1, 0
+        if group is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
         graphs = self.model.__dict__.setdefault("_mdb_graphs", {})
-        gkey = (id(pipe), b, h, w, tuple(ctx.shape))
-        ctx_dev = ctx.to(pipe.device)
+        gkey = (id(pipe), b, h, w, tuple(ctx.shape), world)
+        ctx_dev = ctx[:1].to(pipe.device)  # all rows are identical (checked above): one row, broadcast in-kernel
         ent = graphs.get(gkey)
         if ent is None or not torch.equal(ent["ctx"], ctx_dev):
             graphs.clear()  # one captured configuration at a time: each owns gigabytes of graph memory
             ctx_own = ctx_dev.clone()
-            gd = GraphedDenoiser(pipe, b, (h, w), ctx_own, bank_chunk=parallel.bank_chunk_size(total, 1))
+            gd = GraphedDenoiser(pipe, b, (h, w), ctx_own, bank_chunk=parallel.bank_chunk_size(total, world))
             gd.capture()
             ent = {"gd": gd, "ctx": ctx_own, "ref": None,
-                   "slots": torch.empty((total, gd.layout.numel), dtype=torch.float16, device=pipe.device)}
+                   "storage": parallel.bank_storage((total + world - 1) // world, gd.layout, pipe.device, world)}
             graphs[gkey] = ent
         gd = ent["gd"]
         ref_dev = ref[:1].to(device=pipe.device, dtype=torch.float32)
         if ent["ref"] is None or not torch.equal(ent["ref"], ref_dev):
-            # a new reference image: one batched appearance pass per chunk of timesteps
+            # a new reference image: one batched appearance pass per chunk of (this rank's) timesteps
             order = list(range(total - 1, -1, -1))
-            ent["slot_of"] = {ix: s for s, ix in enumerate(order)}
-            for s0, part in plan_bank_chunks(order, gd.bank_chunk):
-                gd.build_bank(part, ref_dev, ent["slots"][s0:s0 + len(part)])
+            ent["bank"] = parallel.build_and_gather_bank(
+                order, gd.layout, lambda part, slots: gd.build_bank(part, ref_dev, slots), pipe.device, world, rank,
+                group=group, chunk=gd.bank_chunk, storage=ent["storage"])
             ent["ref"] = ref_dev.clone()
+        bank = ent["bank"]
         gd.hint.copy_(pipe.hint(pose_map.to(pipe.device),
                                 frame_key=(pose_map.data_ptr(), pose_map._version, tuple(pose_map.shape)),
                                 keep_alive=pose_map))
         gd.x.copy_(img.to(device=pipe.device, dtype=torch.float32))
         for i in range(total):
             index = total - i - 1
-            gd.step(index, ent["slots"][ent["slot_of"][index]])
+            bank.wait(index)
+            gd.step(index, bank[index])
             if callback:
                 callback(i)
             if img_callback:
@@ -165,6 +179,21 @@ class DDIMSampler_ReferenceOnly(object):
                 intermediates["x_inter"].append(gd.x_prev.clone())
                 intermediates["pred_x0"].append(gd.pred_x0.clone())
         return gd.x_prev.clone(), intermediates
+
+    def _rows_identical(self, t):
+        """all batch rows of t equal row 0?  One device->host sync per (tensor, version), not per DDIM step: the
+        answer is cached with a strong reference to the tensor (its address cannot be recycled meanwhile)."""
+        if t.shape[0] == 1:
+            return True
+        cache = self.model.__dict__.setdefault("_mdb_rows_identical", {})
+        key = (t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape), tuple(t.stride()), t._version)
+        hit = cache.get(key)
+        if hit is None:
+            if len(cache) >= 8:
+                cache.clear()
+            hit = (bool((t[1:] == t[:1]).all()), t)
+            cache[key] = hit
+        return hit[0]
 
     @torch.no_grad()
     def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
@@ -197,7 +226,7 @@ class DDIMSampler_ReferenceOnly(object):
             # (reference, t) only.  One reference for the whole batch (the scripts repeat it per sample) is
             # computed once and broadcast in-kernel; the result is cached per timestep for the next frames.
             src = c["image_control"][0] if len(c["image_control"]) == 1 else ref
-            shared = src.shape[0] == 1 or bool((src[1:] == src[:1]).all())
+            shared = self._rows_identical(src) and self._rows_identical(ctx)
             if shared:
                 bank_kv = pipe.reference_bank(src, ctx, index, first_only=True)
             else:

@@ -120,19 +120,24 @@ class LatentDiffusionReferenceOnly(DDPM):
         self.scale_factor = scale_factor
         self.cond_stage_forward = cond_stage_forward
         self.clip_denoised = False
+        self.__dict__["_side_errors"] = {}
         self.first_stage_model = self._side_model(first_stage_config, "first_stage_config (VAE)")
         self.cond_stage_model = self._side_model(cond_stage_config, "cond_stage_config (text encoder)")
 
-    @staticmethod
-    def _side_model(config, what):
+    def _side_model(self, config, what):
         """VAE / text encoder: off the accelerated path; built from the YAML when importable, frozen."""
         if config in ("__is_first_stage__", "__is_unconditional__") or config is None:
             return None
         try:
             model = instantiate_from_config(config)
-        except Exception as e:  # noqa: BLE001  (missing reference tree / missing HF weights / ...)
-            print(f"[magicdance_b200] {what} could not be instantiated ({type(e).__name__}: {e}); "
+        except ImportError as e:  # the class lives in a package this environment does not have (clip, open_clip, ...)
+            print(f"[magicdance_b200] {what} is not importable here ({type(e).__name__}: {e}); "
                   f"methods that need it will raise")
+            self._side_errors[what] = e
+            return None
+        except OSError as e:  # weights of a side model that would have to be downloaded (no network)
+            print(f"[magicdance_b200] {what}: {type(e).__name__}: {e}; methods that need it will raise")
+            self._side_errors[what] = e
             return None
         model = model.eval()
         for p in model.parameters():
@@ -146,8 +151,9 @@ class LatentDiffusionReferenceOnly(DDPM):
 
     def _need(self, model, what):
         if model is None:
+            cause = next((e for k, e in self._side_errors.items() if k.split("(")[-1].rstrip(")") in what), None)
             raise RuntimeError(f"{what} is not available: it is outside the accelerated hot path and is taken from "
-                               f"the reference tree (see INTEGRATION.md)")
+                               f"the reference tree (see INTEGRATION.md)") from cause
         return model
 
     @torch.no_grad()

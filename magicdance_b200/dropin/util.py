@@ -55,3 +55,23 @@ def create_model(config_path):
     model = instantiate_from_config(config.model).cpu()
     print(f"Loaded model config from [{config_path}]")
     return model
+
+
+def get_state_dict(container):
+    """a checkpoint file holds either the parameter dict itself or {'state_dict': parameter dict, ...}"""
+    inner = container.get("state_dict") if isinstance(container, dict) else None
+    return container if inner is None else inner
+
+
+def load_state_dict(ckpt_path, location="cpu"):
+    """name -> tensor of a .ckpt/.pth (torch pickle) or .safetensors checkpoint, tensors placed on `location`
+    (the signature of the reference's cldm/model.py:12-21; the released MagicPose weights are a .pth)"""
+    import torch
+    if str(ckpt_path).lower().endswith(".safetensors"):
+        from safetensors.torch import load_file
+        tensors = load_file(ckpt_path, device=location)
+    else:
+        tensors = torch.load(ckpt_path, map_location=torch.device(location))
+    tensors = get_state_dict(tensors)
+    print(f"Loaded state_dict from [{ckpt_path}]")
+    return tensors

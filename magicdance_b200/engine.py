@@ -471,7 +471,6 @@ class DenoiseEngine:
         norm1(x) token matrices [B*N_l, C_l] fp16 (attention.py:287-298).  Layers after the last
         norm1 (dead compute in the reference) are skipped."""
         net = self.appearance
-        ops.gn_ring_reset(self.device)
         x, ctx16, key = self._prep(ref_latent, context)
         ctx_kvs = self.context_kv(net, ctx16, key)
         emb_all = self.time_bias(net, t)
@@ -545,7 +544,6 @@ class DenoiseEngine:
     def controlnet(self, x_noisy, hint_feat, t, context):
         """ControlNet.forward (cldm.py:736-757) -> 13 residuals as fp16 [B*H*W, C] matrices."""
         net = self.pose
-        ops.gn_ring_reset(self.device)
         x, ctx16, key = self._prep(x_noisy, context)
         ctx_kvs = self.context_kv(net, ctx16, key)
         emb_all = self.time_bias(net, t)
@@ -572,7 +570,6 @@ class DenoiseEngine:
         layer streams its weights once and sees twice the rows; samples [0,B) read the bank and take the
         pose residuals, samples [B,2B) do neither.  Returns (eps_cond, eps_uncond)."""
         net = self.unet
-        ops.gn_ring_reset(self.device)
         x, ctx16, key = self._prep(x_noisy, context)
         b = x.b
         if cfg_pair:

@@ -119,11 +119,21 @@ def current_lane():
     return _ws_tag
 
 
-def _workspace(key, numel, dtype, device):
+_ws_retired = []  # outgrown buffers stay alive: captured CUDA graphs hold raw pointers into them
+
+
+def _workspace(key, numel, dtype, device, zero=False):
+    """Per-(key, device, lane) scratch buffer, grown geometrically.  A buffer that is outgrown is RETIRED, never
+    freed: launches captured into CUDA graphs keep its address, and a replay must not touch memory the caching
+    allocator has handed to somebody else."""
     k = (key, device, _ws_tag)
     t = _ws_cache.get(k)
     if t is None or t.numel() < numel or t.dtype != dtype:
-        t = torch.empty(max(numel, 1), dtype=dtype, device=device)
+        if t is not None:
+            _ws_retired.append(t)
+            numel = max(numel, 2 * t.numel())
+        alloc = torch.zeros if zero else torch.empty
+        t = alloc(max(numel, 1), dtype=dtype, device=device)
         _ws_cache[k] = t
     return t
 
@@ -270,50 +280,26 @@ def attention(q, k0, vt0, n0, *, heads, d, batch, nq, out=None, kv0_batches=None
     return out
 
 
-def _gn_fused_max_batch():
-    """MDB_GN_FUSED=1 (opt-in; read per call — calls are captured into graphs, so this is off the replay path):
-    the single-launch GroupNorm for batches up to MDB_GN_FUSED_MAX_BATCH (default 4 = cond+uncond of two frames)"""
-    if os.environ.get("MDB_GN_FUSED", "0") != "1":
-        return 0
-    return int(os.environ.get("MDB_GN_FUSED_MAX_BATCH", "4"))
+GN_AUTO, GN_TWO_KERNELS, GN_CLUSTER = 0, 1, 2  # mdb_groupnorm_f16 `mode`
+GN_DEFAULT_MODE = GN_AUTO
 
 
-GN_RING_SLOTS = 160     # >= GroupNorm calls of one network pass (61) with margin
-GN_RING_MAX_BATCH = 64
-_gn_ring_pos = {}
-
-
-def gn_ring_reset(device):
-    """Clears this lane's ring of GroupNorm statistics slots (one small fill per network pass); every
-    groupnorm() call then takes a fresh, already-zero slot instead of issuing its own memset."""
-    ring = _workspace("gnring", GN_RING_SLOTS * GN_RING_MAX_BATCH * 64, torch.float32, device)
-    ring.zero_()
-    _gn_ring_pos[(device, _ws_tag)] = 0
-
-
-def groupnorm(x1, gamma, beta, *, batch, hw, eps, silu, x2=None, out=None):
+def groupnorm(x1, gamma, beta, *, batch, hw, eps, silu, x2=None, out=None, mode=None):
+    """GroupNorm(32) [+SiLU] over [x1 | x2] channels; deterministic, pivot-shifted statistics (csrc/norm.cu)."""
     lib = _lib.load()
     _chk(x1, torch.float16, "x1")
+    mode = GN_DEFAULT_MODE if mode is None else mode
     c1 = x1.shape[-1]
     c2 = 0 if x2 is None else x2.shape[-1]
     assert x1.is_contiguous() and (x2 is None or x2.is_contiguous())
     if out is None:
         out = torch.empty((batch * hw, c1 + c2), dtype=torch.float16, device=x1.device)
-    if batch <= _gn_fused_max_batch() and (c1 + c2) % 64 == 0:
-        # opt-in (MDB_GN_FUSED=1), not yet run on a GPU: one launch instead of stats -> apply for small batches
-        _lib.check(lib.mdb_groupnorm_fused_f16(x1.data_ptr(), c1, _ptr(x2), c2, gamma.data_ptr(), beta.data_ptr(),
-                                               out.data_ptr(), batch, hw, eps, int(silu), _stream()), "groupnorm_fused_f16")
-        return out
-    key = (x1.device, _ws_tag)
-    pos = _gn_ring_pos.get(key)
-    if pos is not None and pos < GN_RING_SLOTS and batch <= GN_RING_MAX_BATCH:
-        ring = _workspace("gnring", GN_RING_SLOTS * GN_RING_MAX_BATCH * 64, torch.float32, x1.device)
-        stats_ptr, prezeroed = ring.data_ptr() + pos * GN_RING_MAX_BATCH * 64 * 4, 1
-        _gn_ring_pos[key] = pos + 1
-    else:
-        stats_ptr, prezeroed = _workspace("gnstats", batch * 64, torch.float32, x1.device).data_ptr(), 0
+    # workspace of the two-kernel path (tickets must be zero at first use: _workspace(zero=True)); the single-launch
+    # cluster path ignores it
+    need = int(lib.mdb_groupnorm_ws_floats(c1 + c2, batch, hw))
+    ws = _workspace("gn", need, torch.float32, x1.device, zero=True)
     _lib.check(lib.mdb_groupnorm_f16(x1.data_ptr(), c1, _ptr(x2), c2, gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
-                                     stats_ptr, batch, hw, eps, int(silu), prezeroed, _stream()), "groupnorm_f16")
+                                     ws.data_ptr(), batch, hw, eps, int(silu), int(mode), _stream()), "groupnorm_f16")
     return out
 
 

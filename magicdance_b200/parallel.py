@@ -58,9 +58,10 @@ class BankLayout:
 
 
 def bank_storage(slots: int, layout: BankLayout, device, world: int = 1):
-    """(local [slots, numel], gathered [world, slots, numel] or None) fp16 buffers for build_and_gather_bank"""
+    """(local [slots, numel], gathered [slots, world, numel] or None) fp16 buffers for build_and_gather_bank: row s of
+    `gathered` is the contiguous destination of the all-gather of every rank's slot s"""
     local = torch.zeros((slots, layout.numel), dtype=torch.float16, device=device)
-    gathered = torch.empty((world, slots, layout.numel), dtype=torch.float16, device=device) if world > 1 else None
+    gathered = torch.empty((slots, world, layout.numel), dtype=torch.float16, device=device) if world > 1 else None
     return local, gathered
 
 
@@ -73,25 +74,78 @@ def bank_chunk_size(n_timesteps: int, world: int, max_chunk: int = 25) -> int:
     n_chunks = (per_rank + max_chunk - 1) // max_chunk
     return (per_rank + n_chunks - 1) // n_chunks
 
+class GatheredBank:
+    """ddim index -> flat fp16 bank buffer, plus the handles of the exchange that fills it.
+
+    The timesteps are dealt round-robin in CONSUMPTION order, so slot s of every rank together holds the timesteps
+    the steps s*world ... (s+1)*world-1 need: the exchange is issued as one all-gather PER SLOT ROW, in that order,
+    and a step only waits for its own row (`wait(index)`); the remaining rows travel over NVLink while the first
+    steps already run.  `dict`-like for the callers that only need index -> buffer."""
+
+    def __init__(self, table, works=None, slot_of=None):
+        self.table, self.works, self.slot_of = table, works or {}, slot_of or {}
+        self._waited = set()
+
+    def __getitem__(self, ix):
+        return self.table[ix]
+
+    def __iter__(self):
+        return iter(self.table)
+
+    def __len__(self):
+        return len(self.table)
+
+    def items(self):
+        return self.table.items()
+
+    def wait(self, ix=None):
+        """make the CURRENT stream wait for the gather that delivers ddim index ix (all of them if None)"""
+        slots = list(self.works) if ix is None else [self.slot_of.get(ix)]
+        for s_ in slots:
+            if s_ is not None and s_ in self.works and s_ not in self._waited:
+                self.works[s_].wait()
+                self._waited.add(s_)
+
+
 def build_and_gather_bank(indices: Sequence[int], layout: BankLayout,
                           build_fn: Callable[[List[int], torch.Tensor], None], device, world: int = 1, rank: int = 0,
-                          group=None, chunk: int = 10, storage=None) -> Dict[int, torch.Tensor]:
+                          group=None, chunk: int = 10, storage=None, timing=None) -> GatheredBank:
     """Each rank calls build_fn(ddim_indices_chunk, slots[len(chunk), numel]) for its share of `indices`
     (build_fn fills the flat fp16 slots in place; chunks of up to `chunk` timesteps are built as ONE
-    batched appearance pass), then ONE all_gather_into_tensor exchanges all slots.  Returns
-    ddim index -> flat buffer (a view into the gathered storage)."""
+    batched appearance pass), then the slots are exchanged: one all_gather_into_tensor per slot row, issued
+    asynchronously in consumption order (see GatheredBank).  Returns ddim index -> flat buffer (views into the
+    gathered storage); call .wait(index) before reading one.  timing: optional dict that receives CUDA events
+    ('build0', 'build1', 'gather1') recorded on the current stream around the two phases."""
     mine = shard_timesteps(indices, world, rank)
     slots = (len(indices) + world - 1) // world
     if storage is not None:  # (local, gathered) preallocated by bank_storage(): keeps cudaMalloc out of timed regions
-        local, gathered = storage[0][:slots], (storage[1][:, :slots] if storage[1] is not None else None)
-        assert local.is_contiguous() or slots == storage[0].shape[0]
+        if storage[0].shape[0] != slots:
+            raise ValueError(f"bank storage holds {storage[0].shape[0]} slots per rank, this exchange needs {slots}: "
+                             "allocate it with bank_storage(slots, ...) for the sequence length at hand")
+        local, gathered = storage
     else:
         local, gathered = bank_storage(slots, layout, device, world)
+    ev = (lambda: None)
+    if timing is not None and torch.device(device).type == "cuda":
+        def ev(name=None):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+        timing["build0"] = ev()
     for s0 in range(0, len(mine), chunk):
         part = mine[s0:s0 + chunk]
         build_fn(part, local[s0:s0 + len(part)])
+    if timing is not None and "build0" in timing:
+        timing["build1"] = ev()
     if world == 1:
-        return {ix: local[s] for s, ix in enumerate(mine)}
-    dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=group)
+        return GatheredBank({ix: local[s] for s, ix in enumerate(mine)})
     table = owner_slot(indices, world)
-    return {ix: gathered[r, s] for ix, (r, s) in table.items()}
+    flat_of = {ix: gathered[s, r] for ix, (r, s) in table.items()}
+    slot_of = {ix: s for ix, (r, s) in table.items()}
+    works = {}
+    for s in range(slots):
+        works[s] = dist.all_gather_into_tensor(gathered[s].view(-1), local[s], group=group, async_op=True)
+    gb = GatheredBank(flat_of, works, slot_of)
+    if timing is not None and "build0" in timing:
+        timing["bank"] = gb
+    return gb

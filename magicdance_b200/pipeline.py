@@ -71,26 +71,36 @@ class DenoisePipeline:
         self.t_dev = torch.from_numpy(self.timesteps.astype(np.int64)).to(self.device)
 
     # ---- per-sequence / per-frame preparation --------------------------------------------------
+    @staticmethod
+    def _ident(t):
+        """identity of a tensor's contents as far as the host can tell without a device sync: storage address, view
+        geometry and the in-place version counter (cache entries also hold a strong reference to the tensor, so the
+        address cannot be recycled while the entry lives)"""
+        return (t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape), tuple(t.stride()), t._version)
+
     def reference_bank(self, ref_latent, context, index, first_only=False):
         """Bank K/V for ddim index `index` (appearance 'write' pass + projection), cached per
-        (reference tensor, index).  first_only: all rows of ref_latent are the same image; compute row 0."""
-        key = (ref_latent.data_ptr(), ref_latent._version, int(index))
-        if self._bank_cache and next(iter(self._bank_cache))[:2] != key[:2]:
-            self._bank_cache.clear()  # a new reference image: drop the previous sequence's banks (2.3 GB)
-            self._bank_ref = None
-        self._bank_ref = ref_latent  # keep the tensor alive so its address cannot be recycled under the cache
-        hit = self._bank_cache.get(key)
+        (reference tensor, CONTEXT tensor, index): the appearance net runs with the prompt's context
+        (cldm.py:1110), so a new prompt with the same reference image needs a new bank.
+        first_only: all rows of ref_latent AND of context are the same; compute row 0 and broadcast."""
+        seq = (self._ident(ref_latent), self._ident(context), bool(first_only))
+        if getattr(self, "_bank_seq", None) != seq:
+            self._bank_cache.clear()  # a new reference image or prompt: drop the previous sequence's banks (2.3 GB)
+            self._bank_seq = seq
+            self._bank_keep = (ref_latent, context)  # keep both alive: their addresses key the cache
+        hit = self._bank_cache.get(int(index))
         if hit is None:
             src = ref_latent[:1].contiguous() if first_only else ref_latent
             rb = src.shape[0]
             t = self.t_dev[index].expand(rb).contiguous()
             bank = self.engine.appearance_write(src, t, context[:rb])
             hit = self.engine.project_bank(bank, rb)
-            self._bank_cache[key] = hit
+            self._bank_cache[int(index)] = hit
         return hit
 
     def clear_caches(self):
         self._bank_cache.clear()
+        self._bank_seq = self._bank_keep = None
         self._hint_cache.clear()
 
     HINT_CACHE_FRAMES = 8
@@ -204,8 +214,11 @@ class GraphedDenoiser:
         self.bank_stream = torch.cuda.Stream(device=dev) if self.overlap else None
         # auxiliary streams for independent branches inside a block (engine._fork): lane 0 (UNet pass) -> lane 2,
         # lane 1 (ControlNet pass on the side stream) -> lane 3
+        # (kept on THIS object and handed to the engine only for the duration of _step_body: eager calls through the
+        # same engine must not inherit the fork/join path and its scratch lanes)
+        self.aux_streams = None
         if os.environ.get("MDB_AUX_STREAMS", "1") != "0" and batch <= 2:
-            self.eng.aux_streams = {0: (torch.cuda.Stream(device=dev), 2), 1: (torch.cuda.Stream(device=dev), 3)}
+            self.aux_streams = {0: (torch.cuda.Stream(device=dev), 2), 1: (torch.cuda.Stream(device=dev), 3)}
         # run-ahead L2 weight prefetch (one prefetcher per concurrently running network pass)
         # (measured on B200: no gain at one frame per GPU — 9.06 vs 8.94 ms/step — so it is opt-in: MDB_PREFETCH=1)
         if os.environ.get("MDB_PREFETCH", "0") == "1":
@@ -222,6 +235,13 @@ class GraphedDenoiser:
         kernels fills only part of the 148 SMs, so the ControlNet runs on a second stream (forked and
         joined with events, captured into the same graph) with its own scratch buffers."""
         eng, b = self.eng, self.batch
+        prev_aux, eng.aux_streams = eng.aux_streams, self.aux_streams
+        try:
+            self._step_body_inner(eng, b)
+        finally:
+            eng.aux_streams = prev_aux
+
+    def _step_body_inner(self, eng, b):
         t = self.t_cur.expand(b).contiguous()
         bank_kv = self.layout.views(self.bank_cur, self.tokens, 1)
         main = torch.cuda.current_stream()
@@ -286,6 +306,9 @@ class GraphedDenoiser:
         torch.cuda.synchronize()
         # kernels of OUR library inside each graph (the C ABI counts launches at capture time only)
         self.bank_launches, self.step_launches = n1 - n0, ops.launch_count() - n1
+        # The graphs hold raw pointers to the text K/V of this context (engine._ctx_cache evicts) — keep those
+        # tensors alive for as long as the graphs are; scratch workspaces are never freed (ops._workspace retires).
+        self._pinned = list(self.eng._ctx_cache.values())
         return self
 
     # ---- replay helpers ---------------------------------------------------------------------------

@@ -1,22 +1,5 @@
-"""model_lib.ControlNet.cldm.model (reference: cldm/model.py:7-28): create_model / load_state_dict."""
-import os
-
-import torch
-
-from magicdance_b200.dropin.util import create_model, instantiate_from_config  # noqa: F401
-
-
-def get_state_dict(d):
-    return d.get("state_dict", d)
-
-
-def load_state_dict(ckpt_path, location="cpu"):
-    _, extension = os.path.splitext(ckpt_path)
-    if extension.lower() == ".safetensors":
-        import safetensors.torch
-        state_dict = safetensors.torch.load_file(ckpt_path, device=location)
-    else:
-        state_dict = get_state_dict(torch.load(ckpt_path, map_location=torch.device(location)))
-    state_dict = get_state_dict(state_dict)
-    print(f"Loaded state_dict from [{ckpt_path}]")
-    return state_dict
+"""model_lib.ControlNet.cldm.model — the import path the MagicPose scripts use (test_tiktok.py:39) for
+create_model / load_state_dict / get_state_dict.  Interface of the reference's cldm/model.py:7-28; the checkpoint
+readers here are this repo's own (magicdance_b200.dropin.util)."""
+from magicdance_b200.dropin.util import (create_model, get_state_dict, instantiate_from_config,  # noqa: F401
+                                         load_state_dict)

@@ -94,7 +94,7 @@ def conv3x3_direct(x, wt, bias, *, batch, h, w, cin, cout, stride=1, silu=False,
     return _h(y)
 
 
-def groupnorm(x1, gamma, beta, *, batch, hw, eps, silu, x2=None, out=None):
+def groupnorm(x1, gamma, beta, *, batch, hw, eps, silu, x2=None, out=None, mode=0):
     assert x1.dtype == torch.float16 and gamma.dtype == torch.float32
     if x2 is not None:  # fused channel concat (cldm.py:104)
         x1 = torch.cat([x1, x2], dim=1)
@@ -170,10 +170,6 @@ def skinny_linear(x, w, bias, *, silu_in=False, silu_out=False):
 
 
 def ensure_device():
-    return None
-
-
-def gn_ring_reset(device):
     return None
 
 

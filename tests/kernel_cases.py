@@ -185,20 +185,27 @@ def case_upsample(batch, h, w, c, seed=0):
     return rel(out.float(), ref), 0.0, f"upsample2x B={batch} {h}x{w} c={c}"
 
 
-def case_groupnorm(batch, hw, c1, c2, eps, silu, seed=0):
-    x1 = _rand(batch * hw, c1, seed=seed).half() * 1.5 + 0.3
-    x2 = (_rand(batch * hw, c2, seed=seed + 1).half() - 0.2) if c2 else None
+def case_groupnorm(batch, hw, c1, c2, eps, silu, mode=None, offset=0.3, seed=0):
+    """mode: 0 auto, 1 two kernels (stats + last-CTA fold -> apply), 2 single-launch cluster kernel.
+    offset: mean of the activations — a large value against a spread of ~1 is the catastrophic-cancellation case of
+    E[x^2] - mean^2 that the pivot-shifted sums avoid.  Also checks run-to-run bit-equality (no atomics)."""
+    x1 = (_rand(batch * hw, c1, seed=seed) * 1.5 + offset).half()
+    x2 = (_rand(batch * hw, c2, seed=seed + 1) - 0.2 + offset).half() if c2 else None
     c = c1 + c2
     g = (1 + 0.1 * _rand(c, seed=seed + 2)).float()
     b = (0.1 * _rand(c, seed=seed + 3)).float()
-    out = ops.groupnorm(x1, g, b, batch=batch, hw=hw, eps=eps, silu=silu, x2=x2)
+    out = ops.groupnorm(x1, g, b, batch=batch, hw=hw, eps=eps, silu=silu, x2=x2, mode=mode)
+    again = ops.groupnorm(x1, g, b, batch=batch, hw=hw, eps=eps, silu=silu, x2=x2, mode=mode)
     xc = x1 if x2 is None else torch.cat([x1, x2], 1)
-    xr = xc.float().reshape(batch, hw, c).permute(0, 2, 1)
-    ref = F.group_norm(xr, 32, g, b, eps)
+    xr = xc.double().reshape(batch, hw, c).permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, g.double(), b.double(), eps)
     if silu:
         ref = F.silu(ref)
     ref = ref.permute(0, 2, 1).reshape(batch * hw, c)
-    return rel(out.float(), ref), 2e-3, f"groupnorm B={batch} hw={hw} c={c1}+{c2} silu={silu}"
+    err = rel(out.float(), ref)
+    if not torch.equal(out, again):
+        err = float("inf")  # non-deterministic
+    return err, 2e-3, f"groupnorm B={batch} hw={hw} c={c1}+{c2} silu={silu} mode={mode} offset={offset}"
 
 
 def case_layernorm(rows, c, seed=0):
@@ -304,11 +311,26 @@ ALL_CASES = [
     (case_layernorm, (4096, 320)),
     (case_layernorm, (300, 640)),
     (case_layernorm, (64, 1280)),
-    (case_groupnorm, (2, 4096, 320, 0, 1e-5, True)),
-    (case_groupnorm, (1, 1024, 640, 320, 1e-5, True)),
-    (case_groupnorm, (2, 64, 1280, 1280, 1e-5, True)),
+    (case_groupnorm, (2, 4096, 320, 0, 1e-5, True)),                 # auto: cluster of 4, 5 words per pixel
+    (case_groupnorm, (1, 1024, 640, 320, 1e-5, True)),               # concat: groups straddle the two sources
+    (case_groupnorm, (2, 64, 1280, 1280, 1e-5, True)),               # 8x8 level: one CTA per group
     (case_groupnorm, (2, 256, 1280, 0, 1e-6, False)),
     (case_groupnorm, (1, 16, 1280, 640, 1e-5, True)),
+    (case_groupnorm, (2, 4096, 640, 320, 1e-5, True)),               # 960 channels at 64x64: the largest slice
+    (case_groupnorm, (4, 1000, 320, 0, 1e-5, True)),                 # pixel count not a multiple of anything
+    (case_groupnorm, (2, 4096, 320, 0, 1e-5, True, None, 40.0)),     # mean 40, spread 1.5: pivot-shifted variance
+    (case_groupnorm, (16, 4096, 320, 0, 1e-5, True)),                # eight frames (cond+uncond): two-kernel path
+    (case_groupnorm, (16, 1024, 1280, 640, 1e-5, True)),
+    (case_groupnorm, (25, 256, 1280, 0, 1e-6, False)),               # bank build: 25 timesteps
+    (case_groupnorm, (16, 64, 1280, 1280, 1e-5, True)),
+    (case_groupnorm, (2, 4096, 320, 0, 1e-5, True, 1)),              # two-kernel path forced on small batches
+    (case_groupnorm, (1, 1024, 640, 320, 1e-5, True, 1)),
+    (case_groupnorm, (1, 16, 1280, 640, 1e-5, True, 1)),
+    (case_groupnorm, (3, 1000, 320, 0, 1e-5, True, 1)),
+    (case_groupnorm, (2, 4096, 128, 0, 1e-6, True, 1)),              # VAE: 4 channels per group
+    (case_groupnorm, (8, 4096, 320, 0, 1e-5, True, 1, 40.0)),        # large mean on the two-kernel path
+    (case_groupnorm, (16, 1024, 640, 0, 1e-5, True, 2)),             # cluster path forced on a large batch
+    (case_groupnorm, (2, 16384, 128, 0, 1e-6, True, 2)),             # VAE widths on the cluster path
     (case_gemm, (128, 128, 64)),
     (case_gemm, (128, 160, 128)),
     (case_gemm, (4096, 320, 320, True, True)),
@@ -378,7 +400,6 @@ ALL_CASES = [
 _PAIRQ = (("MDB_GEMM_PAIR", "3"), ("MDB_GEMM_PAIR_MIN", "1"))     # persistent pair GEMM, TMA-store epilogue
 _PAIRS = (("MDB_GEMM_PAIR_SPLITK", "1"), ("MDB_GEMM_PAIR_SPLITK_MINK", "1"))                         # pair tiles + split-K inside the cluster
 _TMAST = (("MDB_GEMM_TMAST", "1"),)                              # default tiles, TMA-store epilogue (gemm_ts_kernel)
-_GNF = (("MDB_GN_FUSED", "1"),)                                   # single-launch GroupNorm (cluster per batch x group)
 PENDING_CASES = [
     (case_env, (_TMAST, case_gemm, 8192, 320, 320, True, True)),          # 160-wide tiles, K = 5 chunks
     (case_env, (_TMAST, case_gemm, 16384, 640, 640, True, True)),
@@ -390,13 +411,6 @@ PENDING_CASES = [
     (case_env, (_TMAST, case_geglu, 4096, 320)),
     (case_env, (_TMAST, case_geglu, 64, 1280)),
     (case_env, (_TMAST, case_conv, 8, 32, 32, 640, 640, True, True)),
-    (case_env, (_GNF, case_groupnorm, 2, 4096, 320, 0, 1e-5, True)),      # cluster of 4, 5 words per pixel
-    (case_env, (_GNF, case_groupnorm, 1, 1024, 640, 320, 1e-5, True)),    # concat: groups straddle the two sources
-    (case_env, (_GNF, case_groupnorm, 2, 64, 1280, 1280, 1e-5, True)),    # 8x8 level: one CTA per group
-    (case_env, (_GNF, case_groupnorm, 2, 256, 1280, 0, 1e-6, False)),
-    (case_env, (_GNF, case_groupnorm, 1, 16, 1280, 640, 1e-5, True)),
-    (case_env, (_GNF, case_groupnorm, 2, 4096, 640, 320, 1e-5, True)),    # 960 channels at 64x64: the largest slice
-    (case_env, (_GNF, case_groupnorm, 4, 1000, 320, 0, 1e-5, True)),      # pixel count not a multiple of anything
     (case_env, (_PAIRQ, case_gemm, 512, 256, 128)),                       # 256-wide tile, 2 pairs, one K pass of 2 chunks
     (case_env, (_PAIRQ, case_gemm, 384, 320, 320, True, True)),           # odd M tiles: last pair half empty; bias+residual
     (case_env, (_PAIRQ, case_gemm, 1000, 640, 1280, True, False)),        # ragged M (TMA store clips rows)

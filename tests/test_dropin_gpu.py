@@ -94,8 +94,7 @@ def test_sample_log_runs_the_chain_and_reuses_the_bank(model):
     n2 = ops.launch_count()
     model.image_size = 64
     assert s1.shape == (1, 4, 32, 32) and torch.isfinite(s1).all() and "pred_x0" in inter
-    # GroupNorm statistics are summed with fp32 atomics (order varies run to run) and a 4-step chain with
-    # CFG 7 amplifies the resulting fp16 rounding flips; the two frames must agree to well under 1 %
-    from tests import golden_util as G
-    assert G.rel_l2(s1, s2) < 5e-3
+    # nothing on the path uses atomics on data (GroupNorm reduces in a fixed order): the second frame, which reuses
+    # the bank of the first, must reproduce it bit for bit
+    assert torch.equal(s1, s2)
     assert (n2 - n1) < 0.8 * (n1 - n0)  # second frame skipped the 4 appearance passes + text K/V

@@ -17,7 +17,7 @@ TOL = 5e-3  # fp16 storage (emulated by the stand-ins) vs the fp32 reference
 
 _PATCHED = ("gemm", "attention", "conv3x3_direct", "groupnorm", "layernorm", "upsample2x", "add", "im2col3x3",
             "timestep_embedding", "skinny_linear", "nchw_f32_to_nhwc_f16", "nhwc_f16_to_nchw_f32", "softmax_rows",
-            "ensure_device", "gn_ring_reset", "require_cuda")
+            "ensure_device", "require_cuda")
 
 
 @pytest.fixture(scope="module")

@@ -36,6 +36,9 @@ def _worker(rank, world, port, q):
 
     indices = list(range(9, -1, -1))  # 10 timesteps over 2 ranks
     table = P.build_and_gather_bank(indices, layout, build_fn, "cpu", world, rank, chunk=3)
+    # one asynchronous all-gather per slot row, in consumption order: a step waits for its own row only
+    for ix in indices:
+        table.wait(ix)
     ok = sorted(table) == list(range(10)) and built == P.shard_timesteps(indices, world, rank)
     for ix, flat in table.items():
         for li, (k, vt, n, b) in enumerate(layout.views(flat, [16, 4], 1)):

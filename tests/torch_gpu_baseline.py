@@ -28,7 +28,7 @@ sys.path.insert(0, REPO)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--batch", default="1", help="frames per step; a comma list runs several in one process")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--latent", type=int, default=64)
@@ -66,51 +66,57 @@ def main():
         R.attention = sdpa_attention
 
     sd = synth.synth_state_dict(seed=0, device=dev)
-    B, L = args.batch, args.latent
-    inp = {k: v.to(dev) for k, v in synth.synth_inputs(B, L, seed=0, shared_reference=True).items()}
+    L = args.latent
     sched = R.ddim_schedule(R.make_schedule()["alphas_cumprod"].astype(np.float32).astype(np.float64))
     dtype = getattr(torch, args.dtype)
-    ctx = torch.autocast("cuda" if on_gpu else "cpu", dtype=dtype if on_gpu or dtype != torch.float16 else torch.bfloat16,
-                         enabled=dtype != torch.float32)
+    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
 
-    def step(x, index, bank_cache):
-        t = torch.full((B,), int(sched["timesteps"][index]), dtype=torch.long, device=dev)
-        if not args.algorithmic:
-            x_prev, _, _, _ = R.p_sample_ddim(sd, x, t, index, inp["context"], inp["pose"], inp["ref"], sched, scale=7.0)
-            return x_prev.float()
-        bank = bank_cache[index]
-        pose = R.controlnet_forward(sd, R.POSE, x, inp["pose"], t, inp["context"])
-        e_c = R.unet_forward(sd, R.UNET, x, t, inp["context"], bank=bank, pose_control=pose, uc=False)
-        e_u = R.unet_forward(sd, R.UNET, x, t, inp["context"], bank=[], pose_control=None, uc=True)
-        e_t = e_u + 7.0 * (e_c - e_u)
-        return R.ddim_update(x, e_t.float(), index, sched)[0].float()
+    def one(B):
+        inp = {k: v.to(dev) for k, v in synth.synth_inputs(B, L, seed=0, shared_reference=True).items()}
+        ctx = torch.autocast("cuda" if on_gpu else "cpu", dtype=dtype if on_gpu or dtype != torch.float16 else torch.bfloat16,
+                             enabled=dtype != torch.float32)
 
-    n = args.warmup + args.steps
-    idxs = [49 - (i % 50) for i in range(n)]
-    bank_cache = {}
-    with ctx:
-        if args.algorithmic:
-            for ix in sorted(set(idxs)):
-                t = torch.full((B,), int(sched["timesteps"][ix]), dtype=torch.long, device=dev)
-                bank_cache[ix] = R.appearance_forward(sd, R.APPEARANCE, inp["ref"], t, inp["context"])
-        x = inp["x"]
-        sync = torch.cuda.synchronize if on_gpu else (lambda: None)
-        t_start = 0.0
-        for i, ix in enumerate(idxs):
-            if i == args.warmup:
-                sync()
-                t_start = time.perf_counter()   # whole-chain wall clock between two device synchronisations
-            x = step(x, ix, bank_cache)
-        sync()
-    sec = (time.perf_counter() - t_start) / args.steps
-    gf = 2037.9 if args.algorithmic else 3124.4
-    print(json.dumps({
-        "impl": "torch-eager-gpu (oracle restatement under autocast; cuDNN/cuBLAS" + ("" if args.no_sdpa else "/SDPA") + ")",
-        "metric": "denoise-steps/sec @512x512 50-step DDIM", "value": B / sec, "unit": "frame-steps/s",
-        "ms_per_step": sec * 1e3, "steps": args.steps, "warmup": args.warmup, "dtype": args.dtype,
-        "work": "algorithmic (bank prebuilt, no discarded pose pass)" if args.algorithmic else "as executed by the reference",
-        "gflop_per_frame_step": gf, "tflops": gf * B / sec / 1e3, "frames": B, "latent": L,
-        "finite": bool(torch.isfinite(x).all()), "device": torch.cuda.get_device_name(0) if on_gpu else "cpu"}))
+        def step(x, index, bank_cache):
+            t = torch.full((B,), int(sched["timesteps"][index]), dtype=torch.long, device=dev)
+            if not args.algorithmic:
+                x_prev, _, _, _ = R.p_sample_ddim(sd, x, t, index, inp["context"], inp["pose"], inp["ref"], sched, scale=7.0)
+                return x_prev.float()
+            bank = bank_cache[index]
+            pose = R.controlnet_forward(sd, R.POSE, x, inp["pose"], t, inp["context"])
+            e_c = R.unet_forward(sd, R.UNET, x, t, inp["context"], bank=bank, pose_control=pose, uc=False)
+            e_u = R.unet_forward(sd, R.UNET, x, t, inp["context"], bank=[], pose_control=None, uc=True)
+            e_t = e_u + 7.0 * (e_c - e_u)
+            return R.ddim_update(x, e_t.float(), index, sched)[0].float()
+
+        n = args.warmup + args.steps
+        idxs = [49 - (i % 50) for i in range(n)]
+        bank_cache = {}
+        with ctx:
+            if args.algorithmic:
+                for ix in sorted(set(idxs)):
+                    t = torch.full((B,), int(sched["timesteps"][ix]), dtype=torch.long, device=dev)
+                    bank_cache[ix] = R.appearance_forward(sd, R.APPEARANCE, inp["ref"], t, inp["context"])
+            x = inp["x"]
+            t_start = 0.0
+            for i, ix in enumerate(idxs):
+                if i == args.warmup:
+                    sync()
+                    t_start = time.perf_counter()   # whole-chain wall clock between two device synchronisations
+                x = step(x, ix, bank_cache)
+            sync()
+        sec = (time.perf_counter() - t_start) / args.steps
+        gf = 2037.9 if args.algorithmic else 3124.4
+        return {
+            "impl": "torch-eager-gpu (oracle restatement under autocast; cuDNN/cuBLAS" + ("" if args.no_sdpa else "/SDPA") + ")",
+            "metric": "denoise-steps/sec @512x512 50-step DDIM", "value": B / sec, "unit": "frame-steps/s",
+            "ms_per_step": sec * 1e3, "steps": args.steps, "warmup": args.warmup, "dtype": args.dtype,
+            "work": "algorithmic (bank prebuilt, no discarded pose pass)" if args.algorithmic else "as executed by the reference",
+            "gflop_per_frame_step": gf, "tflops": gf * B / sec / 1e3, "frames": B, "latent": L,
+            "finite": bool(torch.isfinite(x).all()), "device": torch.cuda.get_device_name(0) if on_gpu else "cpu"}
+
+    batches = [int(v) for v in str(args.batch).split(",")]
+    res = [one(B) for B in batches]
+    print(json.dumps(res[0] if len(res) == 1 else {"runs": res}))
 
 
 if __name__ == "__main__":
