@@ -182,7 +182,8 @@ class GraphedDenoiser:
     memory refreshed by tiny copies before each replay (the timestep, the DDIM coefficient row, the
     bank K/V of that timestep), so ONE graph serves every step."""
 
-    def __init__(self, pipe: DenoisePipeline, batch: int, latent_hw, context: torch.Tensor, bank_chunk: int = 10):
+    def __init__(self, pipe: DenoisePipeline, batch: int, latent_hw, context: torch.Tensor, bank_chunk: int = 10,
+                 overlap_bank: bool = False):
         from . import parallel
         self.pipe, self.eng = pipe, pipe.engine
         eng, dev = self.eng, pipe.device
@@ -206,11 +207,11 @@ class GraphedDenoiser:
         self.replayed_launches = 0
         import os
         self.side = torch.cuda.Stream(device=dev) if os.environ.get("MDB_DUAL_STREAM", "1") != "0" else None
-        # Opt-in (MDB_BANK_OVERLAP=1; the stream plumbing below has not run on a GPU yet): build the appearance bank
-        # on its own stream WHILE the first DDIM steps run — a step only needs the bank of its own timestep, and at one
-        # frame per GPU the step's ~650 small kernels leave most of the tensor pipe idle.  The bank graph then owns
-        # its scratch lane and its memory pool (two graphs that replay concurrently must not share either).
-        self.overlap = os.environ.get("MDB_BANK_OVERLAP", "0") == "1"
+        # overlap_bank: build the appearance bank on its own stream WHILE the first DDIM steps run — a step only needs
+        # the bank of its own timestep, and at one frame per GPU the step's small kernels leave most of the tensor pipe
+        # idle.  The bank graph then owns its scratch lane and its memory pool (two graphs that replay concurrently
+        # must not share either).
+        self.overlap = bool(overlap_bank)
         self.bank_stream = torch.cuda.Stream(device=dev) if self.overlap else None
         # auxiliary streams for independent branches inside a block (engine._fork): lane 0 (UNet pass) -> lane 2,
         # lane 1 (ControlNet pass on the side stream) -> lane 3
@@ -322,23 +323,6 @@ class GraphedDenoiser:
         self.g_bank.replay()
         self.replayed_launches += self.bank_launches
         out_slots.copy_(self.bank_built[:n])
-
-    def build_bank_overlapped(self, indices, ref_latent, out_slots):
-        """Like build_bank for a whole sequence, but on the bank stream and chunk by chunk in the order the steps
-        will need them: returns {ddim index: (flat slot, event)}; a step waits for its own event only
-        (step(..., ready=event)), so denoising starts as soon as the first chunk exists."""
-        assert self.overlap, "construct the GraphedDenoiser with MDB_BANK_OVERLAP=1"
-        main, bs = torch.cuda.current_stream(), self.bank_stream
-        bs.wait_stream(main)  # the reference latent is uploaded; earlier readers of out_slots have been issued
-        table = {}
-        with torch.cuda.stream(bs):
-            for s0, part in plan_bank_chunks(indices, self.bank_chunk):
-                self.build_bank(part, ref_latent, out_slots[s0:s0 + len(part)])
-                ev = torch.cuda.Event()
-                ev.record(bs)
-                for j, ix in enumerate(part):
-                    table[ix] = (out_slots[s0 + j], ev)
-        return table
 
     def step(self, index, bank_flat, ready=None):
         """one DDIM step on self.x in place (result also in self.x_prev / self.pred_x0); `ready`: event after which

@@ -102,7 +102,7 @@ def case_gemm_strided_out(m, n, k, seed=0):
     buf = torch.zeros(m, 2 * ld, dtype=torch.float16, device=DEV)
     ops.gemm(a, w, out=buf[:, ld:ld + n])
     ref = a.float() @ w.float().t()
-    untouched = float(buf[:, :ld].abs().max()) + float(buf[:, ld + n:].abs().max())
+    untouched = float(buf[:, :ld].abs().max()) + (float(buf[:, ld + n:].abs().max()) if ld > n else 0.0)
     return rel(buf[:, ld:ld + n].float(), ref) + untouched, 2e-3, f"gemm strided out m={m} n={n} k={k}"
 
 
