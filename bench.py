@@ -61,8 +61,7 @@ def parse():
     ap.add_argument("--no-batch8", action="store_true", help="skip the configs[2] sub-record (N = 1)")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager GPU baseline (N = 1)")
     ap.add_argument("--no-config4", action="store_true", help="skip the configs[3] sub-record and the probe (N > 1)")
-    ap.add_argument("--bank-overlap", default="off", choices=["auto", "on", "off"],
-                    help="build the appearance bank on a side stream while the first steps run (auto: N = 1, <= 2 frames)")
+    ap.add_argument("--tune", default="", help="experiments: launch heuristics as k=v[,k=v] (keys of ops.tuning)")
     return ap.parse_args()
 
 
@@ -304,11 +303,7 @@ class Bench:
         ctx = ctx_host[:1].cuda(non_blocking=True)
         uniq_n = min(K, 50)
         chunk = parallel.bank_chunk_size(uniq_n, world)
-        mode = self.args.bank_overlap
-        overlap = mode == "on" or (mode == "auto" and world == 1 and B <= 2)
-        if overlap:
-            chunk = min(chunk, 5)  # the first step starts after ONE chunk; the rest is built under the steps
-        gd = GraphedDenoiser(pipe, B, (L, L), ctx, bank_chunk=chunk, overlap_bank=overlap)
+        gd = GraphedDenoiser(pipe, B, (L, L), ctx, bank_chunk=chunk)
         gd.ref.copy_(ref)
         gd.capture()
         layout = gd.layout
@@ -323,7 +318,7 @@ class Bench:
             if prebuilt is None:
                 st = storage if (len(uniq) + world - 1) // world == slots else None
                 bank = parallel.build_and_gather_bank(uniq, layout, build_fn, eng.device, world, rank, chunk=chunk,
-                                                      storage=st, timing=timing, stream=gd.bank_stream)
+                                                      storage=st, timing=timing)
             else:
                 bank = prebuilt
             x = x_host.cuda(non_blocking=True)
@@ -353,7 +348,7 @@ class Bench:
         finite = bool(torch.isfinite(x_final).all())
         fp = [float(x_final.float().abs().mean()), float(x_final.float().flatten()[::997].sum())]
         rec = {"frames_per_gpu": B, "value": world * B * K / sec, "unit": UNIT, "ms_per_step": sec * 1e3 / K, "steps": K,
-               "bank_build_ms": bank_ms, "bank_chunk": chunk, "bank_overlap": overlap, "gpu_launches": int(launches), "clocks": clk,
+               "bank_build_ms": bank_ms, "bank_chunk": chunk, "gpu_launches": int(launches), "clocks": clk,
                "finite": finite, "x_final_fingerprint": fp, "step_launches": int(gd.step_launches),
                "bank_launches": int(gd.bank_launches)}
         gflop = GF_FRAME_STEP * B * K * world + GF_REF_STEP * uniq_n
@@ -493,6 +488,9 @@ class Bench:
 
 
 def run_ours(args):
+    if args.tune:
+        from magicdance_b200 import ops
+        ops.tuning(**{k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(","))}).__enter__()
     b = Bench(args)
     torch, dist = b.torch, b.dist
     world, rank = b.world, b.rank
@@ -535,7 +533,7 @@ def run_ours(args):
                            "timed region" % main["bank_chunk"],
                    "l2": "no flush needed: each step streams >4 GB of fp16 weights (L2 is 126 MB)",
                    "weights": "random init (seeded), fp16 storage, fp32 accumulate",
-                   "cuda_graph": True},
+                   "cuda_graph": True, **({"tune": args.tune} if args.tune else {})},
         "gpu_launches": main["gpu_launches"], "clocks": main["clocks"], "finite": main["finite"],
         "x_final_fingerprint": main["x_final_fingerprint"], "step_roofline": main["step_roofline"],
         "launches_per_step": main["step_launches"], "bank_build_ms": main["bank_build_ms"],
@@ -581,8 +579,10 @@ def gpu_eager_baseline(args):
            "--warmup", "2", "--algorithmic", "--latent", str(args.latent)]
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=REPO)
-        last = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")][-1]
-        res = json.loads(last)
+        lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
+        if not lines:
+            return {"unavailable": f"rc {out.returncode}: " + out.stderr.strip()[-600:]}
+        res = json.loads(lines[-1])
         res["cmd"] = " ".join(cmd[1:])
         return res
     except Exception as e:  # noqa: BLE001

@@ -30,7 +30,7 @@ extern "C" {
 #define MDB_ERR_CUDA (-2)
 #define MDB_ERR_UNSUPPORTED (-3)
 
-#define MDB_ABI_VERSION 1
+#define MDB_ABI_VERSION 2
 
 typedef void* mdb_stream_t;
 
@@ -41,6 +41,17 @@ const char* mdb_last_error(void);
 int mdb_device_check(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t mdb_launch_count(void);
+/* sizeof(mdb_gemm_desc) (which = 0) / sizeof(mdb_attn_desc) (which = 1): a binding checks its struct mirrors */
+int64_t mdb_abi_struct_bytes(int32_t which);
+
+/* Launch heuristics, process-wide.  The defaults are what the B200 measurements selected (profiles/); tests use the
+ * setter to force a kernel variant onto small problems. */
+#define MDB_TUNE_GEMM_PAIR_MIN_TILES 1 /* grids of >= this many 128-row tiles use the persistent CTA-pair GEMM (128) */
+#define MDB_TUNE_GEMM_TMA_STORE 2      /* != 0: single-CTA GEMM tiles leave through shared memory + TMA stores (0)  */
+#define MDB_TUNE_ATTN40_2Q_MIN_CTAS 3  /* d=40 attention grids of >= this many CTAs use the two-Q-tile kernel (2048) */
+#define MDB_TUNE_GEMM_BN80_BELOW 4     /* N %% 160 == 0 layers with fewer 160-wide CTAs than this take 80-wide tiles (100) */
+int mdb_set_tuning(int32_t key, int32_t value);
+int32_t mdb_get_tuning(int32_t key);
 
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core GEMM / implicit-GEMM convolution (tcgen05 + TMEM + TMA).
@@ -171,9 +182,6 @@ int mdb_timestep_embedding_f32(const int64_t* t, float* out, int32_t batch, int3
 int mdb_skinny_linear_f32(const float* x, const void* w, const float* bias, float* out, int32_t rows, int32_t n,
                           int32_t k, int32_t silu_in, int32_t silu_out, mdb_stream_t stream);
 
-/* L2 prefetch hint for a weight tensor (cp.async.bulk.prefetch.L2); no reference counterpart — it only
- * overlaps the next layers' cold weight reads with the current layer when one frame cannot fill the GPU. */
-int mdb_prefetch_l2(const void* ptr, int64_t bytes, mdb_stream_t stream);
 
 /* Row softmax in place over fp16 logits x[rows][cols] (row pitch ld elements), fp32 arithmetic:
  * x <- softmax(scale * x) along the columns.  The single-head, 512-channel attention of the first-stage VAE's

@@ -43,6 +43,9 @@ SIGNATURES = {
     "mdb_last_error": (C.c_char_p, []),
     "mdb_device_check": (c_int32, []),
     "mdb_launch_count": (c_int64, []),
+    "mdb_abi_struct_bytes": (c_int64, [c_int32]),
+    "mdb_set_tuning": (c_int32, [c_int32, c_int32]),
+    "mdb_get_tuning": (c_int32, [c_int32]),
     "mdb_gemm_f16": (c_int32, [C.POINTER(GemmDesc), c_void_p]),
     "mdb_attention_f16": (c_int32, [C.POINTER(AttnDesc), c_void_p]),
     "mdb_groupnorm_f16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -60,13 +63,14 @@ SIGNATURES = {
                                         c_int32, c_void_p]),
     "mdb_nchw_f32_to_nhwc_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mdb_nhwc_f16_to_nchw_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
-    "mdb_prefetch_l2": (c_int32, [c_void_p, c_int64, c_void_p]),
     "mdb_softmax_rows_f16": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p]),
     "mdb_cfg_ddim_update_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                           c_void_p, c_void_p]),
 }
 
 _lib = None
+ABI_VERSION = 2
+TUNE_GEMM_PAIR_MIN_TILES, TUNE_GEMM_TMA_STORE, TUNE_ATTN40_2Q_MIN_CTAS, TUNE_GEMM_BN80_BELOW = 1, 2, 3, 4
 
 
 def library_path() -> str:
@@ -93,8 +97,13 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.mdb_abi_version() != 1:
-        raise RuntimeError(f"magicdance_b200: ABI version mismatch ({lib.mdb_abi_version()} != 1); rebuild the library")
+    if lib.mdb_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"magicdance_b200: ABI version mismatch ({lib.mdb_abi_version()} != {ABI_VERSION}); "
+                           "rebuild the library")
+    for which, mirror in ((0, GemmDesc), (1, AttnDesc)):
+        if lib.mdb_abi_struct_bytes(which) != C.sizeof(mirror):
+            raise RuntimeError(f"magicdance_b200: {mirror.__name__} mirrors {C.sizeof(mirror)} bytes, the library's "
+                               f"struct has {lib.mdb_abi_struct_bytes(which)}: the binding and the library disagree")
     _lib = lib
     return lib
 

@@ -21,6 +21,9 @@
 
 namespace mdb {
 
+int get_attn_tuning();
+void set_attn_tuning(int v);
+
 constexpr int kAttnThreads = 192;
 constexpr int kBQ = 128;
 
@@ -899,14 +902,12 @@ static int launch_attn3(const AttnKParams& kp, dim3 grid, cudaStream_t st) {
   return MDB_OK;
 }
 
-static int attn_version() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MDB_ATTN");
-    v = (e != nullptr && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 3;  // 4: like 3, but d=40 on v2 at two CTAs/SM
-  }
-  return v;
-}
+// d = 40 self-attention (the 64x64 level): grids of at least this many 128-row CTAs go to the two-Q-tile kernel at two
+// CTAs per SM (16 softmax warps per SM).  Measured on B200 (profiles/r02_*): +3.3 % on the eight-frame step (4096
+// CTAs per launch), -2 % on the single-frame step (512 CTAs per launch).  mdb_set_tuning(MDB_TUNE_ATTN40_2Q_MIN_CTAS).
+static int g_attn40_2q_min_ctas = 2048;
+int get_attn_tuning() { return g_attn40_2q_min_ctas; }
+void set_attn_tuning(int v) { g_attn40_2q_min_ctas = v; }
 
 template <int D, int BKV, int MINB = 1>
 static int launch_attn2(const AttnKParams& kp, dim3 grid, cudaStream_t st) {
@@ -981,22 +982,15 @@ static int build_and_launch(const mdb_attn_desc* a, cudaStream_t st) {
   dim3 grid((a->nq + kBQ - 1) / kBQ, a->heads, a->batch);
   if constexpr (VER == 3) {
     constexpr int ST = (D == 40 ? 4 : 3);
-    static const int emu = [] { const char* e = getenv("MDB_ATTN_EMU"); return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 1; }();  // 1 of 4 measured best on B200
-    if (emu == 1) return launch_attn3<D, BKV, ST, 1>(kp, grid, st);
-    if (emu == 2) return launch_attn3<D, BKV, ST, 2>(kp, grid, st);
-    if (emu == 3) return launch_attn3<D, BKV, ST, 3>(kp, grid, st);
-    return launch_attn3<D, BKV, ST, 0>(kp, grid, st);
-  }
-  if constexpr (VER == 4) {  // two Q tiles per CTA AND two CTAs per SM (d = 40 only)
-    if (a->nq > kBQ) {
-      dim3 grid2((a->nq + 2 * kBQ - 1) / (2 * kBQ), a->heads, a->batch);
-      return launch_attn2<D, BKV, 2>(kp, grid2, st);
+    if constexpr (D == 40) {
+      // large grids: two Q tiles per CTA AND two CTAs per SM
+      const long long ctas = (long long)grid.x * grid.y * grid.z;
+      if (a->nq > kBQ && ctas >= (long long)g_attn40_2q_min_ctas) {
+        dim3 grid2((a->nq + 2 * kBQ - 1) / (2 * kBQ), a->heads, a->batch);
+        return launch_attn2<D, BKV, 2>(kp, grid2, st);
+      }
     }
-    return launch_attn3<D, BKV, 4, 1>(kp, grid, st);
-  }
-  if (VER == 2 && a->nq > kBQ) {  // two Q tiles per CTA (ping-pong)
-    dim3 grid2((a->nq + 2 * kBQ - 1) / (2 * kBQ), a->heads, a->batch);
-    return launch_attn2<D, BKV>(kp, grid2, st);
+    return launch_attn3<D, BKV, ST, 1>(kp, grid, st);  // 1 of 4 exponentials on the FMA pipe: measured best on B200
   }
   return launch_attn<D, BKV>(kp, grid, st);
 }
@@ -1017,17 +1011,13 @@ extern "C" int mdb_attention_f16(const mdb_attn_desc* a, mdb_stream_t stream) {
   MDB_REQUIRE(a->ldv0_batch >= a->n0 && a->ldv0_batch % 8 == 0, "mdb_attention_f16: ldv0_batch must be >= n0 and %% 8");
   MDB_REQUIRE(a->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "mdb_attention_f16: out alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int ver = attn_version();
   switch (a->d) {
     case 40:
-      if (ver == 4) return build_and_launch<40, 64, 4>(a, st);
-      if (ver == 3) return build_and_launch<40, 64, 3>(a, st);
-      return ver == 2 ? build_and_launch<40, 128, 2>(a, st) : build_and_launch<40, 128, 1>(a, st);
+      return build_and_launch<40, 64, 3>(a, st);
     case 80:
-      if (ver == 3 || ver == 4) return build_and_launch<80, 64, 3>(a, st);
-      return ver == 2 ? build_and_launch<80, 64, 2>(a, st) : build_and_launch<80, 64, 1>(a, st);
+      return build_and_launch<80, 64, 3>(a, st);
     case 160:
-      return ver == 2 ? build_and_launch<160, 64, 2>(a, st) : build_and_launch<160, 64, 1>(a, st);
+      return build_and_launch<160, 64, 1>(a, st);
     default:
       set_error("mdb_attention_f16: head dim %d not supported (40, 80, 160)", a->d);
       return MDB_ERR_UNSUPPORTED;

@@ -21,6 +21,9 @@
 
 namespace mdb {
 
+int get_gemm_tuning(int key);
+void set_gemm_tuning(int key, int value);
+
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 halves = 128 B = one swizzle row
 constexpr int kGemmThreads = 192;
@@ -51,7 +54,7 @@ struct GemmKParams {
 // STAGES = 3: <=108 KB, two CTAs per SM (large grids: the co-resident CTA hides the TMA round trip).
 // STAGES = 6 (8 for 80-wide tiles): one CTA per SM with a ring deep enough to cover the TMA latency on
 // its own — used when the grid has at most one CTA per SM anyway and the K loop is long.
-// PAIR: two CTAs (a cluster of 2 along M) run ONE cta_group::2 UMMA of shape 256 x BN: each keeps its own
+// PAIR (gemm_pair_kernel below): two CTAs run ONE cta_group::2 UMMA of shape 256 x BN: each keeps its own
 // 128 A rows and only BN/2 of the B rows, so a 256 x 160 pair tile pulls 26 KB per CTA and K chunk through
 // the L2 -> SM fabric where two independent 128 x 160 tiles pull 36 KB — the fabric (~6.3 KB/clk chip-wide)
 // is what bounds the large GEMMs of this path, not the tensor pipe.
@@ -115,11 +118,10 @@ __device__ __forceinline__ void epi_store_chunk(const GemmKParams& p, long long 
   }
 }
 
-template <int BN, bool GEGLU, int kStages, bool PAIR = false>
-__global__ void __launch_bounds__(kGemmThreads, (kStages <= (PAIR ? 4 : 3)) ? 2 : 1)
+template <int BN, bool GEGLU, int kStages>
+__global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
     gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
-  using S = GemmSmem<BN, kStages, PAIR>;
-  static_assert(!PAIR || (BN % 16 == 0 && BN <= 256), "cta_group::2 UMMA: N must be a multiple of 16, at most 256");
+  using S = GemmSmem<BN, kStages, false>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= (PAIR ? 4 : 3)) ? 2 
   const int n_iter = kc_end - kc_begin;
   constexpr uint32_t kTmemCols = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
   constexpr int kRedLd = BN + 4;  // fp32 row pitch of the split-K partial tile parked in shared memory
-  static_assert(PAIR || kBM * kRedLd * 4 <= kStages * S::kStageBytes, "partial tile must fit in the operand ring");
+  static_assert(kBM * kRedLd * 4 <= kStages * S::kStageBytes, "partial tile must fit in the operand ring");
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -151,10 +153,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= (PAIR ? 4 : 3)) ? 2 
     mbar_init(&acc_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
-    if constexpr (PAIR) tmem_alloc_pair(&tmem_base_smem, kTmemCols);
-    else tmem_alloc(&tmem_base_smem, kTmemCols);
-  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
   // a bias row that serves all batches is a constant weight: stage it before the PDL wait (overlaps the
   // previous kernel's tail).  Per-batch biases (timestep embedding) are produced upstream and are read later.
   const bool bias_in_smem = (p.bias != nullptr) && (p.bias_batch_stride == 0) && !p.cluster_reduce;
@@ -162,11 +161,9 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= (PAIR ? 4 : 3)) ? 2 
     for (int j = threadIdx.x - 64; j < BN; j += 128) s_bias[j] = (n0 + j < p.n) ? p.bias[n0 + j] : 0.f;
   }
   tc_fence_before_sync();
-  if constexpr (PAIR) cluster_sync_all();  // the partner's barriers must exist before anything is sent to them
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
-  [[maybe_unused]] const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
@@ -184,23 +181,6 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= (PAIR ? 4 : 3)) ? 2 
         uint8_t* sa = smem + s * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
         const int kc = kc_begin + it;
-        if constexpr (PAIR) {
-          // both CTAs' bytes are credited to the LEADER's barrier, which alone announces them
-          if (pair_rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
-          const uint32_t fb = dsmem_map(smem_u32(&full_bar[s]), 0);
-          if (p.conv) {
-            const int tap = kc / p.chunks_per_tap;
-            const int cc = kc - tap * p.chunks_per_tap;
-            const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d_pair(sa, &p.tmA, fb, cc * kBK, kw - 1, y0 + kh - 1, b0);
-          } else if (kc < p.k1_chunks) {
-            tma_load_2d_pair(sa, &p.tmA, fb, kc * kBK, m0);
-          } else {
-            tma_load_2d_pair(sa, &p.tmA2, fb, (kc - p.k1_chunks) * kBK, m0);
-          }
-          tma_load_2d_pair(sb, &p.tmB, fb, kc * kBK, n0 + static_cast<int>(pair_rank) * S::kBRows);
-          continue;
-        }
         mbar_expect_tx(&full_bar[s], S::kStageBytes);
         if (p.conv) {
           const int tap = kc / p.chunks_per_tap;
@@ -216,8 +196,8 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= (PAIR ? 4 : 3)) ? 2 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_iter > 0 && pair_rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * kBM : kBM, BN);
+    if (lane == 0 && n_iter > 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
@@ -230,14 +210,11 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= (PAIR ? 4 : 3)) ? 2 
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k) {
           // advance 16 halves (32 B) along K inside the 128B swizzle row: +2 in the >>4 address field
-          if constexpr (PAIR) umma_f16_ss_pair(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-          else umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
         }
-        if constexpr (PAIR) umma_commit_pair(&empty_bar[s]);  // frees the stage in both CTAs
-        else umma_commit(&empty_bar[s]);
+        umma_commit(&empty_bar[s]);
       }
-      if constexpr (PAIR) umma_commit_pair(&acc_bar);
-      else umma_commit(&acc_bar);
+      umma_commit(&acc_bar);
     }
   } else if (n_iter > 0) {
     // ---------------- epilogue warps 2..5 ----------------
@@ -357,7 +334,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= (PAIR ? 4 : 3)) ? 2 
     }
   }
 
-  if constexpr (!GEGLU && !PAIR) {
+  if constexpr (!GEGLU) {
     if (p.cluster_reduce) {
       // ---- split-K reduction across the cluster through distributed shared memory ----
       // cluster = the `splits` CTAs of this output tile.  CTA r owns rows [r*R, (r+1)*R) of the tile: it
@@ -446,227 +423,33 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= (PAIR ? 4 : 3)) ? 2 
   }
 
   tc_fence_before_sync();
-  if constexpr (PAIR) cluster_sync_all();  // the leader's MMAs read the partner's shared memory and TMEM
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
-    else tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Persistent CTA-pair GEMM: one cluster of two CTAs per TPC, ONE CTA per SM (the ~200 KB operand ring
-// keeps every other tensor-memory kernel off the SM), all 512 TMEM columns owned by the pair and used as
-// two accumulator buffers.  Each pair walks the 256 x BN output tiles t = cluster, cluster + #clusters, ...
-// (M fastest, so the pairs running at one time share a B tile); the leader's MMA thread fills buffer
-// (i & 1) for the i-th tile while the epilogue warps of both CTAs drain the other one, and the producers
-// run ahead into the next tile's operands.  Operand staging and barriers as in the PAIR mode above, plus
-//   acc_full[2]   (each CTA, count 1)  tcgen05.commit multicast: tile i is complete in both CTAs' TMEM
-//   acc_empty[2]  (leader, count 8)    one arrival per epilogue warp of BOTH CTAs: buffer drained
-// ------------------------------------------------------------------------------------------------
-template <int BN, bool GEGLU, int kStages>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_pairp_kernel(const __grid_constant__ GemmKParams p) {
-  using S = GemmSmem<BN, kStages, true>;
-  static_assert(BN % 16 == 0 && BN <= 256, "cta_group::2 UMMA: N must be a multiple of 16, at most 256");
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kStages];
-  __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ __align__(8) uint64_t acc_full[2];
-  __shared__ __align__(8) uint64_t acc_empty[2];
-  __shared__ uint32_t tmem_base_smem;
-
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  constexpr uint32_t kTmemCols = 512;
-  constexpr uint32_t kAccStride = 256;  // columns between the two accumulator buffers
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA);
-    tma_prefetch_desc(&p.tmB);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 8);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc_pair(&tmem_base_smem, kTmemCols);
-  tc_fence_before_sync();
-  cluster_sync_all();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t pair_rank = cluster_ctarank();
-  const int n_clusters = gridDim.x >> 1;
-  const int cluster_id = blockIdx.x >> 1;
-  const int m_pairs = (p.m + 2 * kBM - 1) / (2 * kBM);
-  const int n_tiles = (p.n + BN - 1) / BN;
-  const int total_tiles = m_pairs * n_tiles;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t g = 0;  // K chunks issued so far (ring position)
-      for (int t = cluster_id; t < total_tiles; t += n_clusters) {
-        const int mp = t % m_pairs, nt = t / m_pairs;
-        const int m0 = (2 * mp + static_cast<int>(pair_rank)) * kBM;
-        const int n0 = nt * BN;
-        int b0 = 0, y0 = 0;
-        if (p.conv) {
-          b0 = m0 / p.hw;
-          y0 = (p.hw >= kBM) ? (m0 % p.hw) / p.w : 0;
-        }
-        for (int kc = 0; kc < p.k_chunks; ++kc, ++g) {
-          const int s = g % kStages;
-          const uint32_t ph = (g / kStages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * S::kStageBytes;
-          uint8_t* sb = sa + S::kABytes;
-          if (pair_rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
-          const uint32_t fb = dsmem_map(smem_u32(&full_bar[s]), 0);
-          if (p.conv) {
-            const int tap = kc / p.chunks_per_tap;
-            const int cc = kc - tap * p.chunks_per_tap;
-            const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d_pair(sa, &p.tmA, fb, cc * kBK, kw - 1, y0 + kh - 1, b0);
-          } else if (kc < p.k1_chunks) {
-            tma_load_2d_pair(sa, &p.tmA, fb, kc * kBK, m0);
-          } else {
-            tma_load_2d_pair(sa, &p.tmA2, fb, (kc - p.k1_chunks) * kBK, m0);
-          }
-          tma_load_2d_pair(sb, &p.tmB, fb, kc * kBK, n0 + static_cast<int>(pair_rank) * S::kBRows);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && pair_rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(2 * kBM, BN);
-      uint32_t g = 0;
-      int i = 0;
-      for (int t = cluster_id; t < total_tiles; t += n_clusters, ++i) {
-        const int buf = i & 1;
-        mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this buffer
-        tc_fence_after_sync();
-        const uint32_t tacc = tmem_base + buf * kAccStride;
-        for (int kc = 0; kc < p.k_chunks; ++kc, ++g) {
-          const int s = g % kStages;
-          const uint32_t ph = (g / kStages) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
-          const uint32_t b_addr = a_addr + S::kABytes;
-          const uint64_t da = umma_desc_k_sw128(a_addr);
-          const uint64_t db = umma_desc_k_sw128(b_addr);
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) umma_f16_ss_pair(tacc, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
-          umma_commit_pair(&empty_bar[s]);
-        }
-        umma_commit_pair(&acc_full[buf]);
-      }
-    }
-  } else {
-    // ---------------- epilogue warps 2..5 of both CTAs ----------------
-    const int gq = warp & 3;  // TMEM lane quarter this warp may access
-    const uint32_t acc_empty_leader0 = dsmem_map(smem_u32(&acc_empty[0]), 0);
-    const uint32_t acc_empty_leader1 = dsmem_map(smem_u32(&acc_empty[1]), 0);
-    int i = 0;
-    for (int t = cluster_id; t < total_tiles; t += n_clusters, ++i) {
-      const int buf = i & 1;
-      const int mp = t % m_pairs, nt = t / m_pairs;
-      const int m0 = (2 * mp + static_cast<int>(pair_rank)) * kBM;
-      const int n0 = nt * BN;
-      const long long row = static_cast<long long>(m0) + gq * 32 + lane;
-      const bool row_ok = row < p.m;
-      const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
-      mbar_wait(&acc_full[buf], (i >> 1) & 1);
-      tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + buf * kAccStride + (static_cast<uint32_t>(gq * 32) << 16);
-      if constexpr (!GEGLU) {
-#pragma unroll
-        for (int ch = 0; ch < (BN + 31) / 32; ++ch) {
-          const int col0 = n0 + ch * 32;
-          if (col0 >= p.n) break;  // warp-uniform
-          uint32_t r[32];
-          tmem_ld_x32(taddr + ch * 32, r);
-          tmem_wait_ld();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const int ncols = min(min(32, BN - ch * 32), p.n - col0);
-          if (row_ok) {
-            const float* bias_chunk = (p.bias != nullptr) ? p.bias + brow * p.bias_batch_stride + col0 : nullptr;
-            epi_store_chunk(p, row, col0, ncols, v, bias_chunk, nullptr);
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int pr = 0; pr < BN / 64; ++pr) {
-          const int col0 = n0 + pr * 64;
-          if (col0 >= p.n) break;
-          uint32_t rv[32], rg[32];
-          tmem_ld_x32(taddr + pr * 64, rv);
-          tmem_ld_x32(taddr + pr * 64 + 32, rg);
-          tmem_wait_ld();
-          if (row_ok) {
-            const float* bp = (p.bias != nullptr) ? p.bias + brow * p.bias_batch_stride + col0 : nullptr;
-            uint4* d4 = reinterpret_cast<uint4*>(p.d + row * p.ldd + (col0 >> 1));
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float o[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int j = q * 8 + e;
-                float a = __uint_as_float(rv[j]);
-                float gt = __uint_as_float(rg[j]);
-                if (bp != nullptr) {
-                  a += bp[j];
-                  gt += bp[32 + j];
-                }
-                o[e] = a * gelu_erf_f(gt);
-              }
-              uint4 o4;
-              o4.x = pack_half2(o[0], o[1]);
-              o4.y = pack_half2(o[2], o[3]);
-              o4.z = pack_half2(o[4], o[5]);
-              o4.w = pack_half2(o[6], o[7]);
-              d4[q] = o4;
-            }
-          }
-        }
-      }
-      // this warp's quarter of the buffer is in registers/stored: hand the buffer back to the leader's MMA thread
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(buf == 0 ? acc_empty_leader0 : acc_empty_leader1);
-    }
-  }
-
-  tc_fence_before_sync();
-  cluster_sync_all();  // the leader's MMAs read the partner's shared memory and write its TMEM
-  if (warp == 1) {
-    tc_fence_after_sync();
-    tmem_dealloc_pair(tmem_base, kTmemCols);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Persistent CTA-pair GEMM, second cut (MDB_GEMM_PAIR=3) — written after the round-1 GPU budget was spent:
-// compiled and SASS-checked, NOT YET RUN ON A GPU, therefore opt-in (scripts/gpu_pending_checks.sh is its gate).
-// Same operand staging, barriers and tile walk as gemm_pairp_kernel above; what changes is the epilogue, which
-// bounded that kernel on the short-K layers (K = 320 / 640: four warps per CTA drained a 128 x BN fp32 tile
-// with dependent global loads of bias and residual per 32-column chunk and 16-byte stores strided by the row
-// pitch):
-//   * EIGHT epilogue warps per CTA (warps 2..9): two per TMEM lane quarter, each taking half of the tile's
-//     32-column chunks; acc_empty counts 16 arrivals (8 warps x 2 CTAs) and a warp arrives as soon as its last
-//     tcgen05.ld has returned, before it converts and stores;
-//   * the residual of the NEXT chunk (or of the next tile's first chunk) is fetched into registers while the
-//     current one is converted;
-//   * output through shared memory and TMA: a warp packs its 32 rows x 32 columns of fp16 into a 2 KB staging
-//     buffer (two per warp) and one lane issues cp.async.bulk.tensor (store); rows >= M and columns >= N are
-//     clipped by the tensor map, whole 64-byte row segments reach L2 instead of 16-byte pieces.
+// Persistent CTA-pair GEMM (the large grids: eight frames per GPU, the batched appearance passes): one cluster of
+// two CTAs per TPC, ONE CTA per SM (the ~200 KB operand ring keeps every other tensor-memory kernel off the SM),
+// all 512 TMEM columns owned by the pair and used as two accumulator buffers.  Each pair walks the 256 x BN output
+// tiles t = cluster, cluster + #clusters, ... (M fastest, so the pairs running at one time share a B tile); the
+// leader's MMA thread fills buffer (i & 1) for the i-th tile while the epilogue warps of both CTAs drain the other
+// one, and the producers run ahead into the next tile's operands.  Barriers:
+//   full/empty[stage]  both CTAs' TMA bytes are credited to the LEADER's `full`; tcgen05.commit multicast frees a
+//                      stage in both CTAs
+//   acc_full[2]        (each CTA, count 1)   tcgen05.commit multicast: tile i is complete in both CTAs' TMEM
+//   acc_empty[2]       (leader, count 16)    one arrival per epilogue warp of BOTH CTAs: buffer drained
+// Epilogue: EIGHT warps per CTA (two per TMEM lane quarter, each taking half of the tile's 32-column chunks); a warp
+// hands its share of the buffer back as soon as its last tcgen05.ld has returned; the residual of the NEXT chunk
+// is fetched while the current one is converted; output goes through shared memory and TMA (a warp packs 32 rows x
+// 32 columns of fp16 into a 2 KB staging buffer and one lane issues cp.async.bulk.tensor — rows >= M and columns
+// >= N are clipped by the tensor map, whole 64-byte row segments reach L2 instead of 16-byte pieces).
+// Launched WITHOUT programmatic stream serialization and never triggering its dependents early: a pair whose
+// cta_group::2 TMEM allocation is pending must not share its SMs with a foreign tensor-memory CTA (measured: the
+// one-tile-per-launch pair mode of round 1 dead-locked inside the full step for exactly that reason).
+// Measured on B200 (profiles/r02_*): +7 % on the eight-frame step over the single-CTA tiles.
 // ------------------------------------------------------------------------------------------------
 constexpr int kPairqThreads = 320;                    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kPairqEpiWarps = 8;
@@ -693,7 +476,7 @@ __device__ __forceinline__ void pairq_load_res(const GemmKParams& p, long long r
 
 template <int BN, bool GEGLU, int kStages>
 __global__ void __launch_bounds__(kPairqThreads, 1)
-    gemm_pairq_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ CUtensorMap tmD) {
+    gemm_pair_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ CUtensorMap tmD) {
   using S = GemmSmem<BN, kStages, true>;
   using Q = PairqSmem<BN, kStages>;
   // UMMA N <= 256: a 320-wide tile (BN = 320, the full width of the 64x64 level: every A tile is loaded exactly once)
@@ -968,241 +751,11 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-// CTA-pair tiles WITH split-K inside one cluster (MDB_GEMM_PAIR_SPLITK=1) — for the single-frame, weight-
-// streaming layers (M = 256 ... 8192 rows, K up to 11520, at most one wave of CTAs).  NOT YET RUN ON A GPU,
-// opt-in (same gate as above).  Why: those layers are bound by the bytes every SM pulls through the L2 -> SM
-// fabric (~46 B/clk per SM), not by DRAM or the tensor pipe: a 128 x 80 tile moves 26 KB per K chunk for
-// 128 x 80 outputs; one half of a 256 x 160 pair tile moves the same 26 KB (its own 128 A rows + 80 of the 160
-// B rows) for 128 x 160 outputs.  Keeping the CTA count (~one per SM) by splitting K across the cluster halves
-// the fabric traffic of the layer.
-// Cluster = (2, 1, S), S in {1, 2, 4}: x = the cta_group::2 pair (cluster ranks 2z, 2z+1: the pair of split z),
-// z = the K split.  Every CTA parks its 128 x BN fp32 partial in its own (by then idle) operand ring; the S
-// CTAs with the same pair rank then reduce it through DSMEM exactly like gemm_tc_kernel's cluster split-K (CTA
-// z sums rows [z*128/S, (z+1)*128/S) over all partners, applies bias/residual, stores fp16).
-// One CTA per SM by construction (>= 190 KB of shared memory), no early griddepcontrol.launch_dependents: no
-// foreign tensor-memory CTA can sit next to a pair whose cta_group::2 allocation is still pending — the
-// situation in which the one-tile pair mode of gemm_tc_kernel dead-locked inside the full step.
-// ------------------------------------------------------------------------------------------------
-template <int BN, int kStages>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_pairs_kernel(const __grid_constant__ GemmKParams p) {
-  using S = GemmSmem<BN, kStages, true>;
-  // BN = 320: two 160-wide MMAs per K step into one 320-column accumulator (see gemm_pairq_kernel)
-  constexpr int kParts = (BN > 256) ? 2 : 1;
-  constexpr int kPartN = BN / kParts;
-  static_assert(BN % 32 == 0 && kPartN % 16 == 0 && kPartN <= 256 && BN <= 512, "tile width");
-  static_assert(((kPartN / 2) * 128) % 1024 == 0, "each part's B rows start on a swizzle-atom boundary");
-  constexpr int kRedLd = BN + 4;  // fp32 row pitch of the parked partial tile
-  static_assert(kBM * kRedLd * 4 <= kStages * S::kStageBytes, "partial tile must fit in the operand ring");
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kStages];
-  __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ __align__(8) uint64_t acc_bar;
-  __shared__ uint32_t tmem_base_smem;
-
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM;
-  const int n0 = blockIdx.y * BN;
-  const int split = blockIdx.z;
-  const int kc_begin = split * p.chunks_per_split;
-  const int kc_end = min(p.k_chunks, kc_begin + p.chunks_per_split);
-  const int n_iter = kc_end - kc_begin;  // > 0: the host never creates an empty split
-  constexpr uint32_t kTmemCols = (BN <= 128) ? 128 : (BN <= 256 ? 256 : 512);
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA);
-    tma_prefetch_desc(&p.tmB);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(&acc_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc_pair(&tmem_base_smem, kTmemCols);
-  tc_fence_before_sync();
-  cluster_sync_all();  // every CTA's barriers exist and every pair owns its tensor memory from here on
-  tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t crank = cluster_ctarank();     // x + 2 * z inside the (2, 1, S) cluster
-  const uint32_t pair_rank = crank & 1u;        // 0 = leader of its pair (issues the MMAs)
-  const uint32_t leader = crank & ~1u;
-  // the pairing and the reduction below rely on the x-major linearisation of the cluster rank: fail loudly otherwise
-  if (pair_rank != (blockIdx.x & 1u) || (crank >> 1) != blockIdx.z) __trap();
-  pdl_wait();  // a no-op unless launched with programmatic serialization
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int b0 = 0, y0 = 0;
-      if (p.conv) {
-        b0 = m0 / p.hw;
-        y0 = (p.hw >= kBM) ? (m0 % p.hw) / p.w : 0;
-      }
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * S::kStageBytes;
-        uint8_t* sb = sa + S::kABytes;
-        const int kc = kc_begin + it;
-        if (pair_rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
-        const uint32_t fb = dsmem_map(smem_u32(&full_bar[s]), leader);
-        if (p.conv) {
-          const int tap = kc / p.chunks_per_tap;
-          const int cc = kc - tap * p.chunks_per_tap;
-          const int kh = tap / 3, kw = tap - kh * 3;
-          tma_load_4d_pair(sa, &p.tmA, fb, cc * kBK, kw - 1, y0 + kh - 1, b0);
-        } else if (kc < p.k1_chunks) {
-          tma_load_2d_pair(sa, &p.tmA, fb, kc * kBK, m0);
-        } else {
-          tma_load_2d_pair(sa, &p.tmA2, fb, (kc - p.k1_chunks) * kBK, m0);
-        }
-#pragma unroll
-        for (int h = 0; h < kParts; ++h)  // this CTA's half of each part's B rows (tmB's box is kPartN / 2 rows)
-          tma_load_2d_pair(sb + h * (kPartN / 2) * 128, &p.tmB, fb, kc * kBK,
-                           n0 + h * kPartN + static_cast<int>(pair_rank) * (kPartN / 2));
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && pair_rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(2 * kBM, kPartN);
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
-        const uint32_t b_addr = a_addr + S::kABytes;
-        const uint64_t da = umma_desc_k_sw128(a_addr);
-        const uint64_t db = umma_desc_k_sw128(b_addr);
-#pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-#pragma unroll
-          for (int h = 0; h < kParts; ++h)
-            umma_f16_ss_pair(tmem_base + h * kPartN, da + 2 * k, db + h * (((kPartN / 2) * 128) >> 4) + 2 * k, idesc,
-                             (it | k) != 0 ? 1u : 0u);
-        }
-        umma_commit_pair_at(&empty_bar[s], leader);  // frees the stage in both CTAs of THIS pair
-      }
-      umma_commit_pair_at(&acc_bar, leader);
-    }
-  } else {
-    // ---------------- epilogue warps 2..5: park the fp32 partial tile in shared memory ----------------
-    const int g = warp & 3;
-    mbar_wait(&acc_bar, 0);  // all MMAs of the pair are complete: both CTAs' operand rings are idle
-    tc_fence_after_sync();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
-#pragma unroll
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld_x32(taddr + ch * 32, r);
-      tmem_wait_ld();
-      float* rp = reinterpret_cast<float*>(smem) + (g * 32 + lane) * kRedLd + ch * 32;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(rp + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-    }
-  }
-
-  {
-    // ---- split-K reduction across the cluster through distributed shared memory (all 192 threads) ----
-    const int S_ = p.splits;
-    const int R = kBM / S_;
-    const int groups = BN / 8;
-    const int sidx = static_cast<int>(crank >> 1);  // this CTA's split == the row slice it reduces
-    constexpr int kMaxItems = 4;
-    uint4 rpre[kMaxItems];
-    if (p.residual != nullptr) {
-#pragma unroll
-      for (int q = 0; q < kMaxItems; ++q) {
-        const int item = threadIdx.x + q * kGemmThreads;
-        if (item < R * groups) {
-          const int rl = item / groups, cgp = item - rl * groups;
-          const long long row = static_cast<long long>(m0) + sidx * R + rl;
-          const int col0 = n0 + cgp * 8;
-          if (row < p.m && col0 + 8 <= p.n) rpre[q] = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
-        }
-      }
-    }
-    cluster_sync_all();  // every partial is parked (release) and visible (acquire)
-    const uint32_t red_base = smem_u32(smem);
-#pragma unroll 1
-    for (int it_ = 0; it_ * kGemmThreads < R * groups; ++it_) {
-      const int item = threadIdx.x + it_ * kGemmThreads;
-      if (item >= R * groups) break;
-      const int rl = item / groups, cgp = item - rl * groups;
-      const int rt = sidx * R + rl;  // row inside the 128-row tile
-      const long long row = static_cast<long long>(m0) + rt;
-      const int col0 = n0 + cgp * 8;
-      if (row >= p.m || col0 >= p.n) continue;
-      const uint32_t off = red_base + static_cast<uint32_t>((rt * kRedLd + cgp * 8) * 4);
-      float o[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = 0.f;
-      for (int pr = 0; pr < S_; ++pr) {
-        const uint32_t ra = dsmem_map(off, pair_rank + 2u * static_cast<uint32_t>(pr));  // same half of split pr's pair
-        const float4 a = dsmem_ld_f4(ra), b = dsmem_ld_f4(ra + 16);
-        o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
-        o[4] += b.x; o[5] += b.y; o[6] += b.z; o[7] += b.w;
-      }
-      const int ncols = min(8, p.n - col0);
-      const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
-      if (p.bias != nullptr) {
-        const float* bp = p.bias + brow * p.bias_batch_stride + col0;
-        for (int e = 0; e < ncols; ++e) o[e] += bp[e];
-      }
-      if (ncols == 8) {
-        if (p.residual != nullptr) {
-          uint4 r4 = make_uint4(0, 0, 0, 0);
-          if (it_ < kMaxItems) {
-#pragma unroll
-            for (int q = 0; q < kMaxItems; ++q)
-              if (q == it_) r4 = rpre[q];
-          } else {
-            r4 = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
-          }
-          const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = __half22float2(h2[e]);
-            o[2 * e] += f.x;
-            o[2 * e + 1] += f.y;
-          }
-        }
-        uint4 o4;
-        o4.x = pack_half2(o[0], o[1]);
-        o4.y = pack_half2(o[2], o[3]);
-        o4.z = pack_half2(o[4], o[5]);
-        o4.w = pack_half2(o[6], o[7]);
-        *reinterpret_cast<uint4*>(p.d + row * p.ldd + col0) = o4;
-      } else {
-        for (int e = 0; e < ncols; ++e) {
-          float x = o[e];
-          if (p.residual != nullptr) x += __half2float(p.residual[row * p.ldr + col0 + e]);
-          p.d[row * p.ldd + col0 + e] = __float2half_rn(x);
-        }
-      }
-    }
-  }
-
-  tc_fence_before_sync();
-  cluster_sync_all();  // nobody leaves while a partner may still read its shared memory or write its TMEM
-  if (warp == 1) {
-    tc_fence_after_sync();
-    tmem_dealloc_pair(tmem_base, kTmemCols);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// gemm_tc_kernel's plain path (one 128 x BN tile per CTA, no split-K, no cluster) with the TMA-store epilogue
-// of gemm_pairq_kernel (MDB_GEMM_TMAST=1) — NOT YET RUN ON A GPU, opt-in.  The main loop, the barriers and the
-// operand prefetches are those of the validated kernel; only the way the tile leaves the SM differs: each
-// epilogue warp packs 32 rows x 32 columns of fp16 into the (by then idle) operand ring and one lane issues a
-// cp.async.bulk.tensor store, instead of every lane writing 16-byte pieces one row pitch apart.  Aimed at the
-// short-K layers of the eight-frame regime (q/k/v/out projections, 1x1 convs, GEGLU: K = 320 ... 1280), where
-// the default epilogue takes longer than the main loop.
+// gemm_tc_kernel's plain path (one 128 x BN tile per CTA, no split-K, no cluster) with the TMA-store epilogue of
+// gemm_pair_kernel: each epilogue warp packs 32 rows x 32 columns of fp16 into the (by then idle) operand ring and
+// one lane issues a cp.async.bulk.tensor store, instead of every lane writing 16-byte pieces one row pitch apart.
+// For the short-K layers (q/k/v/out projections, 1x1 convs, GEGLU: K = 320 ... 1280) whose grid is too small for
+// the pair kernel: there the default epilogue takes longer than the main loop.
 // ------------------------------------------------------------------------------------------------
 template <int BN, bool GEGLU, int kStages>
 __global__ void __launch_bounds__(kGemmThreads, 2)
@@ -1519,38 +1072,42 @@ int make_tmap_f16_plain(CUtensorMap* out, const void* base, int rank, const uint
 
 void count_launch(int n = 1);
 
-template <int BN, bool GEGLU, int STAGES, bool PAIR = false>
+// launch heuristics (mdb_set_tuning): defaults selected by the B200 measurements under profiles/
+static int g_pair_min_tiles = 128;  // smallest grid, in 128-row tile equivalents, that goes to gemm_pair_kernel
+static int g_tma_store = 0;         // single-CTA tiles through the TMA-store epilogue (gemm_ts_kernel)
+static int g_bn80_below = 100;      // N % 160 == 0 layers with fewer 160-wide CTAs than this use 80-wide tiles
+
+template <int BN, bool GEGLU, int STAGES>
 static int launch_gemm(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
   const unsigned cluster_z = kp.cluster_reduce ? static_cast<unsigned>(kp.splits) : 1u;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, GEGLU, STAGES, PAIR>;
-  constexpr int kSmem = GemmSmem<BN, STAGES, PAIR>::kTotal;
+  auto kern = gemm_tc_kernel<BN, GEGLU, STAGES>;
+  constexpr int kSmem = GemmSmem<BN, STAGES, false>::kTotal;
   if (!attr_set) {
     MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
-  MDB_CHECK_CUDA(launch_pdl_cluster2(kern, grid, dim3(kGemmThreads), kSmem, st, PAIR ? 2u : 1u, cluster_z, kp));
+  MDB_CHECK_CUDA(launch_pdl_cluster(kern, grid, dim3(kGemmThreads), kSmem, st, cluster_z, kp));
   count_launch();
   return MDB_OK;
 }
 
 template <int BN, bool GEGLU, int STAGES>
-static int launch_gemm_pairp(const GemmKParams& kp, int total_tiles, cudaStream_t st) {
+static int launch_gemm_pair(const GemmKParams& kp, const CUtensorMap& tmD, int total_tiles, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = gemm_pairp_kernel<BN, GEGLU, STAGES>;
-  constexpr int kSmem = GemmSmem<BN, STAGES, true>::kTotal;
+  auto kern = gemm_pair_kernel<BN, GEGLU, STAGES>;
+  constexpr int kSmem = PairqSmem<BN, STAGES>::kTotal;
+  static_assert(kSmem <= 227 * 1024, "shared memory budget");
   if (!attr_set) {
     MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
   const int clusters = total_tiles < 74 ? total_tiles : 74;  // one pair per TPC (148 SMs)
-  // Launched WITHOUT programmatic stream serialization and never triggering its dependents early: with PDL
-  // around it the persistent pair kernel dead-locks inside the full step (measured), and a kernel of this
-  // size (>= 256 tiles) has nothing to gain from overlapping a few microseconds of prologue.
+  // no programmatic stream serialization: the pair kernel starts only after its predecessor has completed
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(kPairqThreads);
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1560,46 +1117,9 @@ static int launch_gemm_pairp(const GemmKParams& kp, int total_tiles, cudaStream_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MDB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
+  MDB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, kp, tmD));
   count_launch();
   return MDB_OK;
-}
-
-static int launch_cluster_nopdl(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cx,
-                                unsigned cz, void** args) {
-  // no programmatic stream serialization: a pair kernel starts only after its predecessor has completed
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cx;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = cz;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  MDB_CHECK_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
-  count_launch();
-  return MDB_OK;
-}
-
-template <int BN, bool GEGLU, int STAGES>
-static int launch_gemm_pairq(const GemmKParams& kp, const CUtensorMap& tmD, int total_tiles, cudaStream_t st) {
-  static bool attr_set = false;
-  auto kern = gemm_pairq_kernel<BN, GEGLU, STAGES>;
-  constexpr int kSmem = PairqSmem<BN, STAGES>::kTotal;
-  static_assert(kSmem <= 227 * 1024, "shared memory budget");
-  if (!attr_set) {
-    MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_set = true;
-  }
-  const int clusters = total_tiles < 74 ? total_tiles : 74;  // one pair per TPC (148 SMs)
-  void* args[2] = {const_cast<GemmKParams*>(&kp), const_cast<CUtensorMap*>(&tmD)};
-  return launch_cluster_nopdl(reinterpret_cast<const void*>(kern), dim3(2 * clusters), dim3(kPairqThreads), kSmem, st, 2u,
-                              1u, args);
 }
 
 template <int BN, bool GEGLU, int STAGES>
@@ -1616,20 +1136,13 @@ static int launch_gemm_ts(const GemmKParams& kp, const CUtensorMap& tmD, dim3 gr
   return MDB_OK;
 }
 
-template <int BN, int STAGES>
-static int launch_gemm_pairs(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
-  auto kern = gemm_pairs_kernel<BN, STAGES>;
-  constexpr int kSmem = GemmSmem<BN, STAGES, true>::kTotal;
-  // one CTA per SM and less than the smallest tensor-memory kernel's footprint (78 KB) left beside it
-  static_assert(kSmem <= 227 * 1024 && kSmem >= 180 * 1024, "one CTA per SM, nothing else with tensor memory beside it");
-  if (!attr_set) {
-    MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_set = true;
-  }
-  void* args[1] = {const_cast<GemmKParams*>(&kp)};
-  return launch_cluster_nopdl(reinterpret_cast<const void*>(kern), grid, dim3(kGemmThreads), kSmem, st, 2u,
-                              static_cast<unsigned>(kp.splits), args);
+int get_gemm_tuning(int key) {
+  return key == MDB_TUNE_GEMM_PAIR_MIN_TILES ? g_pair_min_tiles : (key == MDB_TUNE_GEMM_BN80_BELOW ? g_bn80_below : g_tma_store);
+}
+void set_gemm_tuning(int key, int value) {
+  if (key == MDB_TUNE_GEMM_PAIR_MIN_TILES) g_pair_min_tiles = value;
+  else if (key == MDB_TUNE_GEMM_BN80_BELOW) g_bn80_below = value;
+  else g_tma_store = value;
 }
 
 }  // namespace mdb
@@ -1709,94 +1222,20 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     kp.k1_chunks = k1 / kBK;
   }
 
-  // CTA-pair (cta_group::2, 256 x BN) tiles — EXPERIMENTAL, opt-in: MDB_GEMM_PAIR=1 (one tile per cluster
-  // launch, PAIR mode of gemm_tc_kernel) or =2 (persistent gemm_pairp_kernel).  Conditions: no split-K, at
-  // least two M tiles, a grid of at least MDB_GEMM_PAIR_MIN (default 256) CTAs.  Measured on B200
-  // (scripts/gpu_microbench.py pair): variant 1 is +4..17 % on grids from ~256 CTAs up and neutral to -15 %
-  // on the one-wave grids of a single frame, but dead-locks inside the full step when CTAs of other
-  // tensor-memory kernels are co-resident with a pair (scripts/repro_pair_hang.sh); variant 2 owns its SMs and
-  // all 512 TMEM columns and runs the full step, but is not yet tuned.  Both give the
-  // same results as the single-CTA tiles (tests/kernel_cases.py case_pair).  The switches are read per call
-  // (launches are captured into graphs, so this is off the replay path), which lets the tests force pair
-  // tiles onto small problems.
-  // Pair tiles with split-K inside the cluster (gemm_pairs_kernel) — EXPERIMENTAL, opt-in, not yet run on a GPU:
-  // MDB_GEMM_PAIR_SPLITK=1.  Takes the layers that fit in one wave of CTAs (the single-frame regime) and have at
-  // least two M tiles; picks its own split count S in {1, 2, 4} (cluster of 2*S <= 8 CTAs) so that about one CTA
-  // lands on every SM, whatever `splits` the caller asked for (no workspace is needed: DSMEM reduction).
-  {
-    const char* ps_env = getenv("MDB_GEMM_PAIR_SPLITK");
-    const int mt = (g->m + kBM - 1) / kBM;
-    // long-K layers only (3x3 convs, the 4C -> C feed-forward): with a handful of K chunks the park-and-reduce
-    // epilogue costs more than the operand traffic it saves.  MDB_GEMM_PAIR_SPLITK_MINK overrides the threshold.
-    const char* mink_env = getenv("MDB_GEMM_PAIR_SPLITK_MINK");
-    const int min_chunks = mink_env ? atoi(mink_env) : 16;
-    if (ps_env != nullptr && ps_env[0] == '1' && !geglu && mt >= 2 && g->n % 8 == 0 && kp.k_chunks >= min_chunks) {
-      // Tile width and split count: what bounds these layers is the bytes ONE SM pulls through the L2 -> SM fabric,
-      // chunks/S x (16 KB of A + 64 B x BN of B) — so take the (BN, S) that minimises it.  Co-resident CTAs at one
-      // ~200 KB CTA per SM: 148 in clusters of 2, 132 in clusters of 4, 128 in clusters of 8 (8 GPCs of 16/18/20
-      // SMs, a cluster never straddles a GPC).  MDB_GEMM_PAIR_SPLITK_BN forces the width (tuner / tests).
-      const int m_pairs = (mt + 1) / 2;
-      const char* pbn_env = getenv("MDB_GEMM_PAIR_SPLITK_BN");
-      const int forced_bn = pbn_env ? atoi(pbn_env) : 0;
-      int bnp = 0, S_ = 1, ctas = 0;
-      long long best_cost = -1;
-      const int widths[3] = {320, 160, 128};
-      for (int wi = 0; wi < 3; ++wi) {
-        const int w = widths[wi];
-        if (forced_bn ? (w != forced_bn) : ((w != 128 && g->n % w != 0) || (w == 128 && g->n % 160 == 0))) continue;
-        const int nt = (g->n + w - 1) / w;
-        const int c = 2 * m_pairs * nt;
-        if (c > 148) continue;
-        int sp = 1;
-        if (c * 4 <= 128 && kp.k_chunks >= 16) sp = 4;
-        else if (c * 2 <= 132 && kp.k_chunks >= 8) sp = 2;
-        const long long cost = (long long)((kp.k_chunks + sp - 1) / sp) * (16384 + 64 * w);
-        if (best_cost < 0 || cost < best_cost) {
-          best_cost = cost; bnp = w; S_ = sp; ctas = c;
-        }
-      }
-      const int n_tiles = bnp ? (g->n + bnp - 1) / bnp : 0;
-      if (bnp != 0 && ctas <= 148) {
-        // each CTA of a pair stages half of the B rows (of each 160-wide part of a 320-wide tile)
-        uint32_t boxb[2] = {kBK, (uint32_t)(bnp == 320 ? 80 : bnp / 2)};
-        uint64_t dimsb[2] = {(uint64_t)g->k, (uint64_t)g->n};
-        uint64_t strb[1] = {(uint64_t)g->ldb * 2};
-        rc = make_tmap_f16(&kp.tmB, g->b, 2, dimsb, strb, boxb);
-        if (rc) return rc;
-        kp.chunks_per_split = (kp.k_chunks + S_ - 1) / S_;
-        S_ = (kp.k_chunks + kp.chunks_per_split - 1) / kp.chunks_per_split;  // no empty splits
-        if (S_ == 3) {  // 4 requested, 3 non-empty: a (2,1,3) cluster is legal but R = 128/3 is not
-          S_ = 2;
-          kp.chunks_per_split = (kp.k_chunks + 1) / 2;
-        }
-        kp.splits = S_;
-        kp.cluster_reduce = 1;
-        dim3 gridp(2 * m_pairs, n_tiles, S_);
-        if (bnp == 320) return launch_gemm_pairs<320, 5>(kp, gridp, st);
-        if (bnp == 160) return launch_gemm_pairs<160, 8>(kp, gridp, st);
-        return launch_gemm_pairs<128, 8>(kp, gridp, st);
-      }
-    }
-  }
-
-  const char* pair_env = getenv("MDB_GEMM_PAIR");
-  const char* pair_min_env = getenv("MDB_GEMM_PAIR_MIN");
-  const bool pairq = (pair_env != nullptr && pair_env[0] == '3');  // gemm_pairq_kernel: see its header comment
-  const bool pair_ok = (pair_env != nullptr && (pair_env[0] == '1' || pair_env[0] == '2')) || (pairq && g->n % 8 == 0);
-  // smallest grid (in single-CTA-tile equivalents) that is worth a pair launch: 256 for the one-tile pair mode
-  // (measured), 128 for the persistent kernels' second cut (one round of 64 pair tiles already fills 128 SMs)
-  const long long pair_min = pair_min_env ? atoll(pair_min_env) : (pairq ? 128ll : 256ll);
+  // ---- which kernel ----
+  // Large grids (>= g_pair_min_tiles 128-row tile equivalents, no split-K, at least two M tiles): the persistent
+  // CTA-pair kernel with 256 x {320, 256, 160, 128} tiles — widest first: fewest L2 -> SM bytes per flop; the
+  // 320-wide tile (two 160-wide MMAs per K step, single accumulator buffer) only for long K.
   const int m_tiles = (g->m + kBM - 1) / kBM;
-  bool pair = pair_ok && g->splits <= 1 && m_tiles >= 2;
-  int bn;
+  bool pair = g->splits <= 1 && m_tiles >= 2 && g->n % 8 == 0;
+  int bn = 0;
   if (pair) {
     if (geglu) bn = (g->n % 256 == 0) ? 256 : 0;
-    else if (pairq && g->n % 320 == 0 && kp.k_chunks >= 16) bn = 320;  // full-width tiles of the long-K layers
-    else if (pairq && g->n % 256 == 0) bn = 256;  // widest tile first: fewest L2 -> SM bytes per flop
-    else if (g->n % 160 == 0) bn = 160;
+    else if (g->n % 320 == 0 && kp.k_chunks >= 16) bn = 320;
     else if (g->n % 256 == 0) bn = 256;
+    else if (g->n % 160 == 0) bn = 160;
     else bn = 128;
-    if (bn == 0 || (long long)((m_tiles + 1) / 2) * 2 * ((g->n + bn - 1) / bn) < pair_min) pair = false;
+    if (bn == 0 || (long long)((m_tiles + 1) / 2) * 2 * ((g->n + bn - 1) / bn) < (long long)g_pair_min_tiles) pair = false;
   }
   if (pair) {
     // bn chosen above
@@ -1805,17 +1244,10 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     bn = 128;
   } else if (g->n % 160 == 0) {
     // 160-wide tiles unless that leaves most of the 148 SMs idle; then halve the tile width
-    const long long tiles160 = (long long)((g->m + kBM - 1) / kBM) * (g->n / 160) * (g->splits > 1 ? g->splits : 1);
-    bn = (tiles160 < 100) ? 80 : 160;
+    const long long tiles160 = (long long)m_tiles * (g->n / 160) * (g->splits > 1 ? g->splits : 1);
+    bn = (tiles160 < g_bn80_below) ? 80 : 160;
   } else {
     bn = 128;
-  }
-  // per-shape overrides for the tuner (scripts/gpu_tune_gemm.py -> magicdance_b200/gemm_plan.json -> ops.gemm):
-  // MDB_GEMM_BN = 80 | 128 | 160 forces the tile width of the single-CTA kernel, MDB_GEMM_DEEP = 0 | 1 the ring depth
-  const char* bn_env = getenv("MDB_GEMM_BN");
-  if (bn_env != nullptr && !pair && !geglu) {
-    const int fb = atoi(bn_env);
-    if (fb == 80 || fb == 128 || fb == 160) bn = fb;
   }
   {
     // a pair CTA stages half of the B rows (of each 160-wide part of a 320-wide tile)
@@ -1835,56 +1267,33 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   kp.ws = g->splitk_ws;
   // 2, 4 or 8 splits: the partners form a thread-block cluster and reduce through DSMEM (one kernel);
   // other counts go through the global fp32 workspace + finalize kernel.
-  static const bool cluster_ok = [] { const char* e = getenv("MDB_CLUSTER_SPLITK"); return !(e && e[0] == '0'); }();
-  kp.cluster_reduce = (cluster_ok && !geglu && (splits == 2 || splits == 4 || splits == 8)) ? 1 : 0;
+  kp.cluster_reduce = (!geglu && (splits == 2 || splits == 4 || splits == 8)) ? 1 : 0;
   if (splits > 1 && !kp.cluster_reduce) {
     MDB_REQUIRE(g->splitk_ws != nullptr, "mdb_gemm_f16: splits > 1 needs splitk_ws");
   }
 
-  dim3 grid(pair ? 2 * ((m_tiles + 1) / 2) : m_tiles, (g->n + bn - 1) / bn, splits);
-  bool deep = (long long)grid.x * grid.y * grid.z <= 148 && kp.chunks_per_split >= 12;
-  if (const char* deep_env = getenv("MDB_GEMM_DEEP")) {
-    if (deep_env[0] == '0') deep = false;
-    else if (deep_env[0] == '1') deep = true;
-  }
-  if (pair) {
-    // MDB_GEMM_PAIR=2: the persistent one-pair-per-TPC kernel (owns the SMs and all of their tensor memory)
-    if (pairq) {
-      // output tensor map of the TMA-store epilogue: [M][N_out] fp16, 32 x 32 boxes, dense (no swizzle)
-      CUtensorMap tmD;
-      uint32_t boxd[2] = {(uint32_t)kOutBox, (uint32_t)kOutBox};
-      uint64_t dimsd[2] = {(uint64_t)(geglu ? g->n / 2 : g->n), (uint64_t)g->m};
-      uint64_t strd[1] = {(uint64_t)g->ldd * 2};
-      rc = make_tmap_f16_plain(&tmD, g->d, 2, dimsd, strd, boxd);
-      if (rc) return rc;
-      const int total_tiles = ((m_tiles + 1) / 2) * (int)grid.y;
-      if (geglu) return launch_gemm_pairq<256, true, 5>(kp, tmD, total_tiles, st);
-      if (bn == 320) return launch_gemm_pairq<320, false, 5>(kp, tmD, total_tiles, st);
-      if (bn == 160) return launch_gemm_pairq<160, false, 6>(kp, tmD, total_tiles, st);
-      if (bn == 256) return launch_gemm_pairq<256, false, 5>(kp, tmD, total_tiles, st);
-      return launch_gemm_pairq<128, false, 6>(kp, tmD, total_tiles, st);
-    }
-    if (pair_env[0] == '2') {
-      const int total_tiles = ((m_tiles + 1) / 2) * (int)grid.y;
-      if (geglu) return launch_gemm_pairp<256, true, 6>(kp, total_tiles, st);
-      if (bn == 160) return launch_gemm_pairp<160, false, 8>(kp, total_tiles, st);
-      if (bn == 256) return launch_gemm_pairp<256, false, 6>(kp, total_tiles, st);
-      return launch_gemm_pairp<128, false, 8>(kp, total_tiles, st);
-    }
-    if (geglu) rc = launch_gemm<256, true, 3, true>(kp, grid, st);
-    else if (bn == 160) rc = deep ? launch_gemm<160, false, 8, true>(kp, grid, st) : launch_gemm<160, false, 4, true>(kp, grid, st);
-    else if (bn == 256) rc = deep ? launch_gemm<256, false, 6, true>(kp, grid, st) : launch_gemm<256, false, 3, true>(kp, grid, st);
-    else rc = deep ? launch_gemm<128, false, 8, true>(kp, grid, st) : launch_gemm<128, false, 4, true>(kp, grid, st);
-  } else if (getenv("MDB_GEMM_TMAST") != nullptr && getenv("MDB_GEMM_TMAST")[0] == '1' && splits == 1 && !deep &&
-             g->n % 8 == 0 && bn != 80) {  // 80-wide tiles end in a 16-column chunk: a 32-wide box would spill
-                                           // into the neighbouring tile
-    // opt-in, not yet run on a GPU: same tiles, output through shared memory + TMA (gemm_ts_kernel)
-    CUtensorMap tmD;
+  dim3 grid(m_tiles, (g->n + bn - 1) / bn, splits);
+  const bool deep = (long long)grid.x * grid.y * grid.z <= 148 && kp.chunks_per_split >= 12;
+  const bool tma_store = !pair && g_tma_store != 0 && splits == 1 && !deep && g->n % 8 == 0 && bn != 80;
+  CUtensorMap tmD;
+  if (pair || tma_store) {
+    // output tensor map of the TMA-store epilogues: [M][N_out] fp16, 32 x 32 boxes, dense (no swizzle);
+    // an 80-wide tile ends in a 16-column chunk whose 32-wide box would spill into the neighbouring tile
     uint32_t boxd[2] = {(uint32_t)kOutBox, (uint32_t)kOutBox};
     uint64_t dimsd[2] = {(uint64_t)(geglu ? g->n / 2 : g->n), (uint64_t)g->m};
     uint64_t strd[1] = {(uint64_t)g->ldd * 2};
     rc = make_tmap_f16_plain(&tmD, g->d, 2, dimsd, strd, boxd);
     if (rc) return rc;
+  }
+  if (pair) {
+    const int total_tiles = ((m_tiles + 1) / 2) * (int)grid.y;
+    if (geglu) return launch_gemm_pair<256, true, 5>(kp, tmD, total_tiles, st);
+    if (bn == 320) return launch_gemm_pair<320, false, 5>(kp, tmD, total_tiles, st);
+    if (bn == 160) return launch_gemm_pair<160, false, 6>(kp, tmD, total_tiles, st);
+    if (bn == 256) return launch_gemm_pair<256, false, 5>(kp, tmD, total_tiles, st);
+    return launch_gemm_pair<128, false, 6>(kp, tmD, total_tiles, st);
+  }
+  if (tma_store) {
     if (geglu) rc = launch_gemm_ts<128, true, 3>(kp, tmD, grid, st);
     else if (bn == 160) rc = launch_gemm_ts<160, false, 3>(kp, tmD, grid, st);
     else rc = launch_gemm_ts<128, false, 3>(kp, tmD, grid, st);

@@ -455,19 +455,6 @@ __global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float*
   }
 }
 
-// L2 prefetch of a (weight) tensor: cp.async.bulk.prefetch.L2 in 16 KB pieces.  At one frame per GPU the layers
-// are weight-stream bound; issuing the NEXT layers' weights from a side stream while the current layer computes
-// turns their cold HBM reads into L2 hits.  Pure hint: no data dependence, no effect on results.
-__global__ void prefetch_l2_kernel(const uint8_t* __restrict__ p, long long bytes) {
-  constexpr long long kPiece = 16384;
-  const long long pieces = (bytes + kPiece - 1) / kPiece;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < pieces;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long off = i * kPiece;
-    const unsigned sz = static_cast<unsigned>(min(kPiece, bytes - off)) & ~15u;
-    if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"(sz) : "memory");
-  }
-}
 
 static inline int grid_for(long long total, int threads = 256, int cap = 148 * 16) {
   long long b = (total + threads - 1) / threads;
@@ -480,7 +467,39 @@ static inline int grid_for(long long total, int threads = 256, int cap = 148 * 1
 
 using namespace mdb;
 
+namespace mdb {
+int get_gemm_tuning(int key);
+void set_gemm_tuning(int key, int value);
+int get_attn_tuning();
+void set_attn_tuning(int v);
+}  // namespace mdb
+
 extern "C" int mdb_abi_version(void) { return MDB_ABI_VERSION; }
+
+extern "C" int64_t mdb_abi_struct_bytes(int32_t which) {
+  return which == 0 ? (int64_t)sizeof(mdb_gemm_desc) : (which == 1 ? (int64_t)sizeof(mdb_attn_desc) : -1);
+}
+
+extern "C" int mdb_set_tuning(int32_t key, int32_t value) {
+  switch (key) {
+    case MDB_TUNE_GEMM_PAIR_MIN_TILES:
+    case MDB_TUNE_GEMM_TMA_STORE:
+    case MDB_TUNE_GEMM_BN80_BELOW:
+      mdb::set_gemm_tuning(key, value);
+      return MDB_OK;
+    case MDB_TUNE_ATTN40_2Q_MIN_CTAS:
+      mdb::set_attn_tuning(value);
+      return MDB_OK;
+    default:
+      mdb::set_error("mdb_set_tuning: unknown key %d", key);
+      return MDB_ERR_INVALID;
+  }
+}
+
+extern "C" int32_t mdb_get_tuning(int32_t key) {
+  if (key == MDB_TUNE_ATTN40_2Q_MIN_CTAS) return mdb::get_attn_tuning();
+  return mdb::get_gemm_tuning(key);
+}
 extern "C" const char* mdb_last_error(void) { return mdb::g_err; }
 extern "C" int64_t mdb_launch_count(void) { return mdb::g_launches.load(); }
 
@@ -571,17 +590,6 @@ extern "C" int mdb_softmax_rows_f16(void* x, int64_t ld, int32_t rows, int32_t c
                                  static_cast<cudaStream_t>(stream), static_cast<__half*>(x), static_cast<long long>(ld),
                                  cols, scale * 1.4426950408889634f));
   mdb::count_launch();
-  return MDB_OK;
-}
-
-extern "C" int mdb_prefetch_l2(const void* ptr, int64_t bytes, mdb_stream_t stream) {
-  MDB_REQUIRE(ptr != nullptr && bytes > 0 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "mdb_prefetch_l2: bad arguments");
-  const long long pieces = (bytes + 16383) / 16384;
-  int blocks = static_cast<int>((pieces + 31) / 32);
-  if (blocks > 148) blocks = 148;
-  prefetch_l2_kernel<<<blocks, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(ptr), bytes);
-  MDB_CHECK_CUDA(cudaGetLastError());
-  count_launch();
   return MDB_OK;
 }
 

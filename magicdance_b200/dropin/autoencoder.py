@@ -4,9 +4,9 @@ same constructor kwargs, the same 248 state-dict keys and shapes (`encoder.*`, `
 `encode(x) -> posterior` / `decode(z) -> image` / `forward(input, sample_posterior)` calls — running on the hot
 path's kernels through magicdance_b200/vae.py.
 
-OPT-IN: the decoder/encoder behind it have not run on a GPU yet (scripts/gpu_vae_parity.py is the gate), so this
-class is NOT re-exported under the shadow tree `model_lib/ControlNet/ldm/models/autoencoder.py`; to use it, point
-`first_stage_config.target` at `magicdance_b200.dropin.autoencoder.AutoencoderKL` (INTEGRATION.md option A).
+Validated on a B200 against the goldens of the unmodified reference AutoencoderKL (tests/test_vae_gpu.py: decode
+and encode rel-L2 ~1.5e-3 at fp16 storage) and re-exported under the reference's dotted path
+`model_lib/ControlNet/ldm/models/autoencoder.py`, so the YAML's first_stage_config resolves to it.
 Parameters stay fp32 in PyTorch-native layouts (checkpoint compatible); the fp16 kernel layouts are packed lazily on
 the GPU and dropped by load_state_dict.  Inference only: no loss, no EMA, no training_step.
 """
@@ -145,3 +145,23 @@ class AutoencoderKL(nn.Module):
 
     def get_last_layer(self):
         return self.decoder.conv_out.weight
+
+
+class IdentityFirstStage(nn.Module):
+    """ldm/models/autoencoder.py:201-219: a first stage that returns its input (used by configs without a VAE)"""
+
+    def __init__(self, *args, vq_interface=False, **kwargs):
+        super().__init__()
+        self.vq_interface = vq_interface
+
+    def encode(self, x, *args, **kwargs):
+        return x
+
+    def decode(self, x, *args, **kwargs):
+        return x
+
+    def quantize(self, x, *args, **kwargs):
+        return (x, None, [None, None, None]) if self.vq_interface else x
+
+    def forward(self, x, *args, **kwargs):
+        return x

@@ -258,8 +258,6 @@ def _auto_splits(m, n, k):
     """Split-K factor: small-M layers (8x8 / 16x16 latents) would otherwise run on a handful of SMs and
     stream their weights at a fraction of HBM bandwidth.  Mirrors the tile choice of mdb_gemm_f16:
     160-wide tiles, 80-wide when that leaves most SMs idle; split K only if still under ~100 CTAs."""
-    if os.environ.get("MDB_SPLITK", "1") == "0":
-        return 1
     mt = (m + 127) // 128
     if n % 160 == 0:
         tiles = mt * (n // 160)

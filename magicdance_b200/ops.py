@@ -18,45 +18,27 @@ _GEMM_DEBUG = os.environ.get("MDB_GEMM_DEBUG", "0") == "1"
 TRACE = None  # set to a list to record (m, n, k, conv, epilogue, splits, k2) of every gemm() call (bench.py)
 
 
-# Per-shape launch choices measured on the target GPU by scripts/gpu_tune_gemm.py: key (gemm_plan_key) ->
-# {"splits": int, "env": {switch: value}}.  Empty unless magicdance_b200/gemm_plan.json exists (none is committed
-# until the tuner has run on a B200) and MDB_GEMM_PLAN != 0; with an empty plan gemm() behaves exactly as before.
-GEMM_PLAN = {}
-_PLAN_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gemm_plan.json")
+class tuning:
+    """`with ops.tuning(pair_min_tiles=1):` — the library's launch heuristics (include/magicdance_b200.h
+    mdb_set_tuning) for the duration of the block; tests use it to force a kernel variant onto small problems.
+    Launches captured into CUDA graphs keep the variant they were captured with."""
+    _KEYS = {"pair_min_tiles": _lib.TUNE_GEMM_PAIR_MIN_TILES, "tma_store": _lib.TUNE_GEMM_TMA_STORE,
+             "attn40_2q_min_ctas": _lib.TUNE_ATTN40_2Q_MIN_CTAS, "bn80_below": _lib.TUNE_GEMM_BN80_BELOW}
 
-
-def gemm_plan_key(m, n, k, conv, epilogue, a2_cols):
-    return f"{m}x{n}x{k}|conv{int(conv is not None)}|epi{int(epilogue)}|a2_{int(a2_cols)}"
-
-
-def load_gemm_plan(path=None):
-    """(Re)loads the plan; returns the number of entries.  A missing file clears the plan."""
-    import json
-    GEMM_PLAN.clear()
-    path = _PLAN_PATH if path is None else path
-    if os.environ.get("MDB_GEMM_PLAN", "1") != "0" and os.path.isfile(path):
-        with open(path) as f:
-            for key, ent in json.load(f).get("plan", {}).items():
-                GEMM_PLAN[key] = {"splits": int(ent.get("splits", 0)), "env": {str(a): str(b) for a, b in ent.get("env", {}).items()}}
-    return len(GEMM_PLAN)
-
-
-class _env_switches:
-    """sets library switches (read by the C entry on every call) for the duration of one launch"""
-
-    def __init__(self, env):
-        self.env = env
+    def __init__(self, **kw):
+        self.want = {self._KEYS[k]: int(v) for k, v in kw.items() if v is not None}
 
     def __enter__(self):
-        self.old = {k: os.environ.get(k) for k in self.env}
-        os.environ.update(self.env)
+        lib = _lib.load()
+        self.old = {k: int(lib.mdb_get_tuning(k)) for k in self.want}
+        for k, v in self.want.items():
+            _lib.check(lib.mdb_set_tuning(k, v), "set_tuning")
+        return self
 
     def __exit__(self, *a):
+        lib = _lib.load()
         for k, v in self.old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
+            lib.mdb_set_tuning(k, v)
 
 
 def _stream() -> int:
@@ -138,49 +120,6 @@ def _workspace(key, numel, dtype, device, zero=False):
     return t
 
 
-class WeightPrefetcher:
-    """Runs ahead of a network pass on a side stream and pulls the weights of the GEMMs `distance` calls ahead
-    into L2 (mdb_prefetch_l2).  The order of GEMM calls of a pass is fixed, so the first (eager) pass records
-    (pointer, bytes) per call and later passes — including the CUDA-graph capture — replay the plan.  Pacing is by
-    events: the prefetch for call i+distance is released when call i-1 has been launched on the main stream."""
-
-    def __init__(self, device, distance=2, min_bytes=1 << 20):
-        self.stream = torch.cuda.Stream(device=device)
-        self.distance, self.min_bytes = distance, min_bytes
-        self.plans, self.key, self.i, self.recording = {}, None, 0, False
-
-    def begin(self, key):
-        self.key, self.i = key, 0
-        self.recording = key not in self.plans
-        if self.recording:
-            self.plans[key] = []
-        else:
-            self.stream.wait_stream(torch.cuda.current_stream())
-
-    def on_gemm(self, w):
-        if self.key is None:
-            return
-        plan = self.plans[self.key]
-        if self.recording:
-            plan.append((w.data_ptr(), w.numel() * 2, w))
-        else:
-            j = self.i + self.distance
-            if j < len(plan) and plan[j][1] >= self.min_bytes:
-                ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream())
-                self.stream.wait_event(ev)
-                _lib.check(_lib.load().mdb_prefetch_l2(plan[j][0], plan[j][1], self.stream.cuda_stream), "prefetch_l2")
-        self.i += 1
-
-    def end(self):
-        if self.key is not None and not self.recording:
-            torch.cuda.current_stream().wait_stream(self.stream)
-        self.key = None
-
-
-PREFETCHER = None  # set by the pipeline (GraphedDenoiser) for single-frame latency runs
-
-
 def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, residual=None, epilogue=EPI_NONE,
          a2=None, conv=None, splits=1, m=None):
     """D = epilogue(A @ W^T).  a: [M, K1] fp16 (last dim contiguous, row stride arbitrary) or, with
@@ -226,26 +165,17 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
     if TRACE is not None:
         TRACE.append((m, n, k, tuple(conv) if conv is not None else None, epilogue, splits,
                       a2.shape[1] if a2 is not None else 0))
-    plan = GEMM_PLAN.get(gemm_plan_key(m, n, k, conv, epilogue, a2.shape[1] if a2 is not None else 0)) if GEMM_PLAN else None
-    if plan is not None and plan["splits"] > 0 and epilogue != EPI_GEGLU:
-        splits = plan["splits"]
     if splits > 1:
         ws = _workspace("splitk", splits * m * n, torch.float32, a.device)
         g.splits, g.splitk_ws = splits, ws.data_ptr()
     else:
         g.splits = 1
-    if PREFETCHER is not None:
-        PREFETCHER.on_gemm(w)
     if _GEMM_DEBUG:  # MDB_GEMM_DEBUG=1: name every GEMM before it runs and wait for it (pins down a hanging shape)
         import sys
         print(f"gemm m={m} n={n} k={k} conv={conv} epi={epilogue} splits={g.splits} a2={a2 is not None} lda={g.lda} "
               f"ldd={g.ldd} bias={bias is not None} bbs={g.bias_batch_stride} res={residual is not None}",
               file=sys.stderr, flush=True)
-    if plan is not None and plan["env"]:
-        with _env_switches(plan["env"]):
-            _lib.check(lib.mdb_gemm_f16(C.byref(g), _stream()), "gemm_f16")
-    else:
-        _lib.check(lib.mdb_gemm_f16(C.byref(g), _stream()), "gemm_f16")
+    _lib.check(lib.mdb_gemm_f16(C.byref(g), _stream()), "gemm_f16")
     if _GEMM_DEBUG:
         torch.cuda.synchronize()
     return out
@@ -437,5 +367,3 @@ def cfg_ddim_update(x, eps_c, eps_u, coef, noise=None, x_prev=None, pred_x0=None
                "cfg_ddim_update_f32")
     return x_prev, pred_x0
 
-
-load_gemm_plan()

@@ -82,10 +82,9 @@ class GatheredBank:
     and a step only waits for its own row (`wait(index)`); the remaining rows travel over NVLink while the first
     steps already run.  `dict`-like for the callers that only need index -> buffer."""
 
-    def __init__(self, table, works=None, slot_of=None, events=None):
-        # works: slot row -> c10d work handle of its all-gather; events: ddim index -> CUDA event after which a
-        # locally built slot is complete (bank built on a side stream, single-GPU case)
-        self.table, self.works, self.slot_of, self.events = table, works or {}, slot_of or {}, events or {}
+    def __init__(self, table, works=None, slot_of=None):
+        # works: slot row -> c10d work handle of its all-gather
+        self.table, self.works, self.slot_of = table, works or {}, slot_of or {}
         self._waited = set()
 
     def __getitem__(self, ix):
@@ -102,11 +101,6 @@ class GatheredBank:
 
     def wait(self, ix=None):
         """make the CURRENT stream wait for the gather that delivers ddim index ix (all of them if None)"""
-        for i_ in (list(self.events) if ix is None else [ix]):
-            e = self.events.get(i_)
-            if e is not None and id(e) not in self._waited:
-                torch.cuda.current_stream().wait_event(e)
-                self._waited.add(id(e))
         slots = list(self.works) if ix is None else [self.slot_of.get(ix)]
         for s_ in slots:
             if s_ is not None and s_ in self.works and s_ not in self._waited:
@@ -116,7 +110,7 @@ class GatheredBank:
 
 def build_and_gather_bank(indices: Sequence[int], layout: BankLayout,
                           build_fn: Callable[[List[int], torch.Tensor], None], device, world: int = 1, rank: int = 0,
-                          group=None, chunk: int = 10, storage=None, timing=None, stream=None) -> GatheredBank:
+                          group=None, chunk: int = 10, storage=None, timing=None) -> GatheredBank:
     """Each rank calls build_fn(ddim_indices_chunk, slots[len(chunk), numel]) for its share of `indices`
     (build_fn fills the flat fp16 slots in place; chunks of up to `chunk` timesteps are built as ONE
     batched appearance pass), then the slots are exchanged: one all_gather_into_tensor per slot row, issued
@@ -139,32 +133,17 @@ def build_and_gather_bank(indices: Sequence[int], layout: BankLayout,
             e.record()
             return e
         timing["build0"] = ev()
-    side = None
-    if stream is not None:
-        side = torch.cuda.stream(stream)
-        stream.wait_stream(torch.cuda.current_stream())  # inputs are uploaded; earlier readers of the slots were issued
-        side.__enter__()
-    try:
-        events = {}
-        for s0 in range(0, len(mine), chunk):
-            part = mine[s0:s0 + chunk]
-            build_fn(part, local[s0:s0 + len(part)])
-            if stream is not None and world == 1:
-                e = torch.cuda.Event()
-                e.record(stream)
-                for ix in part:
-                    events[ix] = e
-        if timing is not None and "build0" in timing:
-            timing["build1"] = ev()
-        if world == 1:
-            return GatheredBank({ix: local[s] for s, ix in enumerate(mine)}, events=events)
-        table = owner_slot(indices, world)
-        flat_of = {ix: gathered[s, r] for ix, (r, s) in table.items()}
-        slot_of = {ix: s for ix, (r, s) in table.items()}
-        works = {}
-        for s in range(slots):
-            works[s] = dist.all_gather_into_tensor(gathered[s].view(-1), local[s], group=group, async_op=True)
-    finally:
-        if side is not None:
-            side.__exit__(None, None, None)
+    for s0 in range(0, len(mine), chunk):
+        part = mine[s0:s0 + chunk]
+        build_fn(part, local[s0:s0 + len(part)])
+    if timing is not None and "build0" in timing:
+        timing["build1"] = ev()
+    if world == 1:
+        return GatheredBank({ix: local[s] for s, ix in enumerate(mine)})
+    table = owner_slot(indices, world)
+    flat_of = {ix: gathered[s, r] for ix, (r, s) in table.items()}
+    slot_of = {ix: s for ix, (r, s) in table.items()}
+    works = {}
+    for s in range(slots):
+        works[s] = dist.all_gather_into_tensor(gathered[s].view(-1), local[s], group=group, async_op=True)
     return GatheredBank(flat_of, works, slot_of)

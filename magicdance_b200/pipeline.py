@@ -182,8 +182,7 @@ class GraphedDenoiser:
     memory refreshed by tiny copies before each replay (the timestep, the DDIM coefficient row, the
     bank K/V of that timestep), so ONE graph serves every step."""
 
-    def __init__(self, pipe: DenoisePipeline, batch: int, latent_hw, context: torch.Tensor, bank_chunk: int = 10,
-                 overlap_bank: bool = False):
+    def __init__(self, pipe: DenoisePipeline, batch: int, latent_hw, context: torch.Tensor, bank_chunk: int = 10):
         from . import parallel
         self.pipe, self.eng = pipe, pipe.engine
         eng, dev = self.eng, pipe.device
@@ -207,12 +206,6 @@ class GraphedDenoiser:
         self.replayed_launches = 0
         import os
         self.side = torch.cuda.Stream(device=dev) if os.environ.get("MDB_DUAL_STREAM", "1") != "0" else None
-        # overlap_bank: build the appearance bank on its own stream WHILE the first DDIM steps run — a step only needs
-        # the bank of its own timestep, and at one frame per GPU the step's small kernels leave most of the tensor pipe
-        # idle.  The bank graph then owns its scratch lane and its memory pool (two graphs that replay concurrently
-        # must not share either).
-        self.overlap = bool(overlap_bank)
-        self.bank_stream = torch.cuda.Stream(device=dev) if self.overlap else None
         # auxiliary streams for independent branches inside a block (engine._fork): lane 0 (UNet pass) -> lane 2,
         # lane 1 (ControlNet pass on the side stream) -> lane 3
         # (kept on THIS object and handed to the engine only for the duration of _step_body: eager calls through the
@@ -220,15 +213,6 @@ class GraphedDenoiser:
         self.aux_streams = None
         if os.environ.get("MDB_AUX_STREAMS", "1") != "0" and batch <= 2:
             self.aux_streams = {0: (torch.cuda.Stream(device=dev), 2), 1: (torch.cuda.Stream(device=dev), 3)}
-        # run-ahead L2 weight prefetch (one prefetcher per concurrently running network pass)
-        # (measured on B200: no gain at one frame per GPU — 9.06 vs 8.94 ms/step — so it is opt-in: MDB_PREFETCH=1)
-        if os.environ.get("MDB_PREFETCH", "0") == "1":
-            dist_ = int(os.environ.get("MDB_PREFETCH_DISTANCE", "2"))
-            self.pf_main = ops.WeightPrefetcher(dev, distance=dist_)
-            self.pf_side = ops.WeightPrefetcher(dev, distance=dist_)
-        else:
-            self.pf_main = self.pf_side = None
-
     # the two bodies, written against the static buffers only
     def _step_body(self):
         """One DDIM step.  The pose ControlNet and the UNet's encoder half are independent (the pose
@@ -246,28 +230,17 @@ class GraphedDenoiser:
         t = self.t_cur.expand(b).contiguous()
         bank_kv = self.layout.views(self.bank_cur, self.tokens, 1)
         main = torch.cuda.current_stream()
-        def with_prefetch(pf, key, fn):
-            if pf is None:
-                return fn()
-            ops.PREFETCHER = pf
-            pf.begin((id(self), key))
-            try:
-                return fn()
-            finally:
-                pf.end()
-                ops.PREFETCHER = None
-
         if self.side is not None:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side), ops.workspace_lane(1):
-                pose = with_prefetch(self.pf_side, "controlnet", lambda: eng.controlnet(self.x, self.hint, t, self.ctx))
+                pose = eng.controlnet(self.x, self.hint, t, self.ctx)
             join = lambda: main.wait_stream(self.side)
         else:
-            pose = with_prefetch(self.pf_side, "controlnet", lambda: eng.controlnet(self.x, self.hint, t, self.ctx))
+            pose = eng.controlnet(self.x, self.hint, t, self.ctx)
             join = None
         if 2 * b <= 16:
-            eps_c, eps_u = with_prefetch(self.pf_main, "unet_pair", lambda: eng.unet_forward(
-                self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, cfg_pair=True, before_pose=join))
+            eps_c, eps_u = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, cfg_pair=True,
+                                            before_pose=join)
         else:
             if join:
                 join()
@@ -277,13 +250,7 @@ class GraphedDenoiser:
                             pred_x0=self.pred_x0)
         self.x.copy_(self.x_prev)
 
-    BANK_LANE = 4  # scratch lane of a bank build that overlaps the steps (lanes 0-3: UNet, ControlNet, their aux streams)
-
     def _bank_body(self):
-        if self.overlap:
-            with ops.workspace_lane(self.BANK_LANE):
-                build_bank_slots(self.eng, self.ref, self.t_vec, self.ctx, self.layout, self.tokens, self.bank_built)
-            return
         build_bank_slots(self.eng, self.ref, self.t_vec, self.ctx, self.layout, self.tokens, self.bank_built)
 
     def capture(self):
@@ -302,7 +269,7 @@ class GraphedDenoiser:
             self._bank_body()
         n1 = ops.launch_count()
         self.g_step = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_step, **({} if self.overlap else {"pool": self.g_bank.pool()})):
+        with torch.cuda.graph(self.g_step, pool=self.g_bank.pool()):
             self._step_body()
         torch.cuda.synchronize()
         # kernels of OUR library inside each graph (the C ABI counts launches at capture time only)
@@ -324,11 +291,8 @@ class GraphedDenoiser:
         self.replayed_launches += self.bank_launches
         out_slots.copy_(self.bank_built[:n])
 
-    def step(self, index, bank_flat, ready=None):
-        """one DDIM step on self.x in place (result also in self.x_prev / self.pred_x0); `ready`: event after which
-        bank_flat is valid (overlapped bank build)"""
-        if ready is not None:
-            torch.cuda.current_stream().wait_event(ready)
+    def step(self, index, bank_flat):
+        """one DDIM step on self.x in place (result also in self.x_prev / self.pred_x0)"""
         self.t_cur.copy_(self.pipe.t_dev[index:index + 1])
         self.coef_cur.copy_(self.pipe.coef[index])
         self.bank_cur.copy_(bank_flat)

@@ -22,22 +22,17 @@ GROUPS = {
     "gemm": ("case_gemm", "case_gemm_batch_bias", "case_gemm_dual", "case_gemm_strided_out", "case_geglu"),
     "conv": ("case_conv", "case_down", "case_conv_im2col"),
     "attn": ("case_attention",),
-    "pair": ("case_pair",),
+    "tuned": ("case_tuned",),
 }
-# kernels that have never run on a GPU (tests/kernel_cases.py PENDING_CASES): --group pending, --pending-filter <text>
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--group", default="all")
     ap.add_argument("--first", type=int, default=0, help="only the first N cases of the group")
-    ap.add_argument("--pending-filter", default="", help="with --group pending: only cases whose switches contain this")
     args = ap.parse_args()
-    if args.group == "pending":
-        cases = [(f, a) for f, a in K.PENDING_CASES if args.pending_filter in str(a[0])]
-    else:
-        names = sum(GROUPS.values(), ()) if args.group == "all" else GROUPS[args.group]
-        cases = [(f, a) for f, a in K.ALL_CASES if f.__name__ in names]
+    names = sum(GROUPS.values(), ()) if args.group == "all" else GROUPS[args.group]
+    cases = [(f, a) for f, a in K.ALL_CASES if f.__name__ in names]
     if args.first:
         cases = cases[:args.first]
     print(f"device: {torch.cuda.get_device_name(0)}; {len(cases)} cases in group {args.group}", flush=True)

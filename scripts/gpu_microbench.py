@@ -97,46 +97,58 @@ def main():
         conv_case(2, 8, 8, 2560, 1280, 16)
         conv_case(8, 8, 8, 1280, 1280, 4)
     if which == "pair":
-        # single-CTA 128 x BN tiles vs CTA-pair (cta_group::2) 256 x BN tiles, shape by shape, at the cond+uncond
-        # batch of one frame (2) and of eight frames (16)
-        for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("0", "1")):
-            os.environ["MDB_GEMM_PAIR"] = mode
-            os.environ["MDB_GEMM_PAIR_MIN"] = "1"
-            print(f"--- MDB_GEMM_PAIR={mode}", flush=True)
-            for b in (2, 16):
-                conv_case(b, 64, 64, 320, 320)
-                conv_case(b, 64, 64, 640, 320)
-                conv_case(b, 32, 32, 640, 640)
-                conv_case(b, 32, 32, 1280, 640)
-                conv_case(b, 16, 16, 1280, 1280)
-                conv_case(b, 8, 8, 1280, 1280)
-                gemm_case(b * 4096, 320, 320)
-                gemm_case(b * 4096, 320, 1280)
-                gemm_case(b * 1024, 640, 640)
-                gemm_case(b * 1024, 640, 2560)
-                gemm_case(b * 256, 1280, 1280)
-                gemm_case(b * 256, 1280, 5120)
-                for hw, c in ((4096, 320), (1024, 640), (256, 1280)):
-                    x, (wp, bp) = h(b * hw, c), pack_geglu(torch.randn(8 * c, c), torch.randn(8 * c), D)
-                    timeit(f"geglu m={b * hw} c={c}", lambda: ops.gemm(x, wp, bias=bp, epilogue=ops.EPI_GEGLU),
-                           flops=2.0 * b * hw * 8 * c * c)
+        # single-CTA 128 x BN tiles vs the persistent CTA-pair kernel (256 x BN, cta_group::2) vs the TMA-store epilogue
+        # of the single-CTA tiles, shape by shape, at the cond+uncond batch of one frame (2) and of eight frames (16)
+        big = 1 << 30
+        for label, tune in (("single-CTA tiles", dict(pair_min_tiles=big, tma_store=0)),
+                            ("single-CTA tiles + TMA store", dict(pair_min_tiles=big, tma_store=1)),
+                            ("pair kernel (forced)", dict(pair_min_tiles=1, tma_store=0))):
+            print(f"--- {label}", flush=True)
+            with ops.tuning(**tune):
+                for b in (2, 16):
+                    conv_case(b, 64, 64, 320, 320)
+                    conv_case(b, 64, 64, 640, 320)
+                    conv_case(b, 32, 32, 640, 640)
+                    conv_case(b, 32, 32, 1280, 640)
+                    conv_case(b, 16, 16, 1280, 1280)
+                    conv_case(b, 8, 8, 1280, 1280)
+                    gemm_case(b * 4096, 320, 320)
+                    gemm_case(b * 4096, 320, 1280)
+                    gemm_case(b * 1024, 640, 640)
+                    gemm_case(b * 1024, 640, 2560)
+                    gemm_case(b * 256, 1280, 1280)
+                    gemm_case(b * 256, 1280, 5120)
+                    for hw, c in ((4096, 320), (1024, 640), (256, 1280)):
+                        x, (wp, bp) = h(b * hw, c), pack_geglu(torch.randn(8 * c, c), torch.randn(8 * c), D)
+                        timeit(f"geglu m={b * hw} c={c}", lambda: ops.gemm(x, wp, bias=bp, epilogue=ops.EPI_GEGLU),
+                               flops=2.0 * b * hw * 8 * c * c)
         return
-    if which == "pairs":
-        # single-frame (cond+uncond batch of 2) weight-streaming layers: default tiles / split-K against pair tiles
-        # with split-K inside the cluster (gemm_pairs_kernel); both take the split count the engine would pass
-        from magicdance_b200.engine import _auto_splits
-        for mode in ("0", "1"):
-            os.environ["MDB_GEMM_PAIR_SPLITK"] = mode
-            os.environ["MDB_GEMM_PAIR_SPLITK_MINK"] = "1"  # every eligible shape, also the short-K ones, to find the threshold
-            print(f"--- MDB_GEMM_PAIR_SPLITK={mode}", flush=True)
-            for (hh, cin, cout) in ((64, 320, 320), (64, 640, 320), (32, 640, 640), (32, 1280, 640), (16, 1280, 1280),
-                                    (16, 2560, 1280), (8, 1280, 1280), (8, 2560, 1280)):
-                conv_case(2, hh, hh, cin, cout, _auto_splits(2 * hh * hh, cout, 9 * cin))
-            for (m, n, k) in ((8192, 320, 320), (8192, 320, 1280), (2048, 640, 640), (2048, 640, 2560), (2048, 1280, 640),
-                              (512, 1280, 1280), (512, 1280, 5120), (512, 2560, 1280)):
-                gemm_case(m, n, k, _auto_splits(m, n, k))
-        os.environ.pop("MDB_GEMM_PAIR_SPLITK", None)
-        os.environ.pop("MDB_GEMM_PAIR_SPLITK_MINK", None)
+    if which == "deepk":
+        # the single-frame weight-streaming layers (cond+uncond batch of 2) with COLD weights, as inside a step (each
+        # step streams 2.4 GB of weights through a 126 MB L2): eight weight copies are cycled; 80- vs 160-wide tiles
+        # and the split-K factor
+        def cold(name, m, n, k, conv, flops):
+            ws = [h(n, k) for _ in range(max(2, int(300e6 / (2.0 * n * k)) + 1))]
+            x = h(m, conv[3] if conv else k)
+            bias, res = f(n), h(m, n)
+            for bn_below, bnl in ((1 << 30, 80), (0, 160)):
+                for sp in (1, 2, 4, 8):
+                    if k // 64 < 4 * sp:
+                        continue
+                    state = {"i": 0}
+
+                    def fn():
+                        w = ws[state["i"] % len(ws)]
+                        state["i"] += 1
+                        ops.gemm(x, w, bias=bias, residual=res, splits=sp, **({"conv": conv} if conv else {}))
+                    with ops.tuning(bn80_below=bn_below, pair_min_tiles=1 << 30):
+                        timeit(f"{name} bn={bnl} splits={sp}", fn, reps=len(ws) * 2, flops=flops)
+        for (hh, cin, cout) in ((16, 1280, 1280), (16, 2560, 1280), (8, 1280, 1280), (8, 2560, 1280), (32, 640, 640),
+                                (32, 1280, 640), (64, 320, 320)):
+            m = 2 * hh * hh
+            cold(f"conv B=2 {hh}x{hh} {cin}->{cout}", m, cout, 9 * cin, (2, hh, hh, cin), 2.0 * m * cout * 9 * cin)
+        for (m, n, k) in ((512, 1280, 5120), (512, 1280, 1280), (2048, 640, 2560), (2048, 640, 640), (8192, 320, 1280)):
+            cold(f"gemm m={m} n={n} k={k}", m, n, k, None, 2.0 * m * n * k)
         return
     if which in ("all", "attn"):
         attn_case(1, 40, 4096, 4096)

@@ -35,43 +35,20 @@ def case_gemm(m, n, k, bias=False, residual=False, splits=1, seed=0):
     return rel(out.float(), ref), 2e-3, f"gemm m={m} n={n} k={k} bias={bias} res={residual} splits={splits}"
 
 
-def case_pair(fn, *args):
-    """Runs another GEMM-family case on the opt-in CTA-pair (cta_group::2, 256 x BN) tiles, whatever the grid
-    size (the library reads MDB_GEMM_PAIR / MDB_GEMM_PAIR_MIN on every call)."""
-    import os
-    # MDB_TEST_PAIR_MODE: "1" = one pair tile per cluster launch, "2" = the persistent pair kernel
-    forced = {"MDB_GEMM_PAIR": os.environ.get("MDB_TEST_PAIR_MODE", "1"), "MDB_GEMM_PAIR_MIN": "1"}
-    old = {k: os.environ.get(k) for k in forced}
-    os.environ.update(forced)
-    try:
+def case_tuned(tune, fn, *args):
+    """Runs another case under `ops.tuning(**tune)` — the library's launch heuristics (mdb_set_tuning) — so that a
+    kernel variant that the heuristics reserve for large grids is exercised on a small problem.
+    tune: tuple of (name, value) pairs, e.g. (("pair_min_tiles", 1),)."""
+    with ops.tuning(**dict(tune)):
         err, tol, desc = fn(*args)
         torch.cuda.synchronize()
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
-    return err, tol, "pair tiles: " + desc
+    return err, tol, " ".join(f"{k}={v}" for k, v in tune) + ": " + desc
 
 
-def case_env(env, fn, *args):
-    """Runs another case with environment switches of the library set for the duration of the call (the GEMM
-    entry reads its MDB_GEMM_* switches on every call).  env: tuple of (name, value) pairs."""
-    import os
-    forced = dict(env)
-    old = {k: os.environ.get(k) for k in forced}
-    os.environ.update(forced)
-    try:
-        err, tol, desc = fn(*args)
-        torch.cuda.synchronize()
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
-    return err, tol, " ".join(f"{k}={v}" for k, v in env) + ": " + desc
+PAIR = (("pair_min_tiles", 1),)     # persistent CTA-pair GEMM (gemm_pair_kernel) whatever the grid size
+TMAST = (("tma_store", 1),)         # single-CTA tiles through the TMA-store epilogue (gemm_ts_kernel)
+NOPAIR = (("pair_min_tiles", 1 << 30),)  # single-CTA tiles on a large grid
+ATT2Q = (("attn40_2q_min_ctas", 0),)     # d=40 attention on the two-Q-tile kernel at two CTAs per SM
 
 
 def case_gemm_batch_bias(batch, hw, n, k, seed=0):
@@ -357,20 +334,41 @@ ALL_CASES = [
     (case_conv, (1, 8, 8, 2560, 1280, True, False, 8)),
     (case_conv, (2, 16, 16, 1280, 1280, True, True, 4)),
     (case_conv, (2, 32, 32, 640, 640, True, True, 2)),
-    (case_pair, (case_gemm, 384, 320, 320, True, True)),       # odd number of M tiles: the last pair is half empty
-    (case_pair, (case_gemm, 1000, 640, 1280, True, False)),    # ragged M, 160-wide halves
-    (case_pair, (case_gemm, 512, 256, 128)),                   # 256-wide pair tile
-    (case_pair, (case_gemm, 300, 384, 192, True, True)),       # 128-wide pair tile, N = 3 tiles
-    (case_pair, (case_gemm, 4096, 320, 2880, True, True)),     # long K: the ring wraps many times
-    (case_pair, (case_gemm_strided_out, 320, 77, 768)),        # ragged N inside one half
-    (case_pair, (case_gemm_batch_bias, 2, 1024, 640, 320)),
-    (case_pair, (case_gemm_dual, 1024, 640, 640, 320)),
-    (case_pair, (case_geglu, 512, 320)),
-    (case_pair, (case_geglu, 4096, 320)),
-    (case_pair, (case_conv, 1, 64, 64, 320, 320)),
-    (case_pair, (case_conv, 2, 32, 32, 640, 640, True, True)),
-    (case_pair, (case_conv, 3, 8, 8, 1280, 1280, True, True)),  # 192 rows: second CTA of the pair is half out of range
-    (case_pair, (case_conv, 2, 16, 16, 1280, 1280)),
+    # ---- persistent CTA-pair GEMM forced onto small and odd problems ----
+    (case_tuned, (PAIR, case_gemm, 512, 256, 128)),                       # 256-wide tile, 2 pairs, one K pass of 2 chunks
+    (case_tuned, (PAIR, case_gemm, 384, 320, 320, True, True)),           # odd M tiles: last pair half empty; bias+residual
+    (case_tuned, (PAIR, case_gemm, 1000, 640, 1280, True, False)),        # ragged M (TMA store clips rows)
+    (case_tuned, (PAIR, case_gemm, 300, 384, 192, True, True)),           # 128-wide tiles
+    (case_tuned, (PAIR, case_gemm, 4096, 320, 2880, True, True)),         # long K: ring wraps; 320-wide tile = full N
+    (case_tuned, (PAIR, case_gemm, 65536, 320, 320, True, True)),         # 512 tiles over 74 pairs: 7 rounds, both buffers
+    (case_tuned, (PAIR, case_gemm, 4096, 1280, 640, True, True)),         # 256-wide tiles, 5 N tiles (K too short for 320)
+    (case_tuned, (PAIR, case_gemm, 4096, 1280, 1280, True, True)),        # 320-wide tiles (2 x 160 MMAs, one accumulator)
+    (case_tuned, (PAIR, case_gemm, 1000, 640, 2560, True, True)),         # 320-wide, ragged M, 2 N tiles
+    (case_tuned, (PAIR, case_gemm, 520, 200, 128, True, True)),           # N = 200: last chunk 8 columns wide, 2nd half empty
+    (case_tuned, (PAIR, case_gemm_batch_bias, 2, 1024, 640, 320)),
+    (case_tuned, (PAIR, case_gemm_dual, 1024, 640, 640, 320)),
+    (case_tuned, (PAIR, case_gemm_strided_out, 320, 80, 768)),            # output row pitch > N
+    (case_tuned, (PAIR, case_geglu, 512, 320)),
+    (case_tuned, (PAIR, case_geglu, 4096, 320)),
+    (case_tuned, (PAIR, case_conv, 1, 64, 64, 320, 320)),
+    (case_tuned, (PAIR, case_conv, 8, 64, 64, 320, 320, True, True)),     # full-width conv tile: 128 pairs over 74 clusters
+    (case_tuned, (PAIR, case_conv, 2, 32, 32, 640, 640, True, True)),
+    (case_tuned, (PAIR, case_conv, 3, 8, 8, 1280, 1280, True, True)),     # 192 rows: second CTA of the pair half out of range
+    (case_tuned, (PAIR, case_conv, 16, 16, 16, 1280, 1280)),
+    # ---- the same large shapes on the single-CTA tiles (what the heuristics would not pick) ----
+    (case_tuned, (NOPAIR, case_gemm, 65536, 320, 320, True, True)),
+    (case_tuned, (NOPAIR, case_conv, 8, 64, 64, 320, 320, True, True)),
+    # ---- TMA-store epilogue of the single-CTA tiles ----
+    (case_tuned, (TMAST, case_gemm, 8192, 320, 320, True, True)),         # 160-wide tiles, K = 5 chunks
+    (case_tuned, (TMAST + NOPAIR, case_gemm, 16384, 640, 640, True, True)),
+    (case_tuned, (TMAST, case_gemm, 1000, 384, 192, True, True)),         # 128-wide tiles, ragged M
+    (case_tuned, (TMAST, case_gemm, 520, 200, 128, True, True)),          # N = 200: last box clipped by the tensor map
+    (case_tuned, (TMAST, case_gemm_batch_bias, 8, 1024, 640, 320)),
+    (case_tuned, (TMAST + NOPAIR, case_gemm_dual, 8192, 640, 640, 320)),
+    (case_tuned, (TMAST, case_gemm_strided_out, 320, 80, 768)),           # row pitch > N: columns beyond N stay untouched
+    (case_tuned, (TMAST + NOPAIR, case_geglu, 4096, 320)),
+    (case_tuned, (TMAST, case_geglu, 64, 1280)),
+    (case_tuned, (TMAST + NOPAIR, case_conv, 8, 32, 32, 640, 640, True, True)),
     (case_conv_direct, (1, 64, 64, 4, 320, 1, False, True)),
     (case_conv_direct, (2, 64, 64, 320, 4, 1, False)),
     (case_conv_direct, (1, 256, 256, 3, 16, 1, True)),
@@ -392,59 +390,11 @@ ALL_CASES = [
     (case_attention, (2, 8, 160, 64, 64, 64, 2)),
     (case_attention, (1, 8, 160, 16, 16, 16, 1)),
     (case_attention, (2, 8, 160, 256, 77, 0, 1, None, True)),
-]
-
-# ---- kernels written after the round's GPU budget was spent: compiled, never run.  NOT part of ALL_CASES (the
-# -m gpu suite must not depend on unvalidated code); `python scripts/gpu_diag.py --group pending` runs them one
-# by one under the caller's timeout (scripts/gpu_pending_checks.sh).  Move a case to ALL_CASES once it is green.
-_PAIRQ = (("MDB_GEMM_PAIR", "3"), ("MDB_GEMM_PAIR_MIN", "1"))     # persistent pair GEMM, TMA-store epilogue
-_PAIRS = (("MDB_GEMM_PAIR_SPLITK", "1"), ("MDB_GEMM_PAIR_SPLITK_MINK", "1"))                         # pair tiles + split-K inside the cluster
-_TMAST = (("MDB_GEMM_TMAST", "1"),)                              # default tiles, TMA-store epilogue (gemm_ts_kernel)
-PENDING_CASES = [
-    (case_env, (_TMAST, case_gemm, 8192, 320, 320, True, True)),          # 160-wide tiles, K = 5 chunks
-    (case_env, (_TMAST, case_gemm, 16384, 640, 640, True, True)),
-    (case_env, (_TMAST, case_gemm, 1000, 384, 192, True, True)),          # 128-wide tiles, ragged M
-    (case_env, (_TMAST, case_gemm, 520, 200, 128, True, True)),           # N = 200: last box clipped by the tensor map
-    (case_env, (_TMAST, case_gemm_batch_bias, 8, 1024, 640, 320)),
-    (case_env, (_TMAST, case_gemm_dual, 8192, 640, 640, 320)),
-    (case_env, (_TMAST, case_gemm_strided_out, 320, 80, 768)),            # row pitch > N: columns beyond N stay untouched
-    (case_env, (_TMAST, case_geglu, 4096, 320)),
-    (case_env, (_TMAST, case_geglu, 64, 1280)),
-    (case_env, (_TMAST, case_conv, 8, 32, 32, 640, 640, True, True)),
-    (case_env, (_PAIRQ, case_gemm, 512, 256, 128)),                       # 256-wide tile, 2 pairs, one K pass of 2 chunks
-    (case_env, (_PAIRQ, case_gemm, 384, 320, 320, True, True)),           # odd M tiles: last pair half empty; bias+residual
-    (case_env, (_PAIRQ, case_gemm, 1000, 640, 1280, True, False)),        # ragged M (TMA store clips rows)
-    (case_env, (_PAIRQ, case_gemm, 300, 384, 192, True, True)),           # 128-wide tiles
-    (case_env, (_PAIRQ, case_gemm, 4096, 320, 2880, True, True)),         # long K: ring wraps; 320-wide tile = full N
-    (case_env, (_PAIRQ, case_gemm, 65536, 320, 320, True, True)),         # 512 tiles over 74 pairs: 7 rounds, both buffers
-    (case_env, (_PAIRQ, case_gemm, 4096, 1280, 640, True, True)),         # 256-wide tiles, 5 N tiles (K too short for 320)
-    (case_env, (_PAIRQ, case_gemm, 4096, 1280, 1280, True, True)),        # 320-wide tiles (2 x 160 MMAs, one accumulator)
-    (case_env, (_PAIRQ, case_gemm, 1000, 640, 2560, True, True)),         # 320-wide, ragged M, 2 N tiles
-    (case_env, (_PAIRQ, case_conv, 8, 64, 64, 320, 320, True, True)),     # full-width conv tile: 128 pairs over 74 clusters
-    (case_env, (_PAIRQ, case_gemm, 520, 200, 128, True, True)),           # N = 200: last chunk 8 columns wide, 2nd half empty
-    (case_env, (_PAIRQ, case_gemm_batch_bias, 2, 1024, 640, 320)),
-    (case_env, (_PAIRQ, case_gemm_dual, 1024, 640, 640, 320)),
-    (case_env, (_PAIRQ, case_gemm_strided_out, 320, 80, 768)),            # output row pitch > N
-    (case_env, (_PAIRQ, case_geglu, 512, 320)),
-    (case_env, (_PAIRQ, case_geglu, 4096, 320)),
-    (case_env, (_PAIRQ, case_conv, 1, 64, 64, 320, 320)),
-    (case_env, (_PAIRQ, case_conv, 2, 32, 32, 640, 640, True, True)),
-    (case_env, (_PAIRQ, case_conv, 3, 8, 8, 1280, 1280, True, True)),     # 192 rows
-    (case_env, (_PAIRQ, case_conv, 16, 16, 16, 1280, 1280)),
-    (case_env, (_PAIRS, case_gemm, 256, 160, 512, True, True)),           # one pair, 8 K chunks -> S = 2
-    (case_env, (_PAIRS, case_gemm, 512, 1280, 1280, True, True)),         # 2 pairs x 8 N tiles x S=4
-    (case_env, (_PAIRS, case_gemm, 2048, 640, 640, True, True)),          # 8 pairs x 4 -> 64 CTAs, S = 2
-    (case_env, (_PAIRS, case_gemm, 8192, 320, 320, True, True)),          # 128 CTAs, S = 1 (reduce over itself)
-    (case_env, (_PAIRS, case_gemm, 384, 320, 1280, True, True)),          # odd M tiles
-    (case_env, (_PAIRS, case_gemm, 300, 384, 1024, True, False)),         # 128-wide tiles, ragged M
-    (case_env, (_PAIRS, case_gemm_batch_bias, 2, 1024, 640, 320)),
-    (case_env, (_PAIRS, case_gemm_dual, 1024, 640, 640, 320)),
-    (case_env, (_PAIRS, case_conv, 2, 16, 16, 1280, 1280, True, True)),   # the 16x16 level of one frame (cond+uncond)
-    (case_env, (_PAIRS, case_conv, 2, 32, 32, 640, 640, True, True)),     # -> 320-wide tiles, S = 4
-    (case_env, (_PAIRS, case_conv, 2, 64, 64, 320, 320, True, True)),     # -> 320-wide tile = full N, S = 2
-    (case_env, (_PAIRS, case_conv, 4, 8, 8, 1280, 1280, True, True)),     # 8x8 level: two images per 128-row tile
-    (case_env, (_PAIRS, case_conv, 3, 8, 8, 2560, 1280, True, False)),    # 192 rows: second CTA half out of range
-    (case_env, (_PAIRS + (("MDB_GEMM_PAIR_SPLITK_BN", "320"),), case_gemm, 384, 640, 1280, True, True)),   # 320-wide, odd M tiles
-    (case_env, (_PAIRS + (("MDB_GEMM_PAIR_SPLITK_BN", "320"),), case_gemm, 8192, 320, 320, True, True)),   # 320-wide, S = 1
-    (case_env, (_PAIRS + (("MDB_GEMM_PAIR_SPLITK_BN", "128"),), case_gemm, 512, 1280, 1280, True, True)),  # 128-wide forced
+    # ---- d=40 on the two-Q-tile kernel at two CTAs per SM (what large grids get) ----
+    (case_tuned, (ATT2Q, case_attention, 1, 8, 40, 4096, 4096)),
+    (case_tuned, (ATT2Q, case_attention, 2, 8, 40, 1024, 1024, 1024, 2)),
+    (case_tuned, (ATT2Q, case_attention, 2, 8, 40, 1024, 1024, 1024, 1, 1)),
+    (case_tuned, (ATT2Q, case_attention, 2, 8, 40, 1024, 77, 0, 1, None, True)),
+    (case_tuned, (ATT2Q, case_attention, 1, 8, 40, 384, 384, 128, 1)),
+    (case_attention, (16, 8, 40, 2048, 2048, 2048, 1, 8)),   # 2048 CTAs: the heuristics pick the two-Q-tile kernel
 ]

@@ -5,6 +5,17 @@ import os
 import pytest
 import torch
 
+
+def _full_manifest():
+    """key -> shape of the reference LDM's state dict: the three networks + 13 schedule buffers recorded by
+    oracle/make_golden.py, plus the 248 first_stage_model.* tensors recorded by oracle/make_golden_vae.py"""
+    import json
+    from magicdance_b200 import synth
+    manifest = dict(synth.load_manifest())
+    with open(os.path.join(os.path.dirname(synth.MANIFEST), "vae_manifest.json")) as f:
+        manifest.update(json.load(f))
+    return manifest
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 YAML = os.path.join(REPO, "model_lib", "ControlNet", "models", "cldm_v15_reference_only_pose.yaml")
 
@@ -35,7 +46,7 @@ def test_yaml_targets_resolve_to_dropin_classes(model):
 
 def test_state_dict_keys_and_shapes_equal_the_reference(model):
     from magicdance_b200 import synth
-    manifest = synth.load_manifest()  # recorded from the unmodified reference (oracle/make_golden.py)
+    manifest = _full_manifest()  # recorded from the unmodified reference
     ours = {k: list(v.shape) for k, v in model.state_dict().items()}
     assert ours == manifest
 
@@ -69,7 +80,7 @@ def test_training_entry_refuses_to_fake_gradients(model):
 
 def test_strict_load_of_a_reference_checkpoint_layout(model):
     from magicdance_b200 import synth
-    manifest = synth.load_manifest()
+    manifest = _full_manifest()
     sd = {k: torch.zeros(v) for k, v in manifest.items()}  # a checkpoint with exactly the reference's keys
     schedule = {k: v.clone() for k, v in model.state_dict().items() if k in synth.SCHEDULE_KEYS}
     try:
@@ -94,6 +105,7 @@ def test_dropin_apply_model_orchestration_matches_reference_small32(model, monke
     sd = synth.synth_state_dict(seed=0)
     own = model.state_dict()
     sd.update({k: own[k] for k in synth.SCHEDULE_KEYS})  # the 13 schedule buffers are derived, not synthesised
+    sd.update({k: own[k] for k in own if k.startswith("first_stage_model.")})  # the VAE is not on this test's path
     missing, unexpected = model.load_state_dict(sd, strict=True)
     assert not missing and not unexpected
     model._test_loaded_seed = 0
