@@ -47,7 +47,6 @@ int64_t mdb_abi_struct_bytes(int32_t which);
 /* Launch heuristics, process-wide.  The defaults are what the B200 measurements selected (profiles/); tests use the
  * setter to force a kernel variant onto small problems. */
 #define MDB_TUNE_GEMM_PAIR_MIN_TILES 1 /* grids of >= this many 128-row tiles use the persistent CTA-pair GEMM (128) */
-#define MDB_TUNE_GEMM_TMA_STORE 2      /* != 0: single-CTA GEMM tiles leave through shared memory + TMA stores (0)  */
 #define MDB_TUNE_ATTN40_2Q_MIN_CTAS 3  /* d=40 attention grids of >= this many CTAs use the two-Q-tile kernel (2048) */
 #define MDB_TUNE_GEMM_BN80_BELOW 4     /* N %% 160 == 0 layers with fewer 160-wide CTAs than this take 80-wide tiles (100) */
 int mdb_set_tuning(int32_t key, int32_t value);
@@ -84,8 +83,8 @@ typedef struct mdb_gemm_desc {
   const void* residual;       /* fp16 [M][N] added after bias, may be NULL                        */
   int64_t ldr;
   int32_t m, n, k;
-  int32_t splits;             /* >1: split-K over gridDim.z through splitk_ws                     */
-  float* splitk_ws;           /* fp32 [splits][M][N] scratch for the per-split partials (splits > 1 only) */
+  int32_t splits;             /* 0: automatic (1, 2, 4 or 8, in-cluster reduction); 1: none; >1: as given */
+  float* splitk_ws;           /* fp32 [splits][M][N] scratch, only for explicit split counts other than 2, 4, 8 */
 } mdb_gemm_desc;
 
 int mdb_gemm_f16(const mdb_gemm_desc* desc, mdb_stream_t stream);
@@ -172,8 +171,10 @@ int mdb_upsample2x_f16(const void* x, void* y, int32_t batch, int32_t h, int32_t
 int mdb_add_f16(const void* a, const void* b, void* y, int64_t n_per_batch, int32_t batch, int32_t b_batches,
                 mdb_stream_t stream);
 
-/* timestep_embedding (util.py:189-209): t int64 [B] -> fp32 [B][dim], [cos | sin], max_period 1e4 */
-int mdb_timestep_embedding_f32(const int64_t* t, float* out, int32_t batch, int32_t dim, mdb_stream_t stream);
+/* timestep_embedding (util.py:189-209): t int64 [t_count] -> fp32 [batch][dim], [cos | sin], max_period 1e4; row b
+ * uses t[b % t_count] (t_count = batch: one timestep per sample; fewer: the timesteps repeat, e.g. cond | uncond) */
+int mdb_timestep_embedding_f32(const int64_t* t, int32_t t_count, float* out, int32_t batch, int32_t dim,
+                               mdb_stream_t stream);
 
 /* Skinny Linear for the timestep path (rows <= 16): out[r][n] = sum_k f(x[r][k]) W[n][k] + bias[n],
  * f = SiLU when silu_in, fp32 in/out, fp16 weights.  Replaces time_embed (openaimodel.py:547-551)
@@ -190,7 +191,9 @@ int mdb_skinny_linear_f32(const float* x, const void* w, const float* bias, floa
 int mdb_softmax_rows_f16(void* x, int64_t ld, int32_t rows, int32_t cols, float scale, mdb_stream_t stream);
 
 /* layout/precision boundary: the reference passes NCHW fp32 tensors (cldm.py:1099) */
-int mdb_nchw_f32_to_nhwc_f16(const float* x, void* y, int32_t batch, int32_t c, int32_t h, int32_t w, mdb_stream_t stream);
+/* y holds the batch `copies` times over ([copies*batch][h][w][c]): the paired cond | uncond batch of p_sample_ddim */
+int mdb_nchw_f32_to_nhwc_f16(const float* x, void* y, int32_t batch, int32_t c, int32_t h, int32_t w, int32_t copies,
+                             mdb_stream_t stream);
 int mdb_nhwc_f16_to_nchw_f32(const void* x, float* y, int32_t batch, int32_t c, int32_t h, int32_t w, mdb_stream_t stream);
 
 /* CFG combine + DDIM update in one pass (ddim.py:605,617-645; eps-parameterisation):
@@ -198,9 +201,10 @@ int mdb_nhwc_f16_to_nchw_f32(const void* x, float* y, int32_t batch, int32_t c, 
  *   x_prev = sqrt(a_prev) pred_x0 + sqrt(1 - a_prev - sigma^2) e + sigma * noise   (noise may be NULL when sigma == 0)
  * all tensors fp32, n elements.  coef is a DEVICE array of 6 floats
  *   {scale, sqrt(a_t), sqrt(a_prev), sqrt(1 - a_prev - sigma^2), sigma, sqrt(1 - a_t)}
- * so that one captured CUDA graph serves every DDIM step. */
-int mdb_cfg_ddim_update_f32(const float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_prev,
-                            float* pred_x0, int64_t n, const float* coef, mdb_stream_t stream);
+ * so that one captured CUDA graph serves every DDIM step.  update_x != 0: x is overwritten with x_prev as well
+ * (the chain's state advances in place). */
+int mdb_cfg_ddim_update_f32(float* x, const float* eps_c, const float* eps_u, const float* noise, float* x_prev,
+                            float* pred_x0, int64_t n, const float* coef, int32_t update_x, mdb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -58,19 +58,19 @@ SIGNATURES = {
     "mdb_im2col3x3_br_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mdb_upsample2x_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mdb_add_f16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
-    "mdb_timestep_embedding_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "mdb_timestep_embedding_f32": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
     "mdb_skinny_linear_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                         c_int32, c_void_p]),
-    "mdb_nchw_f32_to_nhwc_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "mdb_nchw_f32_to_nhwc_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mdb_nhwc_f16_to_nchw_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mdb_softmax_rows_f16": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p]),
     "mdb_cfg_ddim_update_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                          c_void_p, c_void_p]),
+                                          c_void_p, c_int32, c_void_p]),
 }
 
 _lib = None
 ABI_VERSION = 2
-TUNE_GEMM_PAIR_MIN_TILES, TUNE_GEMM_TMA_STORE, TUNE_ATTN40_2Q_MIN_CTAS, TUNE_GEMM_BN80_BELOW = 1, 2, 3, 4
+TUNE_GEMM_PAIR_MIN_TILES, TUNE_ATTN40_2Q_MIN_CTAS, TUNE_GEMM_BN80_BELOW = 1, 3, 4
 
 
 def library_path() -> str:

@@ -750,219 +750,6 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// gemm_tc_kernel's plain path (one 128 x BN tile per CTA, no split-K, no cluster) with the TMA-store epilogue of
-// gemm_pair_kernel: each epilogue warp packs 32 rows x 32 columns of fp16 into the (by then idle) operand ring and
-// one lane issues a cp.async.bulk.tensor store, instead of every lane writing 16-byte pieces one row pitch apart.
-// For the short-K layers (q/k/v/out projections, 1x1 convs, GEGLU: K = 320 ... 1280) whose grid is too small for
-// the pair kernel: there the default epilogue takes longer than the main loop.
-// ------------------------------------------------------------------------------------------------
-template <int BN, bool GEGLU, int kStages>
-__global__ void __launch_bounds__(kGemmThreads, 2)
-    gemm_ts_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ CUtensorMap tmD) {
-  using S = GemmSmem<BN, kStages, false>;
-  static_assert(kStages * S::kStageBytes >= 4 * 2 * kOutBufBytes, "the staging buffers live in the operand ring");
-  static_assert(BN % 32 == 0, "every 32-column store box must lie inside the tile");
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kStages];
-  __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ __align__(8) uint64_t acc_bar;
-  __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float s_bias[BN];
-
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM;
-  const int n0 = blockIdx.y * BN;
-  const int n_iter = p.k_chunks;
-  constexpr uint32_t kTmemCols = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
-
-  pdl_launch_dependents();
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA);
-    tma_prefetch_desc(&p.tmB);
-    tma_prefetch_desc(&tmD);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(&acc_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
-  const bool bias_in_smem = (p.bias != nullptr) && (p.bias_batch_stride == 0);
-  if (bias_in_smem && warp >= 2) {
-    for (int j = threadIdx.x - 64; j < BN; j += 128) s_bias[j] = (n0 + j < p.n) ? p.bias[n0 + j] : 0.f;
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_smem;
-  pdl_wait();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int b0 = 0, y0 = 0;
-      if (p.conv) {
-        b0 = m0 / p.hw;
-        y0 = (p.hw >= kBM) ? (m0 % p.hw) / p.w : 0;
-      }
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * S::kStageBytes;
-        uint8_t* sb = sa + S::kABytes;
-        mbar_expect_tx(&full_bar[s], S::kStageBytes);
-        if (p.conv) {
-          const int tap = it / p.chunks_per_tap;
-          const int cc = it - tap * p.chunks_per_tap;
-          const int kh = tap / 3, kw = tap - kh * 3;
-          tma_load_4d(sa, &p.tmA, &full_bar[s], cc * kBK, kw - 1, y0 + kh - 1, b0);
-        } else if (it < p.k1_chunks) {
-          tma_load_2d(sa, &p.tmA, &full_bar[s], it * kBK, m0);
-        } else {
-          tma_load_2d(sa, &p.tmA2, &full_bar[s], (it - p.k1_chunks) * kBK, m0);
-        }
-        tma_load_2d(sb, &p.tmB, &full_bar[s], it * kBK, n0);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
-        const uint32_t b_addr = a_addr + S::kABytes;
-        const uint64_t da = umma_desc_k_sw128(a_addr);
-        const uint64_t db = umma_desc_k_sw128(b_addr);
-#pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[s]);
-      }
-      umma_commit(&acc_bar);
-    }
-  } else {
-    // ---------------- epilogue warps 2..5 ----------------
-    const int g = warp & 3;
-    const int row0 = m0 + g * 32;
-    const long long row = static_cast<long long>(row0) + lane;
-    const bool row_ok = row < p.m;
-    constexpr int kResVecs = (GEGLU ? 0 : ((BN + 31) / 32) * 4);
-    uint4 res_pref[kResVecs > 0 ? kResVecs : 1];
-    const bool have_res = !GEGLU && (p.residual != nullptr);
-    if constexpr (!GEGLU) {
-      if (have_res) {
-        const __half* rrow = p.residual + row * p.ldr + n0;
-#pragma unroll
-        for (int q = 0; q < kResVecs; ++q) {
-          if (row_ok && q * 8 + 8 <= BN && n0 + q * 8 + 8 <= p.n) res_pref[q] = *reinterpret_cast<const uint4*>(rrow + q * 8);
-          else res_pref[q] = make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
-    }
-    const long long brow = (p.bias_batch_stride != 0) ? (row / p.rows_per_batch) : 0;
-    mbar_wait(&acc_bar, 0);  // every MMA has completed: the operand ring is idle and becomes the staging area
-    tc_fence_after_sync();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
-    uint8_t* obuf = smem + (warp - 2) * (2 * kOutBufBytes);
-    uint32_t ob = 0;
-    constexpr int kUnits = GEGLU ? BN / 64 : (BN + 31) / 32;
-#pragma unroll
-    for (int u = 0; u < kUnits; ++u) {
-      const int col0 = n0 + u * (GEGLU ? 64 : 32);
-      if (col0 >= p.n) break;  // warp-uniform
-      uint4 o4[4];
-      if constexpr (!GEGLU) {
-        uint32_t r[32];
-        tmem_ld_x32(taddr + u * 32, r);
-        tmem_wait_ld();
-        const int ncols = min(32, p.n - col0);
-        const float* bp = nullptr;
-        if (bias_in_smem) bp = s_bias + u * 32;
-        else if (p.bias != nullptr && row_ok) bp = p.bias + brow * p.bias_batch_stride + col0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[q * 8 + e]);
-          if (bp != nullptr && q * 8 + 8 <= ncols) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bp + q * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bp + q * 8 + 4);
-            o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-            o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-          }
-          if (have_res) {
-            const __half2* h2 = reinterpret_cast<const __half2*>(&res_pref[u * 4 + q]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __half22float2(h2[e]);
-              o[2 * e] += f.x;
-              o[2 * e + 1] += f.y;
-            }
-          }
-          o4[q].x = pack_half2(o[0], o[1]);
-          o4[q].y = pack_half2(o[2], o[3]);
-          o4[q].z = pack_half2(o[4], o[5]);
-          o4[q].w = pack_half2(o[6], o[7]);
-        }
-      } else {
-        uint32_t rv[32], rg[32];
-        tmem_ld_x32(taddr + u * 64, rv);
-        tmem_ld_x32(taddr + u * 64 + 32, rg);
-        tmem_wait_ld();
-        const float* bp = nullptr;
-        if (bias_in_smem) bp = s_bias + u * 64;
-        else if (p.bias != nullptr && row_ok) bp = p.bias + brow * p.bias_batch_stride + col0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int j = q * 8 + e;
-            float a = __uint_as_float(rv[j]);
-            float gt = __uint_as_float(rg[j]);
-            if (bp != nullptr) {
-              a += bp[j];
-              gt += bp[32 + j];
-            }
-            o[e] = a * gelu_erf_poly_f(gt);
-          }
-          o4[q].x = pack_half2(o[0], o[1]);
-          o4[q].y = pack_half2(o[2], o[3]);
-          o4[q].z = pack_half2(o[4], o[5]);
-          o4[q].w = pack_half2(o[6], o[7]);
-        }
-      }
-      uint8_t* sbuf = obuf + ob * kOutBufBytes;
-      if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago has finished reading this buffer
-      __syncwarp();
-      uint4* srow = reinterpret_cast<uint4*>(sbuf + lane * (kOutBox * 2));
-#pragma unroll
-      for (int q = 0; q < 4; ++q) srow[q] = o4[q];
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0 && row0 < p.m) {
-        tma_store_2d(&tmD, sbuf, GEGLU ? (col0 >> 1) : col0, row0);
-        tma_store_commit();
-      }
-      ob ^= 1u;
-    }
-    if (lane == 0) tma_store_wait_all();
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after_sync();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
 // split-K second pass: sum of the fp32 partial slabs ws[splits][M][N] -> bias/residual -> fp16 D
 __global__ void splitk_finalize_kernel(GemmKParams p) {
   pdl_launch_dependents();
@@ -1074,8 +861,8 @@ void count_launch(int n = 1);
 
 // launch heuristics (mdb_set_tuning): defaults selected by the B200 measurements under profiles/
 static int g_pair_min_tiles = 128;  // smallest grid, in 128-row tile equivalents, that goes to gemm_pair_kernel
-static int g_tma_store = 0;         // single-CTA tiles through the TMA-store epilogue (gemm_ts_kernel)
 static int g_bn80_below = 100;      // N % 160 == 0 layers with fewer 160-wide CTAs than this use 80-wide tiles
+constexpr int kLongKChunks = 64;    // ... unless K >= 4096 (automatic split-K): then 160-wide tiles and split K
 
 template <int BN, bool GEGLU, int STAGES>
 static int launch_gemm(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
@@ -1122,27 +909,10 @@ static int launch_gemm_pair(const GemmKParams& kp, const CUtensorMap& tmD, int t
   return MDB_OK;
 }
 
-template <int BN, bool GEGLU, int STAGES>
-static int launch_gemm_ts(const GemmKParams& kp, const CUtensorMap& tmD, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
-  auto kern = gemm_ts_kernel<BN, GEGLU, STAGES>;
-  constexpr int kSmem = GemmSmem<BN, STAGES, false>::kTotal;
-  if (!attr_set) {
-    MDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_set = true;
-  }
-  MDB_CHECK_CUDA(launch_pdl(kern, grid, dim3(kGemmThreads), kSmem, st, kp, tmD));
-  count_launch();
-  return MDB_OK;
-}
-
-int get_gemm_tuning(int key) {
-  return key == MDB_TUNE_GEMM_PAIR_MIN_TILES ? g_pair_min_tiles : (key == MDB_TUNE_GEMM_BN80_BELOW ? g_bn80_below : g_tma_store);
-}
+int get_gemm_tuning(int key) { return key == MDB_TUNE_GEMM_PAIR_MIN_TILES ? g_pair_min_tiles : g_bn80_below; }
 void set_gemm_tuning(int key, int value) {
   if (key == MDB_TUNE_GEMM_PAIR_MIN_TILES) g_pair_min_tiles = value;
-  else if (key == MDB_TUNE_GEMM_BN80_BELOW) g_bn80_below = value;
-  else g_tma_store = value;
+  else g_bn80_below = value;
 }
 
 }  // namespace mdb
@@ -1243,9 +1013,12 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     MDB_REQUIRE(g->n % 128 == 0, "mdb_gemm_f16: GEGLU needs N %% 128 == 0 (N=%d)", g->n);
     bn = 128;
   } else if (g->n % 160 == 0) {
-    // 160-wide tiles unless that leaves most of the 148 SMs idle; then halve the tile width
+    // 160-wide tiles unless that leaves most of the 148 SMs idle; then (short K) halve the tile width, or (long K:
+    // the weight-streaming 3x3 convs of the 8x8 ... 32x32 levels at one frame) keep the wide tile and split K —
+    // see auto_splits below and profiles/r02_deepk_microbench.md
     const long long tiles160 = (long long)m_tiles * (g->n / 160) * (g->splits > 1 ? g->splits : 1);
-    bn = (tiles160 < g_bn80_below) ? 80 : 160;
+    const bool wide_split = g->splits == 0 && kp.k_chunks >= kLongKChunks && tiles160 * 2 <= 148;
+    bn = (tiles160 < g_bn80_below && !wide_split) ? 80 : 160;
   } else {
     bn = 128;
   }
@@ -1259,6 +1032,18 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   }
 
   int splits = g->splits > 1 ? g->splits : 1;
+  if (g->splits == 0 && !geglu && !pair) {
+    // automatic split-K: a power of two up to 8 (reduced inside a thread-block cluster through DSMEM) that brings
+    // the grid to about one CTA per SM while every split keeps at least 16 K chunks (measured on B200 with cold
+    // weights: below that the cluster reduction costs more than the extra CTAs gain)
+    const long long tiles = (long long)m_tiles * ((g->n + bn - 1) / bn);
+    if (tiles < 100)
+      for (int c = 8; c >= 2; c >>= 1)
+        if (tiles * c <= 148 && kp.k_chunks / c >= 16) {
+          splits = c;
+          break;
+        }
+  }
   if (splits > kp.k_chunks) splits = kp.k_chunks;
   if (geglu || pair) splits = 1;
   kp.chunks_per_split = (kp.k_chunks + splits - 1) / splits;
@@ -1274,18 +1059,14 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
 
   dim3 grid(m_tiles, (g->n + bn - 1) / bn, splits);
   const bool deep = (long long)grid.x * grid.y * grid.z <= 148 && kp.chunks_per_split >= 12;
-  const bool tma_store = !pair && g_tma_store != 0 && splits == 1 && !deep && g->n % 8 == 0 && bn != 80;
-  CUtensorMap tmD;
-  if (pair || tma_store) {
-    // output tensor map of the TMA-store epilogues: [M][N_out] fp16, 32 x 32 boxes, dense (no swizzle);
-    // an 80-wide tile ends in a 16-column chunk whose 32-wide box would spill into the neighbouring tile
+  if (pair) {
+    // output tensor map of the TMA-store epilogue: [M][N_out] fp16, 32 x 32 boxes, dense (no swizzle)
+    CUtensorMap tmD;
     uint32_t boxd[2] = {(uint32_t)kOutBox, (uint32_t)kOutBox};
     uint64_t dimsd[2] = {(uint64_t)(geglu ? g->n / 2 : g->n), (uint64_t)g->m};
     uint64_t strd[1] = {(uint64_t)g->ldd * 2};
     rc = make_tmap_f16_plain(&tmD, g->d, 2, dimsd, strd, boxd);
     if (rc) return rc;
-  }
-  if (pair) {
     const int total_tiles = ((m_tiles + 1) / 2) * (int)grid.y;
     if (geglu) return launch_gemm_pair<256, true, 5>(kp, tmD, total_tiles, st);
     if (bn == 320) return launch_gemm_pair<320, false, 5>(kp, tmD, total_tiles, st);
@@ -1293,11 +1074,7 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     if (bn == 256) return launch_gemm_pair<256, false, 5>(kp, tmD, total_tiles, st);
     return launch_gemm_pair<128, false, 6>(kp, tmD, total_tiles, st);
   }
-  if (tma_store) {
-    if (geglu) rc = launch_gemm_ts<128, true, 3>(kp, tmD, grid, st);
-    else if (bn == 160) rc = launch_gemm_ts<160, false, 3>(kp, tmD, grid, st);
-    else rc = launch_gemm_ts<128, false, 3>(kp, tmD, grid, st);
-  } else if (geglu) rc = launch_gemm<128, true, 3>(kp, grid, st);
+  if (geglu) rc = launch_gemm<128, true, 3>(kp, grid, st);
   else if (bn == 160) rc = deep ? launch_gemm<160, false, 6>(kp, grid, st) : launch_gemm<160, false, 3>(kp, grid, st);
   else if (bn == 80) rc = deep ? launch_gemm<80, false, 8>(kp, grid, st) : launch_gemm<80, false, 3>(kp, grid, st);
   else rc = deep ? launch_gemm<128, false, 6>(kp, grid, st) : launch_gemm<128, false, 3>(kp, grid, st);

@@ -335,7 +335,8 @@ __global__ void add_kernel(const __half* __restrict__ a, const __half* __restric
   }
 }
 
-__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int batch, int dim) {
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int batch, int dim,
+                                          int t_count) {
   pdl_launch_dependents();
   pdl_wait();
   const int half = dim / 2;
@@ -343,7 +344,7 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* 
   if (i >= batch * half) return;
   const int b = i / half, k = i % half;
   const float freq = expf(-logf(10000.0f) * static_cast<float>(k) / static_cast<float>(half));
-  const float arg = static_cast<float>(t[b]) * freq;
+  const float arg = static_cast<float>(t[b % t_count]) * freq;  // t_count < batch: the timesteps repeat (cond | uncond)
   out[b * dim + k] = cosf(arg);
   out[b * dim + half + k] = sinf(arg);
 }
@@ -398,11 +399,12 @@ __global__ void skinny_linear_kernel(const float* __restrict__ x, const __half* 
   }
 }
 
+// copies > 1: the output holds the batch `copies` times over (the paired cond | uncond batch of p_sample_ddim)
 __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int batch, int c, int h,
-                                            int w) {
+                                            int w, int copies) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long total = static_cast<long long>(batch) * c * h * w;
+  const long long total = static_cast<long long>(batch) * copies * c * h * w;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     // i indexes the NHWC output
@@ -410,7 +412,7 @@ __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half*
     long long r = i / c;
     const int xx = static_cast<int>(r % w);
     const int yy = static_cast<int>((r / w) % h);
-    const int b = static_cast<int>(r / (static_cast<long long>(w) * h));
+    const int b = static_cast<int>(r / (static_cast<long long>(w) * h)) % batch;
     y[i] = __float2half_rn(x[((static_cast<long long>(b) * c + ch) * h + yy) * w + xx]);
   }
 }
@@ -433,10 +435,10 @@ __global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, float*
   }
 }
 
-__global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ ec,
-                                       const float* __restrict__ eu, const float* __restrict__ noise,
-                                       float* __restrict__ x_prev, float* __restrict__ pred_x0, long long n,
-                                       const float* __restrict__ coef) {
+__global__ void cfg_ddim_update_kernel(float* x, const float* __restrict__ ec, const float* __restrict__ eu,
+                                       const float* __restrict__ noise, float* __restrict__ x_prev,
+                                       float* __restrict__ pred_x0, long long n, const float* __restrict__ coef,
+                                       int update_x) {
   pdl_launch_dependents();
   pdl_wait();
   // coef (device, so one captured CUDA graph serves all 50 steps):
@@ -452,6 +454,7 @@ __global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float*
     if (noise != nullptr) xp += sigma * noise[i];
     x_prev[i] = xp;
     pred_x0[i] = p0;
+    if (update_x) x[i] = xp;  // the chain's state advances in place: the next step reads x
   }
 }
 
@@ -483,7 +486,6 @@ extern "C" int64_t mdb_abi_struct_bytes(int32_t which) {
 extern "C" int mdb_set_tuning(int32_t key, int32_t value) {
   switch (key) {
     case MDB_TUNE_GEMM_PAIR_MIN_TILES:
-    case MDB_TUNE_GEMM_TMA_STORE:
     case MDB_TUNE_GEMM_BN80_BELOW:
       mdb::set_gemm_tuning(key, value);
       return MDB_OK;
@@ -695,11 +697,12 @@ extern "C" int mdb_add_f16(const void* a, const void* b, void* y, int64_t n_per_
   return MDB_OK;
 }
 
-extern "C" int mdb_timestep_embedding_f32(const int64_t* t, float* out, int32_t batch, int32_t dim, mdb_stream_t stream) {
-  MDB_REQUIRE(t && out && dim % 2 == 0, "mdb_timestep_embedding_f32: bad arguments");
+extern "C" int mdb_timestep_embedding_f32(const int64_t* t, int32_t t_count, float* out, int32_t batch, int32_t dim,
+                                          mdb_stream_t stream) {
+  MDB_REQUIRE(t && out && dim % 2 == 0 && t_count >= 1 && batch % t_count == 0, "mdb_timestep_embedding_f32: bad arguments");
   const int total = batch * dim / 2;
   MDB_CHECK_CUDA(launch_pdl(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0,
-                            static_cast<cudaStream_t>(stream), t, out, batch, dim));
+                            static_cast<cudaStream_t>(stream), t, out, batch, dim, t_count));
   count_launch();
   return MDB_OK;
 }
@@ -726,11 +729,11 @@ extern "C" int mdb_skinny_linear_f32(const float* x, const void* w, const float*
 }
 
 extern "C" int mdb_nchw_f32_to_nhwc_f16(const float* x, void* y, int32_t batch, int32_t c, int32_t h, int32_t w,
-                                        mdb_stream_t stream) {
-  MDB_REQUIRE(x && y, "mdb_nchw_f32_to_nhwc_f16: null pointer");
-  const long long total = static_cast<long long>(batch) * c * h * w;
+                                        int32_t copies, mdb_stream_t stream) {
+  MDB_REQUIRE(x && y && copies >= 1, "mdb_nchw_f32_to_nhwc_f16: bad arguments");
+  const long long total = static_cast<long long>(batch) * copies * c * h * w;
   MDB_CHECK_CUDA(launch_pdl(nchw_f32_to_nhwc_f16_kernel, dim3(grid_for(total)), dim3(256), 0,
-                            static_cast<cudaStream_t>(stream), x, static_cast<__half*>(y), batch, c, h, w));
+                            static_cast<cudaStream_t>(stream), x, static_cast<__half*>(y), batch, c, h, w, copies));
   count_launch();
   return MDB_OK;
 }
@@ -745,12 +748,12 @@ extern "C" int mdb_nhwc_f16_to_nchw_f32(const void* x, float* y, int32_t batch, 
   return MDB_OK;
 }
 
-extern "C" int mdb_cfg_ddim_update_f32(const float* x, const float* eps_c, const float* eps_u, const float* noise,
-                                       float* x_prev, float* pred_x0, int64_t n, const float* coef,
+extern "C" int mdb_cfg_ddim_update_f32(float* x, const float* eps_c, const float* eps_u, const float* noise,
+                                       float* x_prev, float* pred_x0, int64_t n, const float* coef, int32_t update_x,
                                        mdb_stream_t stream) {
   MDB_REQUIRE(x && eps_c && eps_u && x_prev && pred_x0 && coef && n > 0, "mdb_cfg_ddim_update_f32: bad arguments");
   MDB_CHECK_CUDA(launch_pdl(cfg_ddim_update_kernel, dim3(grid_for(n)), dim3(256), 0, static_cast<cudaStream_t>(stream),
-                            x, eps_c, eps_u, noise, x_prev, pred_x0, static_cast<long long>(n), coef));
+                            x, eps_c, eps_u, noise, x_prev, pred_x0, static_cast<long long>(n), coef, update_x));
   count_launch();
   return MDB_OK;
 }

@@ -254,28 +254,6 @@ def _igemm_ok(h, w, c):
     return 128 % hw == 0
 
 
-def _auto_splits(m, n, k):
-    """Split-K factor: small-M layers (8x8 / 16x16 latents) would otherwise run on a handful of SMs and
-    stream their weights at a fraction of HBM bandwidth.  Mirrors the tile choice of mdb_gemm_f16:
-    160-wide tiles, 80-wide when that leaves most SMs idle; split K only if still under ~100 CTAs."""
-    mt = (m + 127) // 128
-    if n % 160 == 0:
-        tiles = mt * (n // 160)
-        if tiles < 100:
-            tiles *= 2  # the kernel switches to 80-wide tiles
-    else:
-        tiles = mt * ((n + 127) // 128)
-    chunks = k // 64
-    if tiles >= 100 or chunks < 8:
-        return 1
-    want = max(1, min(16, 148 // tiles, chunks // 4))
-    # powers of two up to 8 run as a thread-block cluster with an in-kernel DSMEM reduction
-    for s_ in (8, 4, 2):
-        if want >= s_:
-            return s_
-    return 1
-
-
 class _BankComplete(Exception):
     """unwinds appearance_write as soon as the last norm1 state is in the bank"""
 
@@ -304,10 +282,13 @@ class DenoiseEngine:
         return self
 
     # ---- small pieces -------------------------------------------------------------------------
-    def time_bias(self, net: PackedNet, t: torch.Tensor):
+    def time_bias(self, net: PackedNet, t: torch.Tensor, rows=None):
         """timestep_embedding -> time_embed MLP -> all emb_layers of the net (util.py:189-209,
-        openaimodel.py:547-551,238-244).  Returns fp32 [B, sum(cout)] = emb_out + conv1 bias."""
-        e = ops.timestep_embedding(t, self.cfg.model_channels)
+        openaimodel.py:547-551,238-244).  Returns fp32 [rows, sum(cout)] = emb_out + conv1 bias; t may hold fewer
+        entries than rows (one timestep for the whole batch; the cond | uncond pair): row b uses t[b % len(t)]."""
+        if t.shape[0] == 1:
+            rows = 1  # one timestep for the whole batch: ONE bias row, shared by every sample (bias_batch_stride 0)
+        e = ops.timestep_embedding(t, self.cfg.model_channels, rows)
         e = ops.skinny_linear(e, net.te0_w, net.te0_b, silu_out=True)
         e = ops.skinny_linear(e, net.te2_w, net.te2_b)
         return ops.skinny_linear(e, net.emb_w, net.emb_b, silu_in=True)
@@ -342,14 +323,14 @@ class DenoiseEngine:
         if _igemm_ok(x.h, x.w, cin) and cout % 8 == 0 and cout >= 64:
             m = x.b * x.hw
             y = ops.gemm(x.data, w, bias=bias, bias_batch_stride=bias_batch_stride, rows_per_batch=x.hw,
-                         residual=residual, conv=(x.b, x.h, x.w, cin), splits=_auto_splits(m, cout, 9 * cin))
+                         residual=residual, conv=(x.b, x.h, x.w, cin))
         elif cin % 64 == 0 and cout % 8 == 0 and cout >= 64:
             # latent sizes whose rows do not tile into 128-pixel TMA boxes (e.g. 96x64 -> 12x8 at the deepest
             # level): explicit im2col + the same tensor-core GEMM
             m = x.b * x.hw
             col = ops.im2col3x3(x.data, batch=x.b, h=x.h, w=x.w, c=cin, stride=1)
             y = ops.gemm(col, w, bias=bias, bias_batch_stride=bias_batch_stride, rows_per_batch=x.hw,
-                         residual=residual, splits=_auto_splits(m, cout, 9 * cin))
+                         residual=residual)
         else:
             assert bias_batch_stride == 0
             y = ops.conv3x3_direct(x.data, w, bias, batch=x.b, h=x.h, w=x.w, cin=cin, cout=cout, residual=residual)
@@ -381,11 +362,11 @@ class DenoiseEngine:
             res, join = x.data, (lambda: None)
         else:
             m = x.b * x.hw
-            res, join = self._fork(lambda: ops.gemm(x.data, r.skip_w, bias=r.skip_b, a2=x2,
-                                                    splits=_auto_splits(m, r.cout, r.cin)))
+            res, join = self._fork(lambda: ops.gemm(x.data, r.skip_w, bias=r.skip_b, a2=x2))
         h = ops.groupnorm(x.data, *r.gn1, batch=x.b, hw=x.hw, eps=1e-5, silu=True, x2=x2)
         bias = emb_all[:, r.emb_off:r.emb_off + r.cout]
-        h = self._conv3(Act(h, x.b, x.h, x.w), r.w1, bias, cout=r.cout, bias_batch_stride=emb_all.stride(0))
+        h = self._conv3(Act(h, x.b, x.h, x.w), r.w1, bias, cout=r.cout,
+                        bias_batch_stride=emb_all.stride(0) if emb_all.shape[0] > 1 else 0)
         h2 = ops.groupnorm(h.data, *r.gn2, batch=x.b, hw=x.hw, eps=1e-5, silu=True)
         join()
         return self._conv3(Act(h2, x.b, x.h, x.w), r.w2, r.b2, cout=r.cout, residual=res)
@@ -394,7 +375,7 @@ class DenoiseEngine:
         b, n, c = x.b, x.hw, a.c
         m = b * n
         h = ops.groupnorm(x.data, *a.gn, batch=b, hw=n, eps=1e-6, silu=False)
-        h = ops.gemm(h, a.pin_w, bias=a.pin_b, splits=_auto_splits(m, c, c))
+        h = ops.gemm(h, a.pin_w, bias=a.pin_b)
         # --- attn1 (self / self + bank) ---
         n1 = ops.layernorm(h, *a.ln1)
         if mode == "write":
@@ -403,27 +384,27 @@ class DenoiseEngine:
                 # the LAST bank entry has been produced: everything after it in the appearance net (this
                 # block's attentions and feed-forward, the rest of the decoder) is dead compute
                 raise _BankComplete()
-        vt, join_v = self._fork(lambda: ops.gemm(a.wv, n1, splits=_auto_splits(c, m, c)))  # [C, B*N] == V^T
-        qk = ops.gemm(n1, a.wqk, splits=_auto_splits(m, 2 * c, c))
+        vt, join_v = self._fork(lambda: ops.gemm(a.wv, n1))  # [C, B*N] == V^T
+        qk = ops.gemm(n1, a.wqk)
         join_v()
         kw = {}
         if mode == "read" and bank_kv is not None:
             k1, vt1, nb1, kvb1 = bank_kv
             kw = dict(k1=k1, vt1=vt1, n1=nb1, kv1_batches=kvb1, bank_batches=min(bank_batches, b))
         at = ops.attention(qk[:, :c], qk[:, c:], vt, n, heads=a.heads, d=a.d, batch=b, nq=n, **kw)
-        h = ops.gemm(at, a.wo, bias=a.bo, residual=h, splits=_auto_splits(m, c, c))
+        h = ops.gemm(at, a.wo, bias=a.bo, residual=h)
         # --- attn2 (text) ---
         n2 = ops.layernorm(h, *a.ln2)
-        q2 = ops.gemm(n2, a.wq2, splits=_auto_splits(m, c, c))
+        q2 = ops.gemm(n2, a.wq2)
         kt, vtt, nt, kvb, ldv = ctx_kv
         at2 = ops.attention(q2, kt, vtt, nt, heads=a.heads, d=a.d, batch=b, nq=n, kv0_batches=kvb if kvb == b else 1,
                             ldv0_batch=ldv)
-        h = ops.gemm(at2, a.wo2, bias=a.bo2, residual=h, splits=_auto_splits(m, c, c))
+        h = ops.gemm(at2, a.wo2, bias=a.bo2, residual=h)
         # --- GEGLU feed-forward ---
         n3 = ops.layernorm(h, *a.ln3)
         ff = ops.gemm(n3, a.wff1, bias=a.bff1, epilogue=ops.EPI_GEGLU)
-        h = ops.gemm(ff, a.wff2, bias=a.bff2, residual=h, splits=_auto_splits(m, c, 4 * c))
-        y = ops.gemm(h, a.pout_w, bias=a.pout_b, residual=x.data, splits=_auto_splits(m, c, c))
+        h = ops.gemm(ff, a.wff2, bias=a.bff2, residual=h)
+        y = ops.gemm(h, a.pout_w, bias=a.pout_b, residual=x.data)
         return Act(y, x.b, x.h, x.w)
 
     def _run_block(self, net, bp, blk, x: Act, skip, emb_all, ctx_kvs, state):
@@ -444,7 +425,7 @@ class DenoiseEngine:
             elif kind == "down":
                 col = ops.im2col3x3(x.data, batch=x.b, h=x.h, w=x.w, c=x.c, stride=2)
                 ho, wo = (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1
-                y = ops.gemm(col, lw[0], bias=lw[1], splits=_auto_splits(x.b * ho * wo, cout, 9 * cin))
+                y = ops.gemm(col, lw[0], bias=lw[1])
                 x = Act(y, x.b, ho, wo)
             elif kind == "up":
                 up = ops.upsample2x(x.data, batch=x.b, h=x.h, w=x.w, c=x.c)
@@ -452,10 +433,10 @@ class DenoiseEngine:
         return x
 
     # ---- the three networks -------------------------------------------------------------------
-    def _prep(self, x_nchw, context):
+    def _prep(self, x_nchw, context, copies=1):
         x = x_nchw.to(device=self.device, dtype=torch.float32)
         b, c, h, w = x.shape
-        act = Act(ops.nchw_f32_to_nhwc_f16(x), b, h, w)
+        act = Act(ops.nchw_f32_to_nhwc_f16(x, copies=copies), copies * b, h, w)
         ctx16 = context.to(device=self.device, dtype=torch.float16).contiguous()
         # cache key: storage address + view geometry + version counter (in-place edits invalidate).  The cache
         # entry holds a strong reference to the tensor, so the storage cannot be freed and its address recycled
@@ -471,7 +452,7 @@ class DenoiseEngine:
         net = self.appearance
         x, ctx16, key = self._prep(ref_latent, context)
         ctx_kvs = self.context_kv(net, ctx16, key)
-        emb_all = self.time_bias(net, t)
+        emb_all = self.time_bias(net, t, x.b)
         n_total = len(net.attn_layers())
         # in write mode `bank_batches` carries the number of bank entries after which the pass may stop
         state = {"mode": "write", "attn_i": 0, "bank": [], "bank_batches": n_total}
@@ -518,8 +499,8 @@ class DenoiseEngine:
             c = a.c
             rows = n1.shape[0]
             ko, vo = (out[i][0], out[i][1]) if out is not None else (None, None)
-            k1 = ops.gemm(n1, a.wqk[c:], out=ko, splits=_auto_splits(rows, c, c))
-            vt1 = ops.gemm(a.wv, n1, out=vo, splits=_auto_splits(c, rows, c))
+            k1 = ops.gemm(n1, a.wqk[c:], out=ko)
+            vt1 = ops.gemm(a.wv, n1, out=vo)
             res.append((k1, vt1, rows // batches, batches))
         return res
 
@@ -544,17 +525,17 @@ class DenoiseEngine:
         net = self.pose
         x, ctx16, key = self._prep(x_noisy, context)
         ctx_kvs = self.context_kv(net, ctx16, key)
-        emb_all = self.time_bias(net, t)
+        emb_all = self.time_bias(net, t, x.b)
         state = {"mode": "plain", "attn_i": 0, "hint": hint_feat}
         outs = []
         for i, blk in enumerate(net.inp):
             x = self._run_block(net, f"input_blocks.{i}.", blk, x, None, emb_all, ctx_kvs, state)
             state["hint"] = None
             zw, zb = net.zero[i]
-            outs.append(ops.gemm(x.data, zw, bias=zb, splits=_auto_splits(x.b * x.hw, x.c, x.c)))
+            outs.append(ops.gemm(x.data, zw, bias=zb))
         x = self._run_block(net, "middle_block.", net.mid, x, None, emb_all, ctx_kvs, state)
         zw, zb = net.zero[-1]
-        outs.append(ops.gemm(x.data, zw, bias=zb, splits=_auto_splits(x.b * x.hw, x.c, x.c)))
+        outs.append(ops.gemm(x.data, zw, bias=zb))
         return outs
 
     def unet_forward(self, x_noisy, t, context, bank_kv=None, pose=None, uc=False, taps=None, cfg_pair=False,
@@ -568,20 +549,15 @@ class DenoiseEngine:
         layer streams its weights once and sees twice the rows; samples [0,B) read the bank and take the
         pose residuals, samples [B,2B) do neither.  Returns (eps_cond, eps_uncond)."""
         net = self.unet
-        x, ctx16, key = self._prep(x_noisy, context)
-        b = x.b
+        x, ctx16, key = self._prep(x_noisy, context, copies=2 if cfg_pair else 1)
+        b = x_noisy.shape[0]
         if cfg_pair:
-            assert not uc and 2 * b <= 16, "cfg_pair needs 2*B <= 16 (timestep MLP kernel limit)"
-            both = torch.empty((2 * b * x.hw, x.c), dtype=torch.float16, device=self.device)
-            both[:b * x.hw].copy_(x.data)
-            both[b * x.hw:].copy_(x.data)
-            x = Act(both, 2 * b, x.h, x.w)
-            t = torch.cat([t, t])
+            assert not uc
             if ctx16.shape[0] > 1:
                 ctx16 = torch.cat([ctx16, ctx16])
                 key = (key[0], key[1], key[2] + ("pair",), key[3])
         ctx_kvs = self.context_kv(net, ctx16, key)
-        emb_all = self.time_bias(net, t)
+        emb_all = self.time_bias(net, t, x.b)  # the pair repeats the timesteps: row b uses t[b % B]
         state = {"mode": "plain" if uc else "read", "attn_i": 0}
         pose = None if (uc or pose is None) else list(pose)
         state["bank_kv"] = None if uc else bank_kv

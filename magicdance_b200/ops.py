@@ -22,7 +22,7 @@ class tuning:
     """`with ops.tuning(pair_min_tiles=1):` — the library's launch heuristics (include/magicdance_b200.h
     mdb_set_tuning) for the duration of the block; tests use it to force a kernel variant onto small problems.
     Launches captured into CUDA graphs keep the variant they were captured with."""
-    _KEYS = {"pair_min_tiles": _lib.TUNE_GEMM_PAIR_MIN_TILES, "tma_store": _lib.TUNE_GEMM_TMA_STORE,
+    _KEYS = {"pair_min_tiles": _lib.TUNE_GEMM_PAIR_MIN_TILES,
              "attn40_2q_min_ctas": _lib.TUNE_ATTN40_2Q_MIN_CTAS, "bn80_below": _lib.TUNE_GEMM_BN80_BELOW}
 
     def __init__(self, **kw):
@@ -121,9 +121,11 @@ def _workspace(key, numel, dtype, device, zero=False):
 
 
 def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, residual=None, epilogue=EPI_NONE,
-         a2=None, conv=None, splits=1, m=None):
+         a2=None, conv=None, splits=0, m=None):
     """D = epilogue(A @ W^T).  a: [M, K1] fp16 (last dim contiguous, row stride arbitrary) or, with
-    conv=(nb, h, w, c), an NHWC activation; w: [N, K] fp16; a2: optional second K-range source."""
+    conv=(nb, h, w, c), an NHWC activation; w: [N, K] fp16; a2: optional second K-range source.
+    splits: 0 = the library picks tile width and split-K (1/2/4/8, reduced inside a thread-block cluster),
+    1 = no split, n = exactly n splits (a count other than 2, 4, 8 goes through an fp32 workspace)."""
     lib = _lib.load()
     _chk(a, torch.float16, "a")
     _chk(w, torch.float16, "w")
@@ -165,11 +167,11 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
     if TRACE is not None:
         TRACE.append((m, n, k, tuple(conv) if conv is not None else None, epilogue, splits,
                       a2.shape[1] if a2 is not None else 0))
-    if splits > 1:
+    if splits > 1 and splits not in (2, 4, 8):
         ws = _workspace("splitk", splits * m * n, torch.float32, a.device)
         g.splits, g.splitk_ws = splits, ws.data_ptr()
     else:
-        g.splits = 1
+        g.splits = splits
     if _GEMM_DEBUG:  # MDB_GEMM_DEBUG=1: name every GEMM before it runs and wait for it (pins down a hanging shape)
         import sys
         print(f"gemm m={m} n={n} k={k} conv={conv} epi={epilogue} splits={g.splits} a2={a2 is not None} lda={g.lda} "
@@ -297,11 +299,15 @@ def add(a, b, *, batch, b_batches=None, out=None):
     return out
 
 
-def timestep_embedding(t, dim):
+def timestep_embedding(t, dim, rows=None):
+    """rows > len(t): row b uses t[b % len(t)] (one timestep for the whole batch, or the cond | uncond pair)"""
     lib = _lib.load()
     _chk(t, torch.int64, "t")
-    out = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
-    _lib.check(lib.mdb_timestep_embedding_f32(t.data_ptr(), out.data_ptr(), t.shape[0], dim, _stream()),
+    assert t.dim() == 1 and t.is_contiguous()
+    rows = t.shape[0] if rows is None else rows
+    assert rows % t.shape[0] == 0
+    out = torch.empty((rows, dim), dtype=torch.float32, device=t.device)
+    _lib.check(lib.mdb_timestep_embedding_f32(t.data_ptr(), t.shape[0], out.data_ptr(), rows, dim, _stream()),
                "timestep_embedding_f32")
     return out
 
@@ -333,13 +339,15 @@ def softmax_rows(x, scale=1.0):
     return x
 
 
-def nchw_f32_to_nhwc_f16(x, out=None):
+def nchw_f32_to_nhwc_f16(x, out=None, copies=1):
+    """copies > 1: the result holds the batch `copies` times over ([copies*B*H*W, C])"""
     lib = _lib.load()
     _chk(x, torch.float32, "x")
     x = x.contiguous()
     b, c, h, w = x.shape
-    y = torch.empty((b * h * w, c), dtype=torch.float16, device=x.device) if out is None else out
-    _lib.check(lib.mdb_nchw_f32_to_nhwc_f16(x.data_ptr(), y.data_ptr(), b, c, h, w, _stream()), "nchw_f32_to_nhwc_f16")
+    y = torch.empty((copies * b * h * w, c), dtype=torch.float16, device=x.device) if out is None else out
+    _lib.check(lib.mdb_nchw_f32_to_nhwc_f16(x.data_ptr(), y.data_ptr(), b, c, h, w, copies, _stream()),
+               "nchw_f32_to_nhwc_f16")
     return y
 
 
@@ -353,8 +361,9 @@ def nhwc_f16_to_nchw_f32(x, *, batch, c, h, w, out=None):
     return out
 
 
-def cfg_ddim_update(x, eps_c, eps_u, coef, noise=None, x_prev=None, pred_x0=None):
-    """coef: device fp32[6] = {scale, sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma, sqrt(1-a_t)}"""
+def cfg_ddim_update(x, eps_c, eps_u, coef, noise=None, x_prev=None, pred_x0=None, update_x=False):
+    """coef: device fp32[6] = {scale, sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma, sqrt(1-a_t)};
+    update_x: x is overwritten with x_prev as well (the chain advances in place)"""
     lib = _lib.load()
     for t, nm in ((x, "x"), (eps_c, "eps_c"), (eps_u, "eps_u"), (coef, "coef")):
         _chk(t, torch.float32, nm)
@@ -363,7 +372,8 @@ def cfg_ddim_update(x, eps_c, eps_u, coef, noise=None, x_prev=None, pred_x0=None
     if pred_x0 is None:
         pred_x0 = torch.empty_like(x)
     _lib.check(lib.mdb_cfg_ddim_update_f32(x.data_ptr(), eps_c.data_ptr(), eps_u.data_ptr(), _ptr(noise),
-                                           x_prev.data_ptr(), pred_x0.data_ptr(), x.numel(), coef.data_ptr(), _stream()),
+                                           x_prev.data_ptr(), pred_x0.data_ptr(), x.numel(), coef.data_ptr(),
+                                           int(update_x), _stream()),
                "cfg_ddim_update_f32")
     return x_prev, pred_x0
 

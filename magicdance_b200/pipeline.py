@@ -125,14 +125,9 @@ class DenoisePipeline:
         """p_sample_ddim (ddim.py:518-645): eps_c = apply_model(x,t,c,ref), eps_u = apply_model(x,t,c,None,uc),
         CFG combine, DDIM update.  x: fp32 NCHW on the device.  Returns (x_prev, pred_x0, eps_c, eps_u)."""
         eng = self.engine
-        b = x.shape[0]
-        t = self.t_dev[index].expand(b).contiguous()
+        t = self.t_dev[index:index + 1]  # one timestep for the whole batch (a view: no kernel)
         pose = eng.controlnet(x, hint_feat, t, context)
-        if 2 * b <= 16:
-            eps_c, eps_u = eng.unet_forward(x, t, context, bank_kv=bank_kv, pose=pose, cfg_pair=True)
-        else:
-            eps_c = eng.unet_forward(x, t, context, bank_kv=bank_kv, pose=pose, uc=False)
-            eps_u = eng.unet_forward(x, t, context, uc=True)
+        eps_c, eps_u = eng.unet_forward(x, t, context, bank_kv=bank_kv, pose=pose, cfg_pair=True)
         x_prev, pred_x0 = ops.cfg_ddim_update(x.contiguous(), eps_c.contiguous(), eps_u.contiguous(), self.coef[index],
                                               noise=noise)
         return x_prev, pred_x0, eps_c, eps_u
@@ -227,7 +222,7 @@ class GraphedDenoiser:
             eng.aux_streams = prev_aux
 
     def _step_body_inner(self, eng, b):
-        t = self.t_cur.expand(b).contiguous()
+        t = self.t_cur  # one timestep for the whole batch
         bank_kv = self.layout.views(self.bank_cur, self.tokens, 1)
         main = torch.cuda.current_stream()
         if self.side is not None:
@@ -238,17 +233,9 @@ class GraphedDenoiser:
         else:
             pose = eng.controlnet(self.x, self.hint, t, self.ctx)
             join = None
-        if 2 * b <= 16:
-            eps_c, eps_u = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, cfg_pair=True,
-                                            before_pose=join)
-        else:
-            if join:
-                join()
-            eps_c = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, uc=False)
-            eps_u = eng.unet_forward(self.x, t, self.ctx, uc=True)
-        ops.cfg_ddim_update(self.x, eps_c.contiguous(), eps_u.contiguous(), self.coef_cur, x_prev=self.x_prev,
-                            pred_x0=self.pred_x0)
-        self.x.copy_(self.x_prev)
+        eps_c, eps_u = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, cfg_pair=True, before_pose=join)
+        # x advances in place (x_prev and pred_x0 are also kept for the callers)
+        ops.cfg_ddim_update(self.x, eps_c, eps_u, self.coef_cur, x_prev=self.x_prev, pred_x0=self.pred_x0, update_x=True)
 
     def _bank_body(self):
         build_bank_slots(self.eng, self.ref, self.t_vec, self.ctx, self.layout, self.tokens, self.bank_built)

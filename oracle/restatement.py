@@ -52,7 +52,7 @@ def ddim_schedule(alphas_cumprod, num_ddim_steps=50, num_ddpm_steps=1000, eta=0.
 def timestep_embedding(t, dim, max_period=10000):
     """util.py:189-209: [cos | sin], freqs = exp(-ln(max_period) * i / half)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:

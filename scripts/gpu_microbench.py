@@ -97,12 +97,9 @@ def main():
         conv_case(2, 8, 8, 2560, 1280, 16)
         conv_case(8, 8, 8, 1280, 1280, 4)
     if which == "pair":
-        # single-CTA 128 x BN tiles vs the persistent CTA-pair kernel (256 x BN, cta_group::2) vs the TMA-store epilogue
-        # of the single-CTA tiles, shape by shape, at the cond+uncond batch of one frame (2) and of eight frames (16)
+        # single-CTA 128 x BN tiles vs the persistent CTA-pair kernel (256 x BN, cta_group::2), shape by shape, at the cond+uncond batch of one frame (2) and of eight frames (16)
         big = 1 << 30
-        for label, tune in (("single-CTA tiles", dict(pair_min_tiles=big, tma_store=0)),
-                            ("single-CTA tiles + TMA store", dict(pair_min_tiles=big, tma_store=1)),
-                            ("pair kernel (forced)", dict(pair_min_tiles=1, tma_store=0))):
+        for label, tune in (("single-CTA tiles", dict(pair_min_tiles=big)), ("pair kernel (forced)", dict(pair_min_tiles=1))):
             print(f"--- {label}", flush=True)
             with ops.tuning(**tune):
                 for b in (2, 16):

@@ -117,9 +117,10 @@ def softmax_rows(x, scale=1.0):
     return x
 
 
-def nchw_f32_to_nhwc_f16(x, out=None):
+def nchw_f32_to_nhwc_f16(x, out=None, copies=1):
     b, c, h, w = x.shape
-    return _h(x.permute(0, 2, 3, 1).reshape(b * h * w, c)).contiguous()
+    y = _h(x.permute(0, 2, 3, 1).reshape(b * h * w, c)).contiguous()
+    return y if copies == 1 else y.repeat(copies, 1)
 
 
 def nhwc_f16_to_nchw_f32(x, *, batch, c, h, w, out=None):
@@ -153,10 +154,12 @@ def add(a, b, *, batch, b_batches=None, out=None):
     return y
 
 
-def timestep_embedding(t, dim):
+def timestep_embedding(t, dim, rows=None):
     import math
     half = dim // 2
     freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half)
+    if rows is not None and rows != t.shape[0]:
+        t = t.repeat(rows // t.shape[0])  # row b uses t[b % len(t)]
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -173,7 +176,7 @@ def ensure_device():
     return None
 
 
-def cfg_ddim_update(x, eps_c, eps_u, coef, noise=None, x_prev=None, pred_x0=None):
+def cfg_ddim_update(x, eps_c, eps_u, coef, noise=None, x_prev=None, pred_x0=None, update_x=False):
     """ddim.py:605,617-645 with coef = {scale, sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma, sqrt(1-a_t)}"""
     scale, sa, sap, sdir, sigma, s1a = (float(v) for v in coef[:6])
     eps = eps_u + scale * (eps_c - eps_u)

@@ -46,7 +46,6 @@ def case_tuned(tune, fn, *args):
 
 
 PAIR = (("pair_min_tiles", 1),)     # persistent CTA-pair GEMM (gemm_pair_kernel) whatever the grid size
-TMAST = (("tma_store", 1),)         # single-CTA tiles through the TMA-store epilogue (gemm_ts_kernel)
 NOPAIR = (("pair_min_tiles", 1 << 30),)  # single-CTA tiles on a large grid
 ATT2Q = (("attn40_2q_min_ctas", 0),)     # d=40 attention on the two-Q-tile kernel at two CTAs per SM
 
@@ -321,6 +320,9 @@ ALL_CASES = [
     (case_gemm, (1024, 640, 640, True, True, 2)),
     (case_gemm, (2048, 320, 1280, True, True, 2)),
     (case_gemm, (100, 1280, 2560, True, True, 8)),
+    (case_gemm, (512, 1280, 5120, True, True, 0)),     # automatic: 160-wide tiles, 4 splits in a cluster
+    (case_gemm, (512, 1280, 1280, True, True, 0)),     # automatic: 80-wide tiles, no split (short K)
+    (case_gemm, (128, 1280, 2560, True, True, 0)),
     (case_gemm_batch_bias, (2, 1024, 640, 320)),
     (case_gemm_dual, (1024, 640, 640, 320)),
     (case_gemm_strided_out, (320, 77, 768)),
@@ -334,6 +336,9 @@ ALL_CASES = [
     (case_conv, (1, 8, 8, 2560, 1280, True, False, 8)),
     (case_conv, (2, 16, 16, 1280, 1280, True, True, 4)),
     (case_conv, (2, 32, 32, 640, 640, True, True, 2)),
+    (case_conv, (2, 16, 16, 1280, 1280, True, True, 0)),   # automatic: long K -> 160-wide tiles, 4 splits
+    (case_conv, (2, 8, 8, 2560, 1280, True, True, 0)),     # automatic: 8 splits
+    (case_conv, (1, 16, 16, 1280, 1280, True, False, 0)),  # ControlNet at one frame: M = 256
     # ---- persistent CTA-pair GEMM forced onto small and odd problems ----
     (case_tuned, (PAIR, case_gemm, 512, 256, 128)),                       # 256-wide tile, 2 pairs, one K pass of 2 chunks
     (case_tuned, (PAIR, case_gemm, 384, 320, 320, True, True)),           # odd M tiles: last pair half empty; bias+residual
@@ -358,17 +363,6 @@ ALL_CASES = [
     # ---- the same large shapes on the single-CTA tiles (what the heuristics would not pick) ----
     (case_tuned, (NOPAIR, case_gemm, 65536, 320, 320, True, True)),
     (case_tuned, (NOPAIR, case_conv, 8, 64, 64, 320, 320, True, True)),
-    # ---- TMA-store epilogue of the single-CTA tiles ----
-    (case_tuned, (TMAST, case_gemm, 8192, 320, 320, True, True)),         # 160-wide tiles, K = 5 chunks
-    (case_tuned, (TMAST + NOPAIR, case_gemm, 16384, 640, 640, True, True)),
-    (case_tuned, (TMAST, case_gemm, 1000, 384, 192, True, True)),         # 128-wide tiles, ragged M
-    (case_tuned, (TMAST, case_gemm, 520, 200, 128, True, True)),          # N = 200: last box clipped by the tensor map
-    (case_tuned, (TMAST, case_gemm_batch_bias, 8, 1024, 640, 320)),
-    (case_tuned, (TMAST + NOPAIR, case_gemm_dual, 8192, 640, 640, 320)),
-    (case_tuned, (TMAST, case_gemm_strided_out, 320, 80, 768)),           # row pitch > N: columns beyond N stay untouched
-    (case_tuned, (TMAST + NOPAIR, case_geglu, 4096, 320)),
-    (case_tuned, (TMAST, case_geglu, 64, 1280)),
-    (case_tuned, (TMAST + NOPAIR, case_conv, 8, 32, 32, 640, 640, True, True)),
     (case_conv_direct, (1, 64, 64, 4, 320, 1, False, True)),
     (case_conv_direct, (2, 64, 64, 320, 4, 1, False)),
     (case_conv_direct, (1, 256, 256, 3, 16, 1, True)),

@@ -74,7 +74,7 @@ def test_training_entry_refuses_to_fake_gradients(model):
     x = torch.zeros(1, 4, 64, 64)
     cond = {"c_concat": [torch.zeros(1, 3, 512, 512)], "c_crossattn": [torch.zeros(1, 77, 768)],
             "image_control": [x], "wonoise": True}
-    with pytest.raises(NotImplementedError, match="forward"):
+    with torch.enable_grad(), pytest.raises(NotImplementedError, match="forward"):  # (other modules disable grad globally)
         model(x, cond)
 
 

@@ -288,7 +288,6 @@ def test_tuning_keys_match_the_header():
     hdr = open(os.path.join(here, "include", "magicdance_b200.h")).read()
     consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define (MDB_TUNE_\w+) (\d+)", hdr)}
     assert consts == {"MDB_TUNE_GEMM_PAIR_MIN_TILES": _lib.TUNE_GEMM_PAIR_MIN_TILES,
-                      "MDB_TUNE_GEMM_TMA_STORE": _lib.TUNE_GEMM_TMA_STORE,
                       "MDB_TUNE_ATTN40_2Q_MIN_CTAS": _lib.TUNE_ATTN40_2Q_MIN_CTAS,
                       "MDB_TUNE_GEMM_BN80_BELOW": _lib.TUNE_GEMM_BN80_BELOW}
     assert int(re.search(r"#define MDB_ABI_VERSION (\d+)", hdr).group(1)) == _lib.ABI_VERSION

@@ -126,7 +126,7 @@ def test_graphed_chain_matches_eager(engine):
         x_e, _, _, _ = pipe.step(x_e, ix, ctx, hint, bank_kv)
         x_g = gd.step(ix, slots[j]).clone()
         assert G.rel_l2(x_g, x_e) <= 2e-3, (j, G.rel_l2(x_g, x_e))
-    assert gd.step_launches > 500 and gd.bank_launches > 300
+    assert gd.step_launches > 300 and gd.bank_launches > 200
 
 
 def test_non_square_latent_matches_cpu_oracle(engine):
