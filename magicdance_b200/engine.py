@@ -245,13 +245,22 @@ class Act:
         return self.h * self.w
 
 
+_warned_sizes = set()
+
+
 def _igemm_ok(h, w, c):
+    """does an h x w x c activation tile into the implicit-GEMM conv's 128-pixel TMA boxes?  (512x512 and 256x256
+    images do at every level.)  Other sizes work through im2col + GEMM — 9x the activation traffic — so say so once."""
     hw = h * w
     if c % 64:
         return False
-    if hw >= 128:
-        return 128 % w == 0 and hw % 128 == 0
-    return 128 % hw == 0
+    ok = (128 % w == 0 and hw % 128 == 0) if hw >= 128 else (128 % hw == 0)
+    if not ok and (h, w) not in _warned_sizes:
+        _warned_sizes.add((h, w))
+        import warnings
+        warnings.warn(f"magicdance_b200: a {h}x{w} feature map does not tile into 128-pixel TMA boxes; its 3x3 convs take "
+                      "the slower im2col + GEMM path (latents whose width divides 128 avoid this)", stacklevel=3)
+    return ok
 
 
 class _BankComplete(Exception):
@@ -303,14 +312,15 @@ class DenoiseEngine:
         b, n, cd = ctx16.shape
         flat = ctx16.reshape(b * n, cd)
         ldv = (n + 7) // 8 * 8
+        # tokens padded to ldv per sample with zero rows: ONE swapped-operand GEMM then yields V^T [C, b*ldv] in the
+        # attention kernel's layout (columns n..ldv of each sample stay zero: the kernel masks those keys)
+        padded = torch.zeros((b, ldv, cd), dtype=torch.float16, device=self.device)
+        padded[:, :n].copy_(ctx16)
+        padded = padded.reshape(b * ldv, cd)
         res = []
         for a in net.attn_layers():
             k = ops.gemm(flat, a.wk2)
-            # V^T [C, b*ldv]: per batch element the GEMM  wv2 @ tokens^T  writes its [C, n] block in place
-            # (columns n..ldv of each block stay zero: the kernel masks those keys, and 0 * 0 is finite)
-            vt = torch.zeros((a.c, b * ldv), dtype=torch.float16, device=self.device)
-            for i in range(b):
-                ops.gemm(a.wv2, flat[i * n:(i + 1) * n], out=vt[:, i * ldv:i * ldv + n])
+            vt = ops.gemm(a.wv2, padded)
             res.append((k, vt, n, b, ldv))
         if len(self._ctx_cache) > 8:
             self._ctx_cache.clear()

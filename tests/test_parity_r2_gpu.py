@@ -6,8 +6,10 @@ sample_log / p_losses API, against goldens made by the unmodified reference (ora
   tests/golden/traj50.npz   BASELINE configs[1]: the whole 50-step chain, x after ddim index 49/40/25/10/0
   tests/golden/ploss32.npz  LatentDiffusionReferenceOnly.p_losses forward (ddpm.py:2165-2212)
 
-Tolerances (fp16 storage / fp32 accumulation against the fp32 reference, synthetic weights — SURVEY §8c): CFG-combined
-step outputs <= 2e-2 (the x7 guidance amplifies the cond/uncond difference), 50-step trajectory <= 3e-2, eps <= 5e-3.
+Tolerances (fp16 storage / fp32 accumulation against the fp32 reference; SYNTHETIC weights — no checkpoint ships):
+CFG-combined step outputs <= 5e-3 (measured 0.9e-3 x_prev / 2.4e-3 pred_x0: the x7 guidance amplifies the cond/uncond
+difference), 50-step trajectory <= 1e-2 (measured 1.7e-3 at every checkpoint: the chain does not amplify the error),
+eps <= 5e-3.  SURVEY §8c proposed 2e-2 / 3e-2; the measured margins allow the tighter gates.
 """
 import os
 
@@ -20,8 +22,8 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 YAML = os.path.join(REPO, "model_lib", "ControlNet", "models", "cldm_v15_reference_only_pose.yaml")
 
 TOL_EPS = 5e-3
-TOL_STEP = 2e-2
-TOL_TRAJ = 3e-2
+TOL_STEP = 5e-3
+TOL_TRAJ = 1e-2
 TRAJ_KEEP = (49, 40, 25, 10, 0)
 
 
