@@ -538,7 +538,7 @@ def run_ours(args):
         "x_final_fingerprint": main["x_final_fingerprint"], "step_roofline": main["step_roofline"],
         "launches_per_step": main["step_launches"], "bank_build_ms": main["bank_build_ms"],
     }
-    for k in ("steady_state", "e2e"):
+    for k in ("steady_state", "e2e", "allgather_ms", "allgather_bytes_per_rank", "allgather_note"):
         if k in main:
             line[k] = main[k]
     if roof is not None:
