@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--no-batch8", action="store_true", help="skip the configs[2] sub-record (N = 1)")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager GPU baseline (N = 1)")
     ap.add_argument("--no-config4", action="store_true", help="skip the configs[3] sub-record and the probe (N > 1)")
+    ap.add_argument("--nvtx", action="store_true", help="wrap the LAST step of the steady-state run in an NVTX range "
+                    "'mdb_step' (ncu --nvtx --nvtx-include 'mdb_step/' then profiles exactly one step)")
     ap.add_argument("--tune", default="", help="experiments: launch heuristics as k=v[,k=v] (keys of ops.tuning)")
     return ap.parse_args()
 
@@ -325,9 +327,16 @@ class Bench:
             pose = pose_host.cuda(non_blocking=True)
             gd.hint.copy_(pipe.hint(pose, frame_key=None))
             gd.x.copy_(x)
-            for ix in idxs:
+            for j, ix in enumerate(idxs):
                 bank.wait(ix)
+                mark = self.args.nvtx and prebuilt is not None and j == len(idxs) - 1
+                if mark:
+                    torch.cuda.synchronize()
+                    torch.cuda.nvtx.range_push("mdb_step")
                 gd.step(ix, bank[ix])
+                if mark:
+                    torch.cuda.synchronize()
+                    torch.cuda.nvtx.range_pop()
             run.last_bank = bank
             return gd.x_prev
 

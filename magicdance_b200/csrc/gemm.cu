@@ -169,10 +169,11 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
   if (warp == 0) {
     if (lane == 0 && n_iter > 0) {
       // conv geometry of this M tile
-      int b0 = 0, y0 = 0;
+      int b0 = 0, y0 = 0, x0 = 0;
       if (p.conv) {
         b0 = m0 / p.hw;
         y0 = (p.hw >= kBM) ? (m0 % p.hw) / p.w : 0;
+        x0 = (p.hw >= kBM) ? (m0 % p.hw) % p.w : 0;  // != 0 only for rows wider than the 128-pixel tile
       }
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % kStages;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
           const int tap = kc / p.chunks_per_tap;
           const int cc = kc - tap * p.chunks_per_tap;
           const int kh = tap / 3, kw = tap - kh * 3;
-          tma_load_4d(sa, &p.tmA, &full_bar[s], cc * kBK, kw - 1, y0 + kh - 1, b0);
+          tma_load_4d(sa, &p.tmA, &full_bar[s], cc * kBK, x0 + kw - 1, y0 + kh - 1, b0);
         } else if (kc < p.k1_chunks) {
           tma_load_2d(sa, &p.tmA, &full_bar[s], kc * kBK, m0);
         } else {
@@ -535,10 +536,11 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
         const int mp = t % m_pairs, nt = t / m_pairs;
         const int m0 = (2 * mp + static_cast<int>(pair_rank)) * kBM;
         const int n0 = nt * BN;
-        int b0 = 0, y0 = 0;
+        int b0 = 0, y0 = 0, x0 = 0;
         if (p.conv) {
           b0 = m0 / p.hw;
           y0 = (p.hw >= kBM) ? (m0 % p.hw) / p.w : 0;
+          x0 = (p.hw >= kBM) ? (m0 % p.hw) % p.w : 0;
         }
         for (int kc = 0; kc < p.k_chunks; ++kc, ++g) {
           const int s = g % kStages;
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
             const int tap = kc / p.chunks_per_tap;
             const int cc = kc - tap * p.chunks_per_tap;
             const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d_pair(sa, &p.tmA, fb, cc * kBK, kw - 1, y0 + kh - 1, b0);
+            tma_load_4d_pair(sa, &p.tmA, fb, cc * kBK, x0 + kw - 1, y0 + kh - 1, b0);
           } else if (kc < p.k1_chunks) {
             tma_load_2d_pair(sa, &p.tmA, fb, kc * kBK, m0);
           } else {
@@ -959,7 +961,11 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     MDB_REQUIRE(g->m == g->nb * g->h * g->w, "mdb_gemm_f16: conv m != nb*h*w");
     const int hw = g->h * g->w;
     uint32_t box[4];
-    if (hw >= kBM) {
+    if (g->w > kBM) {
+      // rows wider than the tile (the VAE's 256- and 512-pixel levels): a tile is 128 consecutive pixels of ONE row
+      MDB_REQUIRE(g->w % kBM == 0, "mdb_gemm_f16: conv rows wider than 128 pixels need 128 | w (w=%d)", g->w);
+      box[0] = kBK; box[1] = kBM; box[2] = 1; box[3] = 1;
+    } else if (hw >= kBM) {
       MDB_REQUIRE(kBM % g->w == 0 && hw % kBM == 0,
                   "mdb_gemm_f16: conv tile needs w | 128 and 128 | h*w (h=%d w=%d)", g->h, g->w);
       box[0] = kBK; box[1] = g->w; box[2] = kBM / g->w; box[3] = 1;

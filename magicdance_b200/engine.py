@@ -254,7 +254,7 @@ def _igemm_ok(h, w, c):
     hw = h * w
     if c % 64:
         return False
-    ok = (128 % w == 0 and hw % 128 == 0) if hw >= 128 else (128 % hw == 0)
+    ok = ((128 % w == 0 and hw % 128 == 0) or w % 128 == 0) if hw >= 128 else (128 % hw == 0)
     if not ok and (h, w) not in _warned_sizes:
         _warned_sizes.add((h, w))
         import warnings

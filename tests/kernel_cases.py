@@ -336,6 +336,9 @@ ALL_CASES = [
     (case_conv, (1, 8, 8, 2560, 1280, True, False, 8)),
     (case_conv, (2, 16, 16, 1280, 1280, True, True, 4)),
     (case_conv, (2, 32, 32, 640, 640, True, True, 2)),
+    (case_conv, (1, 8, 256, 128, 128, True, True)),        # rows wider than the 128-pixel tile (VAE levels): x0 != 0
+    (case_conv, (1, 4, 512, 128, 64, True, False)),
+    (case_tuned, (PAIR, case_conv, 2, 6, 256, 64, 128, True, True)),
     (case_conv, (2, 16, 16, 1280, 1280, True, True, 0)),   # automatic: long K -> 160-wide tiles, 4 splits
     (case_conv, (2, 8, 8, 2560, 1280, True, True, 0)),     # automatic: 8 splits
     (case_conv, (1, 16, 16, 1280, 1280, True, False, 0)),  # ControlNet at one frame: M = 256
