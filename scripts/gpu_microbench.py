@@ -120,6 +120,19 @@ def main():
                         timeit(f"geglu m={b * hw} c={c}", lambda: ops.gemm(x, wp, bias=bp, epilogue=ops.EPI_GEGLU),
                                flops=2.0 * b * hw * 8 * c * c)
         return
+    if which == "gn":
+        # GroupNorm paths by batch: mode 1 = stats (+ last-CTA fold) -> apply, mode 2 = single-launch cluster kernel
+        for b in (2, 4, 8, 16, 25):
+            for (hw, c1, c2) in ((4096, 320, 0), (4096, 640, 320), (1024, 640, 0), (1024, 1280, 640), (256, 1280, 0),
+                                 (256, 1280, 1280), (64, 1280, 1280)):
+                x1 = h(b * hw, c1)
+                x2 = h(b * hw, c2) if c2 else None
+                g_, b_ = f(c1 + c2), f(c1 + c2)
+                for mode in (1, 2):
+                    timeit(f"groupnorm B={b} hw={hw} c={c1}+{c2} mode={mode}",
+                           lambda: ops.groupnorm(x1, g_, b_, batch=b, hw=hw, eps=1e-5, silu=True, x2=x2, mode=mode),
+                           bytes_=3.0 * b * hw * (c1 + c2) * 2)
+        return
     if which == "deepk":
         # the single-frame weight-streaming layers (cond+uncond batch of 2) with COLD weights, as inside a step (each
         # step streams 2.4 GB of weights through a 126 MB L2): eight weight copies are cycled; 80- vs 160-wide tiles
