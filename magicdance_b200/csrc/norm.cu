@@ -7,11 +7,12 @@
 // |mean - K| is of the order of the standard deviation and the subtraction loses a few bits at most — unlike
 // E[x^2] - mean^2, which cancels catastrophically for activations whose mean is large against their spread.
 //
-//   small batches  gn_cluster_kernel : ONE launch; a thread-block cluster per (batch element, group) splits the
-//                  pixels, warp shuffles -> shared memory -> DSMEM exchange of (S, Q), second pass from L1/L2.
-//   large batches  gn_stats_kernel   : coalesced full-row reads, per-CTA (S, Q) partials to a workspace, the LAST
-//                  CTA of a batch element (ticket) folds them in slot order -> (mean, var)
-//                  gn_apply_kernel   : y = x * a_c + b_c [+ SiLU], 8 channels per thread.
+//   gn_cluster_kernel   ONE launch (every layer but the 320-channel ones at more than two samples): a thread-block
+//                       cluster per (batch element, group) splits the pixels, warp shuffles -> shared memory ->
+//                       DSMEM exchange of (S, Q), second pass from L1/L2.
+//   gn_stats_kernel     coalesced full-row reads, per-CTA (S, Q) partials to a workspace, the LAST CTA of a batch
+//                       element (ticket) folds them in slot order -> (mean, var)
+//   gn_apply_kernel     y = x * a_c + b_c [+ SiLU], 8 channels per thread.
 // The input may be the channel concatenation of two tensors, which is how torch.cat([h, skip], 1) (cldm.py:104)
 // disappears: the normalised copy is the only concatenated buffer.
 #include "common.cuh"
@@ -375,13 +376,16 @@ extern "C" int64_t mdb_groupnorm_ws_floats(int32_t c, int32_t batch, int32_t hw)
   return kGnMaxBatch + static_cast<int64_t>(batch) * 64 + static_cast<int64_t>(batch) * nblk * 64;
 }
 
-// single-launch cluster path: even channels per group and small enough a batch that 32 x batch x (<= 8) CTAs is
-// about two waves; mode: 0 = automatic, 1 = force the two-kernel path, 2 = force the cluster path (tests)
+// single-launch cluster path: needs even channels per group.  Automatic choice (measured on B200, scripts/gpu_microbench.py
+// gn -> profiles/r02_gn_microbench.md): the cluster kernel wins at every batch size once a group is >= 20 channels wide
+// (>= 40 bytes per pixel: whole sectors); with 10-channel groups (the 320-channel layers of the 64x64 level) its 20-byte
+// slivers waste half of every sector and it only wins while the launch count dominates (batch <= 2).
+// mode: 0 = automatic, 1 = force the two-kernel path, 2 = force the cluster path (tests)
 static bool gn_use_cluster(int c, int c1, int c2, int batch, int mode) {
   const bool ok = (c % 64 == 0) && (c1 % 2 == 0) && (c2 % 2 == 0) && (c / 64 <= kGnFusedThreads);
   if (mode == 1 || !ok) return false;
   if (mode == 2) return true;
-  return batch <= 4;
+  return (c / 32 >= 20) || batch <= 2;
 }
 
 extern "C" int mdb_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* gamma,

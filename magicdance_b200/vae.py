@@ -6,9 +6,8 @@ ldm/modules/diffusionmodules/model.py:619-652) is the step right after the denoi
 conv3x3, model.py:129-149), three nearest-x2 upsample convs, and ONE single-head attention over all 512 channels in
 the middle block (model.py:179-203) — so it maps onto the kernels the denoiser already has:
 
-  conv3x3            engine.DenoiseEngine._conv3: tcgen05 implicit GEMM where the image row tiles into 128-pixel
-                     TMA boxes (64x64 and 128x128 levels), im2col + the same GEMM at 256 and 512 pixels per row
-                     (first cut; the box generalisation `x0 = m0 mod w` is the next step)
+  conv3x3            engine.DenoiseEngine._conv3: tcgen05 implicit GEMM at every level — a 128-pixel TMA box is whole
+                     rows at the 64- and 128-pixel levels and a segment of ONE row (x0 = m0 mod w) at 256 and 512
   GroupNorm + swish  ops.groupnorm(eps=1e-6, silu=True) — 4, 8 and 16 channels per group
   1x1 convs          ops.gemm (nin_shortcut, q, k, proj_out); v is produced transposed by swapping operands
   attention (d=512)  ops.gemm (q k^T, scale folded into the q weights) -> ops.softmax_rows -> ops.gemm (P V);
@@ -16,8 +15,9 @@ the middle block (model.py:179-203) — so it maps onto the kernels the denoiser
   post_quant_conv    a 3x3 direct conv whose only non-zero tap is the centre (1x1 conv, 1/scale_factor folded in)
 
 Validated on a B200 (tests/test_vae_gpu.py): decode / encode rel-L2 ~1.5e-3 against the unmodified reference's
-goldens (tests/golden/vae16.npz, vae64.npz) and the pinned oracle (oracle/vae_restatement.py); 13.4 ms per 512x512
-frame for the decoder (187 TFLOP/s over its 2514.5 GFLOP) with the im2col path at the two widest levels.
+goldens (tests/golden/vae16.npz, vae64.npz) and the pinned oracle (oracle/vae_restatement.py); 5.5 ms per 512x512
+frame for the decoder (458 TFLOP/s over its 2514.5 GFLOP; 13.4 ms with im2col at the two widest levels before the
+conv tile was generalised to rows wider than 128 pixels).
 """
 from __future__ import annotations
 

@@ -295,10 +295,12 @@ ALL_CASES = [
     (case_groupnorm, (2, 4096, 640, 320, 1e-5, True)),               # 960 channels at 64x64: the largest slice
     (case_groupnorm, (4, 1000, 320, 0, 1e-5, True)),                 # pixel count not a multiple of anything
     (case_groupnorm, (2, 4096, 320, 0, 1e-5, True, None, 40.0)),     # mean 40, spread 1.5: pivot-shifted variance
-    (case_groupnorm, (16, 4096, 320, 0, 1e-5, True)),                # eight frames (cond+uncond): two-kernel path
-    (case_groupnorm, (16, 1024, 1280, 640, 1e-5, True)),
+    (case_groupnorm, (16, 4096, 320, 0, 1e-5, True)),                # eight frames (cond+uncond), 10-channel groups: two kernels
+    (case_groupnorm, (16, 1024, 1280, 640, 1e-5, True)),             # wide groups: the cluster kernel at every batch size
     (case_groupnorm, (25, 256, 1280, 0, 1e-6, False)),               # bank build: 25 timesteps
     (case_groupnorm, (16, 64, 1280, 1280, 1e-5, True)),
+    (case_groupnorm, (16, 1024, 1280, 640, 1e-5, True, 1)),          # the same on the two-kernel path
+    (case_groupnorm, (25, 256, 1280, 0, 1e-6, False, 1)),
     (case_groupnorm, (2, 4096, 320, 0, 1e-5, True, 1)),              # two-kernel path forced on small batches
     (case_groupnorm, (1, 1024, 640, 320, 1e-5, True, 1)),
     (case_groupnorm, (1, 16, 1280, 640, 1e-5, True, 1)),
