@@ -36,12 +36,38 @@ struct AttnCfg {
   static constexpr int kQBytes = kDkChunks * kBQ * 128;
   static constexpr int kKBytes = kDkChunks * BKV * 128;
   static constexpr int kVBytes = kKvChunks * kDV * 128;
+  // Row sums on the tensor core: when the PV tile has at least 8 spare rows (d = 40 -> 48), the 8-row swizzle group
+  // [D, D+8) of every V^T stage tile is never written by TMA (the box is D rows) and is pre-filled once per CTA with
+  // row D = ones, rows D+1.. = zeros — so O[:, D] accumulates sum_k P[:, k], the softmax denominator, in the same
+  // MMAs that produce O, and the softmax warps do not sum P at all (64 FADD of ~500 instructions per 128x64 tile).
+  static constexpr bool kOnes = (kDV - D >= 8) && (D % 8 == 0);
+  static constexpr int kVRowsTma = kOnes ? D : kDV;
+  static constexpr int kVBytesTma = kKvChunks * kVRowsTma * 128;
   static constexpr int kPBytes = kKvChunks * kBQ * 128;
   static constexpr int kStages = 2;
   static constexpr int kSmem = kQBytes + kStages * (kKBytes + kVBytes) + kPBytes + 1024;
   static constexpr int kTmemCols = (BKV + kDV <= 128) ? 128 : (BKV + kDV <= 256 ? 256 : 512);
   static constexpr int kOCol = BKV;  // O accumulator starts after S
 };
+
+// rows [D, D+8) of every V^T stage tile <- (ones, zeros x 7); called by the non-producer warps before the CTA barrier
+template <typename C1, int D, int STAGES>
+__device__ __forceinline__ void attn_fill_ones_rows(uint8_t* sKV, int stage_bytes, int k_bytes, int tid, int nthreads) {
+  if constexpr (C1::kOnes) {
+    for (int i = tid; i < STAGES * C1::kKvChunks * 64; i += nthreads) {  // 64 16-byte pieces per 1 KB swizzle group
+      const int piece = i & 63, grp = i >> 6;
+      const int stage = grp / C1::kKvChunks, kc = grp % C1::kKvChunks;
+      uint8_t* g = sKV + stage * stage_bytes + k_bytes + kc * (C1::kDV * 128) + (D / 8) * 1024;
+      const uint32_t v = (piece < 8) ? 0x3C003C00u : 0u;  // row 0 of the group (pieces 0..7) = fp16 1.0 x 64
+      *reinterpret_cast<uint4*>(g + piece * 16) = make_uint4(v, v, v, v);
+    }
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's reads of shared memory
+  }
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 struct AttnKParams {
   CUtensorMap tmQ, tmK0, tmV0, tmK1, tmV1;
@@ -374,6 +400,8 @@ __global__ void __launch_bounds__(kAttn2Threads, MINB) attn2_tc_kernel(const __g
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, C::kTmemCols);
+  if (warp >= 2)
+    attn_fill_ones_rows<C1, D, C::kStages>(sKV, C::kKBytes + C::kVBytes, C::kKBytes, threadIdx.x - 64, kAttn2Threads - 64);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -397,7 +425,7 @@ __global__ void __launch_bounds__(kAttn2Threads, MINB) attn2_tc_kernel(const __g
         const int kvb = src1 ? (p.kv1_batches > 1 ? b : 0) : (p.kv0_batches > 1 ? b : 0);
         const int ldvb = src1 ? p.ldv1_batch : p.ldv0_batch;
         mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_expect_tx(&kv_full[s], C::kKBytes + C::kVBytes);
+        mbar_expect_tx(&kv_full[s], C::kKBytes + C1::kVBytesTma);
         uint8_t* sk = sKV + s * (C::kKBytes + C::kVBytes);
         uint8_t* sv = sk + C::kKBytes;
         for (int dc = 0; dc < C1::kDkChunks; ++dc)
@@ -466,7 +494,7 @@ __global__ void __launch_bounds__(kAttn2Threads, MINB) attn2_tc_kernel(const __g
       const uint32_t t_o = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + 2 * BKV + t * C::kDV;
       float m_run = -INFINITY;
       float l_run = 0.f;
-      uint8_t* p_row = sP + t * C::kPBytes + (r >> 3) * 1024 + (r & 7) * 128;
+      const uint32_t p_row = smem_u32(sP + t * C::kPBytes + (r >> 3) * 1024 + (r & 7) * 128);
       const int sw = r & 7;
 
       for (int j = 0; j < n_tiles; ++j) {
@@ -515,9 +543,11 @@ __global__ void __launch_bounds__(kAttn2Threads, MINB) attn2_tc_kernel(const __g
                 for (int i = 0; i < 32; ++i)
                   pv[i] = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m)) : 0.f;
               }
+              if constexpr (!C1::kOnes) {  // (else: the row sum comes out of the PV MMA, O[:, D])
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                ls0 += pv[i]; ls1 += pv[i + 1]; ls2 += pv[i + 2]; ls3 += pv[i + 3];
+                for (int i = 0; i < 32; i += 4) {
+                  ls0 += pv[i]; ls1 += pv[i + 1]; ls2 += pv[i + 2]; ls3 += pv[i + 3];
+                }
               }
 #pragma unroll
               for (int u4 = 0; u4 < 4; ++u4) {
@@ -528,7 +558,7 @@ __global__ void __launch_bounds__(kAttn2Threads, MINB) attn2_tc_kernel(const __g
                 pk.w = pack_half2(pv[u4 * 8 + 6], pv[u4 * 8 + 7]);
                 const int u = c * 4 + u4;
                 const int kc = u >> 3, uu = u & 7;
-                *reinterpret_cast<uint4*>(p_row + kc * (kBQ * 128) + ((uu ^ sw) << 4)) = pk;
+                st_shared_v4(p_row + kc * (kBQ * 128) + ((uu ^ sw) << 4), pk);
               }
             }
           }
@@ -570,7 +600,13 @@ __global__ void __launch_bounds__(kAttn2Threads, MINB) attn2_tc_kernel(const __g
       // final: O / l -> fp16
       mbar_wait(&o_done[t], (n_tiles - 1) & 1);
       tc_fence_after_sync();
-      const float inv_l = 1.0f / l_run;
+      float inv_l = 1.0f / l_run;
+      if constexpr (C1::kOnes) {
+        uint32_t ol[16];
+        tmem_ld_x16(t_o + (D / 16) * 16, ol);
+        tmem_wait_ld();
+        inv_l = 1.0f / __uint_as_float(ol[D % 16]);  // O[:, D] = sum_k P[:, k] (the ones row of V^T)
+      }
       const int q = q0 + t * kBQ + r;
       __half* op = p.out + (static_cast<long long>(b) * p.nq + q) * p.ldo + head * D;
 #pragma unroll
@@ -671,6 +707,8 @@ __global__ void __launch_bounds__(kAttnThreads, Attn3Cfg<D, BKV, STAGES>::kCtasP
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, C::kTmemCols);
+  if (warp >= 2)
+    attn_fill_ones_rows<C1, D, STAGES>(sKV, C::kKBytes + C::kVBytes, C::kKBytes, threadIdx.x - 64, kAttnThreads - 64);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -693,7 +731,7 @@ __global__ void __launch_bounds__(kAttnThreads, Attn3Cfg<D, BKV, STAGES>::kCtasP
         const int kvb = src1 ? (p.kv1_batches > 1 ? b : 0) : (p.kv0_batches > 1 ? b : 0);
         const int ldvb = src1 ? p.ldv1_batch : p.ldv0_batch;
         mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_expect_tx(&kv_full[s], C::kKBytes + C::kVBytes);
+        mbar_expect_tx(&kv_full[s], C::kKBytes + C1::kVBytesTma);
         uint8_t* sk = sKV + s * (C::kKBytes + C::kVBytes);
         uint8_t* sv = sk + C::kKBytes;
         for (int dc = 0; dc < C1::kDkChunks; ++dc)
@@ -751,7 +789,7 @@ __global__ void __launch_bounds__(kAttnThreads, Attn3Cfg<D, BKV, STAGES>::kCtasP
     const uint32_t t_o = t_lane + 2 * BKV;
     float m_run = -INFINITY;
     float l_run = 0.f;
-    uint8_t* p_row0 = sP + (r >> 3) * 1024 + (r & 7) * 128;
+    const uint32_t p_row0 = smem_u32(sP + (r >> 3) * 1024 + (r & 7) * 128);
     const int sw = r & 7;
 
     for (int j = 0; j < n_tiles; ++j) {
@@ -759,7 +797,7 @@ __global__ void __launch_bounds__(kAttnThreads, Attn3Cfg<D, BKV, STAGES>::kCtasP
       const int key0 = (src1 ? (j - t0) : j) * BKV;
       const int valid = min(BKV, (src1 ? p.n1 : p.n0) - key0);
       const uint32_t t_s = t_lane + (j & 1) * BKV;
-      uint8_t* p_row = p_row0 + (j & 1) * C::kPBytes;
+      const uint32_t p_row = p_row0 + (j & 1) * C::kPBytes;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after_sync();
       float mt = -INFINITY;
@@ -799,9 +837,11 @@ __global__ void __launch_bounds__(kAttnThreads, Attn3Cfg<D, BKV, STAGES>::kCtasP
               for (int i = 0; i < 32; ++i)
                 pv[i] = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m)) : 0.f;
             }
+            if constexpr (!C1::kOnes) {  // (else: the row sum comes out of the PV MMA, O[:, D])
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              ls0 += pv[i]; ls1 += pv[i + 1]; ls2 += pv[i + 2]; ls3 += pv[i + 3];
+              for (int i = 0; i < 32; i += 4) {
+                ls0 += pv[i]; ls1 += pv[i + 1]; ls2 += pv[i + 2]; ls3 += pv[i + 3];
+              }
             }
 #pragma unroll
             for (int u4 = 0; u4 < 4; ++u4) {
@@ -812,7 +852,7 @@ __global__ void __launch_bounds__(kAttnThreads, Attn3Cfg<D, BKV, STAGES>::kCtasP
               pk.w = pack_half2(pv[u4 * 8 + 6], pv[u4 * 8 + 7]);
               const int u = c * 4 + u4;
               const int kc = u >> 3, uu = u & 7;
-              *reinterpret_cast<uint4*>(p_row + kc * (kBQ * 128) + ((uu ^ sw) << 4)) = pk;
+              st_shared_v4(p_row + kc * (kBQ * 128) + ((uu ^ sw) << 4), pk);
             }
           }
         }
@@ -856,7 +896,13 @@ __global__ void __launch_bounds__(kAttnThreads, Attn3Cfg<D, BKV, STAGES>::kCtasP
 
     mbar_wait(&o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after_sync();
-    const float inv_l = 1.0f / l_run;
+    float inv_l = 1.0f / l_run;
+    if constexpr (C1::kOnes) {
+      uint32_t ol[16];
+      tmem_ld_x16(t_o + (D / 16) * 16, ol);
+      tmem_wait_ld();
+      inv_l = 1.0f / __uint_as_float(ol[D % 16]);  // O[:, D] = sum_k P[:, k] (the ones row of V^T)
+    }
     const int q = q0 + r;
     __half* op = p.out + (static_cast<long long>(b) * p.nq + q) * p.ldo + head * D;
 #pragma unroll
@@ -960,7 +1006,7 @@ static int build_and_launch(const mdb_attn_desc* a, cudaStream_t st) {
     if (r) return r;
     uint64_t vdims[2] = {(uint64_t)nb * ldvb, (uint64_t)hd};
     uint64_t vstr[1] = {(uint64_t)ldvt * 2};
-    uint32_t vbox[2] = {64, (uint32_t)C::kDV};
+    uint32_t vbox[2] = {64, (uint32_t)C::kVRowsTma};
     return make_tmap_f16(tv, vt, 2, vdims, vstr, vbox);
   };
   if ((rc = mk_kv(a->k0, a->ldk0, a->vt0, a->ldvt0, a->n0, a->kv0_batches, a->ldv0_batch, &kp.tmK0, &kp.tmV0))) return rc;

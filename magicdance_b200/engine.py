@@ -530,12 +530,15 @@ class DenoiseEngine:
             h, w = (h + 2 - 3) // s + 1, (w + 2 - 3) // s + 1
         return x  # [B*h*w, model_channels]
 
-    def controlnet(self, x_noisy, hint_feat, t, context):
-        """ControlNet.forward (cldm.py:736-757) -> 13 residuals as fp16 [B*H*W, C] matrices."""
+    def controlnet(self, x_noisy, hint_feat, t, context, emb_all=None):
+        """ControlNet.forward (cldm.py:736-757) -> 13 residuals as fp16 [B*H*W, C] matrices.
+        emb_all: precomputed time_bias(self.pose, t) (it depends on the timestep only: a sampler computes it once
+        per schedule entry instead of once per frame-step)."""
         net = self.pose
         x, ctx16, key = self._prep(x_noisy, context)
         ctx_kvs = self.context_kv(net, ctx16, key)
-        emb_all = self.time_bias(net, t, x.b)
+        if emb_all is None:
+            emb_all = self.time_bias(net, t, x.b)
         state = {"mode": "plain", "attn_i": 0, "hint": hint_feat}
         outs = []
         for i, blk in enumerate(net.inp):
@@ -549,7 +552,7 @@ class DenoiseEngine:
         return outs
 
     def unet_forward(self, x_noisy, t, context, bank_kv=None, pose=None, uc=False, taps=None, cfg_pair=False,
-                     before_pose=None):
+                     before_pose=None, emb_all=None):
         """ControlledUnetModelAttnPose.forward (cldm.py:59-112).  uc=True: plain SD UNet without bank
         or pose residuals (cldm.py:70-84); otherwise 'read' mode.  bank_kv: project_bank() output.
         Returns eps as NCHW fp32.
@@ -567,7 +570,8 @@ class DenoiseEngine:
                 ctx16 = torch.cat([ctx16, ctx16])
                 key = (key[0], key[1], key[2] + ("pair",), key[3])
         ctx_kvs = self.context_kv(net, ctx16, key)
-        emb_all = self.time_bias(net, t, x.b)  # the pair repeats the timesteps: row b uses t[b % B]
+        if emb_all is None:  # (else: precomputed time_bias(self.unet, t), one row per distinct timestep)
+            emb_all = self.time_bias(net, t, x.b)  # the pair repeats the timesteps: row b uses t[b % B]
         state = {"mode": "plain" if uc else "read", "attn_i": 0}
         pose = None if (uc or pose is None) else list(pose)
         state["bank_kv"] = None if uc else bank_kv

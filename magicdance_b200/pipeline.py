@@ -197,6 +197,11 @@ class GraphedDenoiser:
         self.layout = parallel.BankLayout([(n, c) for n, c in geo])
         self.bank_cur = torch.zeros((self.layout.numel,), dtype=torch.float16, device=dev)
         self.bank_built = torch.zeros((bank_chunk, self.layout.numel), dtype=torch.float16, device=dev)
+        # timestep path hoisted out of the step: embedding -> time_embed MLP -> all emb_layers depend on t only, so the
+        # tables for every ddim index are computed once (capture()) and a step copies its two rows into these buffers
+        self.emb_unet = torch.zeros((1, eng.unet.emb_total), dtype=torch.float32, device=dev)
+        self.emb_pose = torch.zeros((1, eng.pose.emb_total), dtype=torch.float32, device=dev)
+        self.emb_tab_unet = self.emb_tab_pose = None
         self.g_step = self.g_bank = None
         self.replayed_launches = 0
         import os
@@ -228,12 +233,13 @@ class GraphedDenoiser:
         if self.side is not None:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side), ops.workspace_lane(1):
-                pose = eng.controlnet(self.x, self.hint, t, self.ctx)
+                pose = eng.controlnet(self.x, self.hint, t, self.ctx, emb_all=self.emb_pose)
             join = lambda: main.wait_stream(self.side)
         else:
-            pose = eng.controlnet(self.x, self.hint, t, self.ctx)
+            pose = eng.controlnet(self.x, self.hint, t, self.ctx, emb_all=self.emb_pose)
             join = None
-        eps_c, eps_u = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, cfg_pair=True, before_pose=join)
+        eps_c, eps_u = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, cfg_pair=True, before_pose=join,
+                                        emb_all=self.emb_unet)
         # x advances in place (x_prev and pred_x0 are also kept for the callers)
         ops.cfg_ddim_update(self.x, eps_c, eps_u, self.coef_cur, x_prev=self.x_prev, pred_x0=self.pred_x0, update_x=True)
 
@@ -245,6 +251,11 @@ class GraphedDenoiser:
         s = torch.cuda.Stream(device=self.pipe.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
+            eng, td = self.eng, self.pipe.t_dev
+            self.emb_tab_unet = torch.cat([eng.time_bias(eng.unet, td[i:i + 1]) for i in range(td.shape[0])], 0)
+            self.emb_tab_pose = torch.cat([eng.time_bias(eng.pose, td[i:i + 1]) for i in range(td.shape[0])], 0)
+            self.emb_unet.copy_(self.emb_tab_unet[-1:])
+            self.emb_pose.copy_(self.emb_tab_pose[-1:])
             for _ in range(2):
                 self._bank_body()
                 self._step_body()
@@ -282,6 +293,8 @@ class GraphedDenoiser:
         """one DDIM step on self.x in place (result also in self.x_prev / self.pred_x0)"""
         self.t_cur.copy_(self.pipe.t_dev[index:index + 1])
         self.coef_cur.copy_(self.pipe.coef[index])
+        self.emb_unet.copy_(self.emb_tab_unet[index:index + 1])
+        self.emb_pose.copy_(self.emb_tab_pose[index:index + 1])
         self.bank_cur.copy_(bank_flat)
         self.g_step.replay()
         self.replayed_launches += self.step_launches
