@@ -951,6 +951,8 @@ static int launch_attn3(const AttnKParams& kp, dim3 grid, cudaStream_t st) {
 // d = 40 self-attention (the 64x64 level): grids of at least this many 128-row CTAs go to the two-Q-tile kernel at two
 // CTAs per SM (16 softmax warps per SM).  Measured on B200 (profiles/r02_*): +3.3 % on the eight-frame step (4096
 // CTAs per launch), -2 % on the single-frame step (512 CTAs per launch).  mdb_set_tuning(MDB_TUNE_ATTN40_2Q_MIN_CTAS).
+// d = 80 (the 32x32 level): the one-Q-tile kernel needs 142 KB of shared memory, i.e. ONE CTA and four softmax warps per
+// SM; the two-Q-tile kernel (148 KB, eight softmax warps per SM) takes over at a quarter of the d=40 threshold.
 static int g_attn40_2q_min_ctas = 2048;
 int get_attn_tuning() { return g_attn40_2q_min_ctas; }
 void set_attn_tuning(int v) { g_attn40_2q_min_ctas = v; }
@@ -1034,6 +1036,13 @@ static int build_and_launch(const mdb_attn_desc* a, cudaStream_t st) {
       if (a->nq > kBQ && ctas >= (long long)g_attn40_2q_min_ctas) {
         dim3 grid2((a->nq + 2 * kBQ - 1) / (2 * kBQ), a->heads, a->batch);
         return launch_attn2<D, BKV, 2>(kp, grid2, st);
+      }
+    }
+    if constexpr (D == 80) {
+      const long long ctas = (long long)grid.x * grid.y * grid.z;
+      if (a->nq > kBQ && ctas >= (long long)g_attn40_2q_min_ctas / 4) {
+        dim3 grid2((a->nq + 2 * kBQ - 1) / (2 * kBQ), a->heads, a->batch);
+        return launch_attn2<D, BKV, 1>(kp, grid2, st);
       }
     }
     return launch_attn3<D, BKV, ST, 1>(kp, grid, st);  // 1 of 4 exponentials on the FMA pipe: measured best on B200

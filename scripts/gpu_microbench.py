@@ -165,6 +165,10 @@ def main():
         attn_case(1, 40, 4096, 4096, 4096)
         attn_case(8, 40, 4096, 4096, 4096)
         attn_case(1, 40, 4096, 77)
+        attn_case(16, 80, 1024, 1024, 1024)
+        with ops.tuning(attn40_2q_min_ctas=1 << 30):
+            attn_case(16, 80, 1024, 1024, 1024)   # one-Q-tile kernel for comparison
+            attn_case(8, 40, 4096, 4096, 4096)
         attn_case(1, 80, 1024, 1024, 1024)
         attn_case(1, 80, 1024, 77)
         attn_case(1, 160, 256, 256, 256)

@@ -396,4 +396,10 @@ ALL_CASES = [
     (case_tuned, (ATT2Q, case_attention, 2, 8, 40, 1024, 77, 0, 1, None, True)),
     (case_tuned, (ATT2Q, case_attention, 1, 8, 40, 384, 384, 128, 1)),
     (case_attention, (16, 8, 40, 2048, 2048, 2048, 1, 8)),   # 2048 CTAs: the heuristics pick the two-Q-tile kernel
+    # ---- d=80 on the two-Q-tile kernel (one CTA, eight softmax warps per SM) ----
+    (case_tuned, (ATT2Q, case_attention, 2, 8, 80, 256, 256, 256, 1)),
+    (case_tuned, (ATT2Q, case_attention, 2, 8, 80, 200, 200, 0, 1)),          # ragged: the second Q tile is partly empty
+    (case_tuned, (ATT2Q, case_attention, 2, 8, 80, 1024, 77, 0, 1, None, True)),
+    (case_tuned, (ATT2Q, case_attention, 1, 8, 80, 384, 384, 128, 1)),        # odd number of Q tiles
+    (case_attention, (16, 8, 80, 1024, 1024, 1024, 1, 8)),   # 1024 CTAs: picked by the heuristics
 ]
