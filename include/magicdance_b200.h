@@ -85,6 +85,13 @@ typedef struct mdb_gemm_desc {
   int32_t m, n, k;
   int32_t splits;             /* 0: automatic (1, 2, 4 or 8, in-cluster reduction); 1: none; >1: as given */
   float* splitk_ws;           /* fp32 [splits][M][N] scratch, only for explicit split counts other than 2, 4, 8 */
+  /* LayerNorm over A's rows folded into the GEMM (norm2 -> attn2.to_q of BasicTransformerBlock,
+   * attention.py:271,312-314): with B = W diag(gamma) and bias = W beta (+ the layer's own bias) supplied by the
+   * caller, ln_u[n] = sum_k B[n][k] makes D = rstd_r (A B^T - mean_r ln_u) + bias equal to LayerNorm(A) W^T + b; K must
+   * be the normalised width.  Small grids only: every N tile recomputes the statistics of its rows (no split-K, no
+   * GEGLU epilogue, single-CTA tiles).  NULL = off. */
+  const float* ln_u;
+  float ln_eps;
 } mdb_gemm_desc;
 
 int mdb_gemm_f16(const mdb_gemm_desc* desc, mdb_stream_t stream);

@@ -49,6 +49,13 @@ struct GemmKParams {
   int chunks_per_tap;  // c / 64
   int w, hw;           // conv geometry
   int cluster_reduce;  // split-K partners form a cluster (1,1,splits) and reduce through distributed smem
+  // LayerNorm folded into this GEMM (gemm_tc_kernel only): D = rstd_r (A W'^T - mean_r u) + bias with W' = W diag(gamma),
+  // u[n] = sum_k W'[n][k]; the epilogue warps compute (mean_r, rstd_r) of their A rows while the main loop runs
+  const float* ln_u;
+  const __half* a_raw;
+  long long lda_raw;
+  int ln_k;
+  float ln_eps;
 };
 
 // STAGES = 3: <=108 KB, two CTAs per SM (large grids: the co-resident CTA hides the TMA round trip).
@@ -128,6 +135,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_bias[BN];  // this N tile's bias row (when one row serves all batches)
+  __shared__ __align__(16) float s_lnu[BN];   // this N tile's u (LayerNorm folded into the GEMM)
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
@@ -159,6 +167,9 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
   const bool bias_in_smem = (p.bias != nullptr) && (p.bias_batch_stride == 0) && !p.cluster_reduce;
   if (bias_in_smem && warp >= 2) {
     for (int j = threadIdx.x - 64; j < BN; j += 128) s_bias[j] = (n0 + j < p.n) ? p.bias[n0 + j] : 0.f;
+  }
+  if (p.ln_u != nullptr && warp >= 2) {  // a constant of the weights, like the bias
+    for (int j = threadIdx.x - 64; j < BN; j += 128) s_lnu[j] = (n0 + j < p.n) ? p.ln_u[n0 + j] : 0.f;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -236,6 +247,31 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
           if (q * 8 + 8 <= BN && n0 + q * 8 + 8 <= p.n) res_pref[q] = *reinterpret_cast<const uint4*>(rrow + q * 8);
       }
     }
+    // LayerNorm folded into the GEMM: statistics of this thread's A row (pivot-shifted sums, biased variance as
+    // nn.LayerNorm), computed from global memory (L2: the row was just written) while the main loop runs
+    float ln_mean = 0.f, ln_rstd = 1.f;
+    const bool ln = p.ln_u != nullptr;
+    if (ln && row_ok) {
+      const uint4* xr = reinterpret_cast<const uint4*>(p.a_raw + row * p.lda_raw);
+      const float pivot = __half2float(*reinterpret_cast<const __half*>(xr));
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 4
+      for (int i = 0; i < p.ln_k / 8; ++i) {
+        const uint4 u4 = xr[i];
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          const float d0 = f.x - pivot, d1 = f.y - pivot;
+          s0 += d0; q0 = fmaf(d0, d0, q0);
+          s1 += d1; q1 = fmaf(d1, d1, q1);
+        }
+      }
+      const float inv_k = 1.0f / static_cast<float>(p.ln_k);
+      const float ms = (s0 + s1) * inv_k;
+      ln_mean = pivot + ms;
+      ln_rstd = rsqrtf(fmaxf(fmaf(-ms, ms, (q0 + q1) * inv_k), 0.f) + p.ln_eps);
+    }
     mbar_wait(&acc_bar, 0);
     tc_fence_after_sync();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
@@ -259,6 +295,11 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (ln) {  // rstd_r (acc - mean_r u[n]); the bias row carries W beta (+ the layer's own bias)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (ch * 32 + j < BN) v[j] = ln_rstd * fmaf(-ln_mean, s_lnu[ch * 32 + j], v[j]);
+        }
         const int ncols = min(min(32, BN - ch * 32), p.n - col0);
         if (p.cluster_reduce) {
           // split-K inside a cluster: park this CTA's fp32 partial tile in its own shared memory (the
@@ -953,6 +994,18 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     MDB_REQUIRE(!geglu, "mdb_gemm_f16: residual is not supported with the GEGLU epilogue");
   }
 
+  if (g->ln_u != nullptr) {
+    MDB_REQUIRE(!geglu, "mdb_gemm_f16: LayerNorm fusion is not available with the GEGLU epilogue (N / 128 CTAs per row "
+                        "block would each recompute the row statistics: measured slower than the LayerNorm kernel)");
+    MDB_REQUIRE(!g->conv && g->a2 == nullptr && g->k % 8 == 0 && (reinterpret_cast<uintptr_t>(g->a) & 15) == 0 &&
+                    g->lda % 8 == 0 && (reinterpret_cast<uintptr_t>(g->ln_u) & 15) == 0,
+                "mdb_gemm_f16: LayerNorm fusion needs a plain single-source A (16B-aligned rows) whose K is the normalised width");
+    kp.ln_u = g->ln_u;
+    kp.a_raw = static_cast<const __half*>(g->a);
+    kp.lda_raw = g->lda;
+    kp.ln_k = g->k;
+    kp.ln_eps = g->ln_eps;
+  }
   int rc;
   if (g->conv) {
     MDB_REQUIRE(g->a2 == nullptr, "mdb_gemm_f16: conv mode takes a single source");
@@ -1003,7 +1056,7 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   // CTA-pair kernel with 256 x {320, 256, 160, 128} tiles — widest first: fewest L2 -> SM bytes per flop; the
   // 320-wide tile (two 160-wide MMAs per K step, single accumulator buffer) only for long K.
   const int m_tiles = (g->m + kBM - 1) / kBM;
-  bool pair = g->splits <= 1 && m_tiles >= 2 && g->n % 8 == 0;
+  bool pair = g->splits <= 1 && m_tiles >= 2 && g->n % 8 == 0 && g->ln_u == nullptr;  // (the pair kernel has no LN fusion)
   int bn = 0;
   if (pair) {
     if (geglu) bn = (g->n % 256 == 0) ? 256 : 0;
@@ -1038,7 +1091,8 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   }
 
   int splits = g->splits > 1 ? g->splits : 1;
-  if (g->splits == 0 && !geglu && !pair) {
+  if (g->ln_u != nullptr) splits = 1;  // the correction is applied by the CTA that holds the whole K range
+  if (g->splits == 0 && !geglu && !pair && g->ln_u == nullptr) {
     // automatic split-K: a power of two up to 8 (reduced inside a thread-block cluster through DSMEM) that brings
     // the grid to about one CTA per SM while every split keeps at least 16 K chunks (measured on B200 with cold
     // weights: below that the cluster reduction costs more than the extra CTAs gain)

@@ -117,6 +117,24 @@ def pack_geglu(w, b, device):
     return _f16(w.detach()[order], device), _f32(b.detach()[order], device)
 
 
+def fold_layernorm(w, gamma, beta, bias, device):
+    """LayerNorm(x) W^T + b as ONE GEMM over the raw x (ops.gemm(ln_u=...)): returns
+    (W diag(gamma) in fp16, u = row sums of that fp16 matrix, v = W beta + b) — u is taken from the ROUNDED weights,
+    because it has to cancel exactly what the tensor core sums."""
+    w, gamma, beta = w.detach().to(device).float(), gamma.detach().to(device).float(), beta.detach().to(device).float()
+    w_ln = (w * gamma[None, :]).to(torch.float16).contiguous()
+    u = w_ln.float().sum(dim=1).contiguous()
+    v = w @ beta
+    if bias is not None:
+        v = v + bias.detach().to(device).float()
+    return w_ln, u, v.contiguous()
+
+
+# rows up to which norm2 is folded into the attn2.to_q GEMM (one frame: cond | uncond batch of 2 at 64x64 = 8192 rows).
+# Larger batches run that GEMM on the persistent pair kernel, which has no LayerNorm fusion, after a LayerNorm kernel.
+LN_FUSE_MAX_ROWS = 8192
+
+
 class ResW:
     pass
 
@@ -205,6 +223,8 @@ class PackedNet:
         a.wv = _f16(g(t + "attn1.to_v.weight"), device)
         a.wo, a.bo = _f16(g(t + "attn1.to_out.0.weight"), device), _f32(g(t + "attn1.to_out.0.bias"), device)
         a.wq2 = _f16(g(t + "attn2.to_q.weight"), device)
+        a.wq2_ln, a.q2_u, a.q2_v = fold_layernorm(g(t + "attn2.to_q.weight"), g(t + "norm2.weight"), g(t + "norm2.bias"),
+                                                  None, device)
         a.wk2 = _f16(g(t + "attn2.to_k.weight"), device)
         a.wv2 = _f16(g(t + "attn2.to_v.weight"), device)
         a.wo2, a.bo2 = _f16(g(t + "attn2.to_out.0.weight"), device), _f32(g(t + "attn2.to_out.0.bias"), device)
@@ -404,8 +424,11 @@ class DenoiseEngine:
         at = ops.attention(qk[:, :c], qk[:, c:], vt, n, heads=a.heads, d=a.d, batch=b, nq=n, **kw)
         h = ops.gemm(at, a.wo, bias=a.bo, residual=h)
         # --- attn2 (text) ---
-        n2 = ops.layernorm(h, *a.ln2)
-        q2 = ops.gemm(n2, a.wq2)
+        if m <= LN_FUSE_MAX_ROWS:  # norm2 folded into the projection: row statistics in the GEMM's epilogue warps
+            q2 = ops.gemm(h, a.wq2_ln, bias=a.q2_v, ln_u=a.q2_u, ln_eps=1e-5)
+        else:
+            n2 = ops.layernorm(h, *a.ln2)
+            q2 = ops.gemm(n2, a.wq2)
         kt, vtt, nt, kvb, ldv = ctx_kv
         at2 = ops.attention(q2, kt, vtt, nt, heads=a.heads, d=a.d, batch=b, nq=n, kv0_batches=kvb if kvb == b else 1,
                             ldv0_batch=ldv)

@@ -121,11 +121,13 @@ def _workspace(key, numel, dtype, device, zero=False):
 
 
 def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, residual=None, epilogue=EPI_NONE,
-         a2=None, conv=None, splits=0, m=None):
+         a2=None, conv=None, splits=0, m=None, ln_u=None, ln_eps=1e-5):
     """D = epilogue(A @ W^T).  a: [M, K1] fp16 (last dim contiguous, row stride arbitrary) or, with
     conv=(nb, h, w, c), an NHWC activation; w: [N, K] fp16; a2: optional second K-range source.
     splits: 0 = the library picks tile width and split-K (1/2/4/8, reduced inside a thread-block cluster),
-    1 = no split, n = exactly n splits (a count other than 2, 4, 8 goes through an fp32 workspace)."""
+    1 = no split, n = exactly n splits (a count other than 2, 4, 8 goes through an fp32 workspace).
+    ln_u: LayerNorm over a's rows folded into the GEMM — w must be W diag(gamma), bias W beta (+ b), ln_u the row sums
+    of w (engine.fold_layernorm); D = rstd_r (a w^T - mean_r ln_u) + bias.  Small grids only."""
     lib = _lib.load()
     _chk(a, torch.float16, "a")
     _chk(w, torch.float16, "w")
@@ -164,6 +166,11 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
         assert residual.dim() == 2 and residual.stride(1) == 1
         g.residual, g.ldr = residual.data_ptr(), residual.stride(0)
     g.m, g.n, g.k, g.epilogue = m, n, k, epilogue
+    if ln_u is not None:
+        _chk(ln_u, torch.float32, "ln_u")
+        assert conv is None and a2 is None and ln_u.numel() == n and ln_u.is_contiguous()
+        g.ln_u, g.ln_eps = ln_u.data_ptr(), float(ln_eps)
+        splits = 1
     if TRACE is not None:
         TRACE.append((m, n, k, tuple(conv) if conv is not None else None, epilogue, splits,
                       a2.shape[1] if a2 is not None else 0))

@@ -12,7 +12,7 @@ def _h(t):
 
 
 def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, residual=None, epilogue=0, a2=None,
-         conv=None, splits=1, m=None):
+         conv=None, splits=1, m=None, ln_u=None, ln_eps=1e-5):
     """D = epilogue(A @ W^T) exactly as include/magicdance_b200.h describes mdb_gemm_f16 (dual-source A, conv mode,
     per-batch bias rows, residual, GEGLU over [value | gate] blocks of 32 interleaved columns)."""
     assert a.dtype == torch.float16 and w.dtype == torch.float16
@@ -30,6 +30,10 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
             af = af[:m]
         assert af.shape[1] == k, (af.shape, w.shape)
         y = af @ w.float().t()
+        if ln_u is not None:  # LayerNorm folded into the GEMM: rstd_r (A W'^T - mean_r u); the caller's bias carries W beta
+            mean = af.mean(dim=1, keepdim=True)
+            rstd = torch.rsqrt(af.var(dim=1, unbiased=False, keepdim=True) + ln_eps)
+            y = rstd * (y - mean * ln_u.reshape(1, n))
     rows = y.shape[0]
     if bias is not None:
         assert bias.dtype == torch.float32

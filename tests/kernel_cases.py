@@ -50,6 +50,21 @@ NOPAIR = (("pair_min_tiles", 1 << 30),)  # single-CTA tiles on a large grid
 ATT2Q = (("attn40_2q_min_ctas", 0),)     # d=40 attention on the two-Q-tile kernel at two CTAs per SM
 
 
+def case_gemm_ln(m, n, k, offset=0.5, seed=0):
+    """LayerNorm folded into the GEMM (ops.gemm(ln_u=...), engine.fold_layernorm) against LayerNorm -> Linear in fp32;
+    offset: row mean of the activations (the correction rstd (acc - mean u) must not cancel)."""
+    from magicdance_b200.engine import fold_layernorm
+    x = (_rand(m, k, seed=seed) * 1.3 + offset).half()
+    w = _rand(n, k, seed=seed + 1, scale=k ** -0.5)
+    gamma = 1 + 0.1 * _rand(k, seed=seed + 2)
+    beta = 0.1 * _rand(k, seed=seed + 3)
+    b = 0.1 * _rand(n, seed=seed + 4)
+    w_ln, u, v = fold_layernorm(w, gamma, beta, b, DEV)
+    out = ops.gemm(x, w_ln, bias=v, ln_u=u, ln_eps=1e-5)
+    ref = F.layer_norm(x.double(), (k,), gamma.double(), beta.double(), 1e-5) @ w.double().t() + b.double()
+    return rel(out.float(), ref), 3e-3, f"gemm with folded LayerNorm m={m} n={n} k={k} offset={offset}"
+
+
 def case_gemm_batch_bias(batch, hw, n, k, seed=0):
     m = batch * hw
     a = _rand(m, k, seed=seed).half()
@@ -325,6 +340,11 @@ ALL_CASES = [
     (case_gemm, (512, 1280, 5120, True, True, 0)),     # automatic: 160-wide tiles, 4 splits in a cluster
     (case_gemm, (512, 1280, 1280, True, True, 0)),     # automatic: 80-wide tiles, no split (short K)
     (case_gemm, (128, 1280, 2560, True, True, 0)),
+    (case_gemm_ln, (8192, 320, 320)),                  # norm2 -> attn2.to_q at 64x64 (cond | uncond of one frame)
+    (case_gemm_ln, (2048, 640, 640)),
+    (case_gemm_ln, (512, 1280, 1280)),                 # 80-wide tiles: 16 CTAs recompute the same row statistics
+    (case_gemm_ln, (100, 1280, 1280)),                 # ragged M
+    (case_gemm_ln, (1024, 640, 640, 20.0)),            # row mean 20 against a spread of 1.3
     (case_gemm_batch_bias, (2, 1024, 640, 320)),
     (case_gemm_dual, (1024, 640, 640, 320)),
     (case_gemm_strided_out, (320, 77, 768)),
