@@ -50,11 +50,8 @@ struct GemmKParams {
   int w, hw;           // conv geometry
   int cluster_reduce;  // split-K partners form a cluster (1,1,splits) and reduce through distributed smem
   // LayerNorm folded into this GEMM (gemm_tc_kernel only): D = rstd_r (A W'^T - mean_r u) + bias with W' = W diag(gamma),
-  // u[n] = sum_k W'[n][k]; the epilogue warps compute (mean_r, rstd_r) of their A rows while the main loop runs
+  // u[n] = sum_k W'[n][k]; the epilogue warps compute (mean_r, rstd_r) of their A rows from the staged tiles
   const float* ln_u;
-  const __half* a_raw;
-  long long lda_raw;
-  int ln_k;
   float ln_eps;
 };
 
@@ -156,7 +153,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], p.ln_u != nullptr ? 5 : 1);  // LayerNorm fusion: + one arrival per epilogue warp
     }
     mbar_init(&acc_bar, 1);
     fence_barrier_init();
@@ -248,26 +245,38 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
       }
     }
     // LayerNorm folded into the GEMM: statistics of this thread's A row (pivot-shifted sums, biased variance as
-    // nn.LayerNorm), computed from global memory (L2: the row was just written) while the main loop runs
+    // nn.LayerNorm), taken from the A tiles AS THEY PASS THROUGH SHARED MEMORY on their way to the tensor core — the
+    // epilogue warps are idle during the main loop, wait on the same `full` barriers as the MMA thread and add one
+    // arrival per warp to `empty` (armed with 1 + 4 arrivals in this mode); no extra global or L2 traffic.
     float ln_mean = 0.f, ln_rstd = 1.f;
     const bool ln = p.ln_u != nullptr;
-    if (ln && row_ok) {
-      const uint4* xr = reinterpret_cast<const uint4*>(p.a_raw + row * p.lda_raw);
-      const float pivot = __half2float(*reinterpret_cast<const __half*>(xr));
-      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 4
-      for (int i = 0; i < p.ln_k / 8; ++i) {
-        const uint4 u4 = xr[i];
-        const __half2* h2 = reinterpret_cast<const __half2*>(&u4);
+    if (ln) {
+      const int rt = g * 32 + lane;  // row inside the tile == TMEM lane
+      float pivot = 0.f, s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+      for (int it = 0; it < n_iter; ++it) {
+        const int s_ = it % kStages;
+        mbar_wait(&full_bar[s_], (it / kStages) & 1);
+        const uint32_t arow = smem_u32(smem + s_ * S::kStageBytes) + (rt >> 3) * 1024 + (rt & 7) * 128;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(h2[e]);
-          const float d0 = f.x - pivot, d1 = f.y - pivot;
-          s0 += d0; q0 = fmaf(d0, d0, q0);
-          s1 += d1; q1 = fmaf(d1, d1, q1);
+        for (int l = 0; l < 8; ++l) {  // logical 16-byte chunk l lives at physical chunk l ^ (row & 7): conflict-free
+          uint4 u4;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(u4.x), "=r"(u4.y), "=r"(u4.z), "=r"(u4.w)
+                       : "r"(arow + ((l ^ (rt & 7)) << 4)));
+          const __half2* h2 = reinterpret_cast<const __half2*>(&u4);
+          if (it == 0 && l == 0) pivot = __low2float(h2[0]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h2[e]);
+            const float d0 = f.x - pivot, d1 = f.y - pivot;
+            s0 += d0; q0 = fmaf(d0, d0, q0);
+            s1 += d1; q1 = fmaf(d1, d1, q1);
+          }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s_]);  // this warp is done reading stage s_
       }
-      const float inv_k = 1.0f / static_cast<float>(p.ln_k);
+      const float inv_k = 1.0f / static_cast<float>(p.k_chunks * kBK);
       const float ms = (s0 + s1) * inv_k;
       ln_mean = pivot + ms;
       ln_rstd = rsqrtf(fmaxf(fmaf(-ms, ms, (q0 + q1) * inv_k), 0.f) + p.ln_eps);
@@ -997,13 +1006,9 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   if (g->ln_u != nullptr) {
     MDB_REQUIRE(!geglu, "mdb_gemm_f16: LayerNorm fusion is not available with the GEGLU epilogue (N / 128 CTAs per row "
                         "block would each recompute the row statistics: measured slower than the LayerNorm kernel)");
-    MDB_REQUIRE(!g->conv && g->a2 == nullptr && g->k % 8 == 0 && (reinterpret_cast<uintptr_t>(g->a) & 15) == 0 &&
-                    g->lda % 8 == 0 && (reinterpret_cast<uintptr_t>(g->ln_u) & 15) == 0,
-                "mdb_gemm_f16: LayerNorm fusion needs a plain single-source A (16B-aligned rows) whose K is the normalised width");
+    MDB_REQUIRE(!g->conv && g->a2 == nullptr && (reinterpret_cast<uintptr_t>(g->ln_u) & 15) == 0,
+                "mdb_gemm_f16: LayerNorm fusion needs a plain single-source A whose K is the normalised width");
     kp.ln_u = g->ln_u;
-    kp.a_raw = static_cast<const __half*>(g->a);
-    kp.lda_raw = g->lda;
-    kp.ln_k = g->k;
     kp.ln_eps = g->ln_eps;
   }
   int rc;
