@@ -1069,7 +1069,11 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     else if (g->n % 256 == 0) bn = 256;
     else if (g->n % 160 == 0) bn = 160;
     else bn = 128;
-    if (bn == 0 || (long long)((m_tiles + 1) / 2) * 2 * ((g->n + bn - 1) / bn) < (long long)g_pair_min_tiles) pair = false;
+    // ... and enough work per launch: the pair kernel owns its SMs (one ~200 KB CTA each, no PDL, nothing of the other
+    // stream beside it), which only pays when the grid is large AND the K loop is not a handful of chunks
+    // (measured: 8192x320x320 at one frame is faster on the single-CTA tiles, 4096x1280x1280 at eight on the pair)
+    const long long eq = (long long)((m_tiles + 1) / 2) * 2 * ((g->n + bn - 1) / (bn ? bn : 1));
+    if (bn == 0 || eq < (long long)g_pair_min_tiles || eq * kp.k_chunks < 16ll * g_pair_min_tiles) pair = false;
   }
   if (pair) {
     // bn chosen above
