@@ -180,6 +180,25 @@ class DDIMSampler_ReferenceOnly(object):
                 intermediates["pred_x0"].append(gd.pred_x0.clone())
         return gd.x_prev.clone(), intermediates
 
+    def _p_sample_ddim_batched_cfg(self, x, c, t, index, scale, uc):
+        """ddim.py:539-566 — the unconditional conditioning carries image_control too (every control_mode other than
+        'controlnet_important', test_tiktok.py:237-243): ONE apply_model over the batch [unconditional ; conditional],
+        both halves in 'read' mode with their own prompt, pose map and appearance bank.  Not graph-replayed: the
+        appearance pass depends on both prompts and runs inside every step, exactly as in the reference."""
+        from .. import ops
+        pipe = self._pipeline(scale)
+        dev = pipe.device
+        one = lambda lst: lst[0] if len(lst) == 1 else torch.cat(lst, 1)
+        ref = one(c["image_control"]).to(dev)
+        ref_n = ref if c["wonoise"] else self.model.q_sample(ref, t.to(dev))
+        pair = lambda k: torch.cat([one(uc[k]).to(dev), one(c[k]).to(dev)])
+        x = x.to(device=dev, dtype=torch.float32).contiguous()
+        cond_in = {"c_concat": [pair("c_concat")], "c_crossattn": [pair("c_crossattn")]}
+        eps = self.model.apply_model(torch.cat([x, x]), torch.cat([t, t]).to(dev), cond_in, torch.cat([ref_n, ref_n]))
+        e_u, e_c = eps.chunk(2)
+        noise = torch.randn_like(x) if float(self.ddim_sigmas[index]) != 0.0 else None
+        return ops.cfg_ddim_update(x, e_c.contiguous(), e_u.contiguous(), pipe.coef[index], noise=noise)
+
     def _rows_identical(self, t):
         """all batch rows of t equal row 0?  One device->host sync per (tensor, version), not per DDIM step: the
         answer is cached with a strong reference to the tensor (its address cannot be recycled meanwhile)."""
@@ -200,9 +219,12 @@ class DDIMSampler_ReferenceOnly(object):
                       temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
                       unconditional_guidance_scale=1., unconditional_conditioning=None, dynamic_threshold=None,
                       inpaint=None):
-        """ddim.py:518-645 for the branch MagicPose takes: c carries image_control (+wonoise), the
-        unconditional conditioning does not ('controlnet is more important', ddim.py:598-605), so
-        eps = eps_u + s (eps_c - eps_u) with eps_u = apply_model(x, t, c, None, uc=True)."""
+        """ddim.py:518-645.  The branch MagicPose's released scripts take (graph-replayed by ddim_sampling, fused
+        here): c carries image_control (+wonoise), the unconditional conditioning does not ('controlnet is more
+        important', ddim.py:598-605), so eps = eps_u + s (eps_c - eps_u) with eps_u = apply_model(x, t, c, None,
+        uc=True).  The batched branch for the other control modes (ddim.py:539-566) runs eagerly; the no-guidance
+        call (ddim.py:536-537, which the reference itself cannot execute for this model: apply_model lacks its
+        reference argument) and AnimateDiff overlap sampling (ddim.py:568-594) raise."""
         if (inpaint is not None or use_original_steps or quantize_denoised or score_corrector is not None
                 or dynamic_threshold is not None or noise_dropout != 0.0 or temperature != 1.0):
             raise NotImplementedError("option not used by the MagicPose inference scripts")
@@ -211,7 +233,7 @@ class DDIMSampler_ReferenceOnly(object):
         if unconditional_conditioning is None or unconditional_guidance_scale == 1.0:
             raise NotImplementedError("only the classifier-free-guidance path of the scripts is accelerated")
         if unconditional_conditioning.get("image_control") is not None:
-            raise NotImplementedError("only control_mode='controlnet_important' (test_tiktok.py:237-240) is accelerated")
+            return self._p_sample_ddim_batched_cfg(x, c, t, index, unconditional_guidance_scale, unconditional_conditioning)
         if c.get("overlap_sampling"):
             raise NotImplementedError("overlap_sampling is off in every released script (test_tiktok.py:247)")
         pipe = self._pipeline(unconditional_guidance_scale)

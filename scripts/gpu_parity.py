@@ -11,7 +11,7 @@ sys.path.insert(0, REPO)
 
 import torch  # noqa: E402
 
-from oracle import synth  # noqa: E402  (test infrastructure: weights + golden readers)
+from magicdance_b200 import synth  # noqa: E402  (seeded weights + inputs)
 from tests import golden_util as G  # noqa: E402
 from magicdance_b200.engine import DenoiseEngine  # noqa: E402
 

@@ -1,7 +1,7 @@
 """GPU parity of the (not yet validated) VAE decoder and encoder in magicdance_b200/vae.py against the pinned CPU oracle and
 the reference goldens.  Run on a B200:
 
-    python scripts/gpu_vae_parity.py            # latent 16 (B=2) and latent 64 (B=1)
+    python tests/gpu_vae_parity_report.py            # latent 16 (B=2) and latent 64 (B=1)
 
 Gates: rel-L2 <= 5e-3 against the reference golden image (fp16 storage / fp32 accumulate vs fp32), per stage
 taps are printed to localise a failure.

@@ -146,6 +146,7 @@ def test_sample_log_four_step_chain_matches_the_oracle(model, monkeypatch):
         if getattr(model, "_test_loaded_seed", None) != 0:  # the apply_model test above leaves these weights loaded and packed
             own = model.state_dict()
             sd.update({k: own[k] for k in synth.SCHEDULE_KEYS})
+            sd.update({k: own[k] for k in own if k.startswith("first_stage_model.")})
             model.load_state_dict(sd, strict=True)
             model._test_loaded_seed = 0
         inp = synth.synth_inputs(1, 16, seed=5, shared_reference=True)  # 128x128 image: the host loop is size-independent
@@ -169,6 +170,44 @@ def test_sample_log_four_step_chain_matches_the_oracle(model, monkeypatch):
             x = R.p_sample_ddim(sd, x, t, index, inp["context"], inp["pose"], inp["ref"], sched, scale=7.0)[0]
         err = G.rel_l2(x0, x)
         assert tuple(x0.shape) == (1, 4, 16, 16) and err <= 3e-2, err
+    finally:
+        model.__dict__.pop("_mdb_pipelines", None)
+        torch.set_grad_enabled(True)
+
+
+def test_batched_cfg_branch_matches_the_reference_golden(model, monkeypatch):
+    """p_sample_ddim when the unconditional conditioning carries image_control too (ddim.py:539-566, every control_mode
+    other than 'controlnet_important'): one apply_model over [unconditional ; conditional], both halves with bank and
+    pose residuals and their own prompt — against the UNMODIFIED reference's golden (oracle/make_golden_r2.py cfgb)."""
+    from magicdance_b200 import ops, synth
+    from magicdance_b200.dropin.ddim import DDIMSampler_ReferenceOnly
+    from tests import fake_ops, golden_util as G
+    from tests.test_engine_cpu import _PATCHED
+    for name in _PATCHED + ("cfg_ddim_update",):
+        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    torch.set_grad_enabled(False)
+    try:
+        if getattr(model, "_test_loaded_seed", None) != 0:
+            sd = synth.synth_state_dict(seed=0)
+            own = model.state_dict()
+            sd.update({k: own[k] for k in synth.SCHEDULE_KEYS})
+            sd.update({k: own[k] for k in own if k.startswith("first_stage_model.")})
+            model.load_state_dict(sd, strict=True)
+            model._test_loaded_seed = 0
+        g = G.load("cfgb32")
+        inp = synth.synth_inputs(1, 32, seed=0, shared_reference=True)
+        uc_ctx = torch.from_numpy(g["uc_context"])
+        c = {"c_concat": [inp["pose"]], "c_crossattn": [inp["context"]], "image_control": [inp["ref"]], "wonoise": True,
+             "overlap_sampling": False}
+        uc = {"c_concat": [inp["pose"]], "c_crossattn": [uc_ctx], "image_control": [inp["ref"]], "wonoise": True,
+              "overlap_sampling": False}
+        sampler = DDIMSampler_ReferenceOnly(model)
+        sampler.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+        ts = torch.full((1,), int(sampler.ddim_timesteps[30]), dtype=torch.long)
+        x_prev, pred_x0 = sampler.p_sample_ddim(inp["x"], c, ts, index=30, unconditional_guidance_scale=7.0,
+                                                unconditional_conditioning=uc)
+        assert G.rel_l2(x_prev, torch.from_numpy(g["x_prev"])) <= 2e-2
+        assert G.rel_l2(pred_x0, torch.from_numpy(g["pred_x0"])) <= 2e-2
     finally:
         model.__dict__.pop("_mdb_pipelines", None)
         torch.set_grad_enabled(True)

@@ -76,6 +76,28 @@ def test_sampler_step_matches_reference_p_sample_ddim(model):
     assert G.rel_l2(pred_x0, torch.from_numpy(g["full64/pred_x0"])) <= 2e-2
 
 
+def test_batched_cfg_branch_matches_reference_p_sample_ddim(model):
+    """ddim.py:539-566: the unconditional conditioning keeps image_control (control modes other than
+    'controlnet_important'): one apply_model over [unconditional ; conditional] with two prompts."""
+    from tests import golden_util as G
+    from magicdance_b200 import synth
+    from model_lib.ControlNet.ldm.models.diffusion.ddim import DDIMSampler_ReferenceOnly
+    g = G.load("cfgb32")
+    inp = {k: v.cuda() for k, v in synth.synth_inputs(1, 32, seed=0, shared_reference=True).items()}
+    uc_ctx = torch.from_numpy(g["uc_context"]).cuda()
+    c = {"c_concat": [inp["pose"]], "c_crossattn": [inp["context"]], "image_control": [inp["ref"]], "wonoise": True,
+         "overlap_sampling": False}
+    uc = {"c_concat": [inp["pose"]], "c_crossattn": [uc_ctx], "image_control": [inp["ref"]], "wonoise": True,
+          "overlap_sampling": False}
+    sampler = DDIMSampler_ReferenceOnly(model)
+    sampler.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+    ts = torch.full((1,), int(sampler.ddim_timesteps[30]), dtype=torch.long, device="cuda")
+    x_prev, pred_x0 = sampler.p_sample_ddim(inp["x"], c, ts, index=30, unconditional_guidance_scale=7.0,
+                                            unconditional_conditioning=uc)
+    assert G.rel_l2(x_prev, torch.from_numpy(g["x_prev"])) <= 5e-3
+    assert G.rel_l2(pred_x0, torch.from_numpy(g["pred_x0"])) <= 5e-3
+
+
 def test_sample_log_runs_the_chain_and_reuses_the_bank(model):
     """sample_log (ddpm.py:2401-2413) for two 'frames' of one reference at 256x256, 4 DDIM steps: the second
     frame must hit the per-timestep bank cache (no appearance pass) and stay finite."""

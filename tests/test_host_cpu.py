@@ -180,7 +180,7 @@ def test_vae_decoder_orchestration_matches_the_oracle_with_cpu_test_doubles(monk
     """The VAE decoder's host logic (magicdance_b200/vae.py: operand order, layouts, the three folds, the
     GEMM -> softmax -> GEMM attention) run on tests/fake_ops.py — PyTorch stand-ins that read the same packed
     layouts as the kernels — must reproduce the pinned oracle / the reference golden at latent 16.  The CUDA
-    kernels are not exercised here (tests/test_kernels_gpu.py, scripts/gpu_vae_parity.py)."""
+    kernels are not exercised here (tests/test_kernels_gpu.py, tests/gpu_vae_parity_report.py)."""
     import json
     import os
     import numpy as np
