@@ -352,10 +352,10 @@ struct Attn2Cfg {
   static_assert(kCols <= 512, "TMEM budget");
 };
 
-// MINB = 2 (MDB_ATTN=4, d=40 with 64-key tiles: 224 TMEM columns, 93 KB of shared memory) puts TWO such CTAs on
-// an SM — 16 softmax warps instead of the 8 that v1 (two CTAs), v2 (one CTA) and v3 (two CTAs) all run with and
-// that all land on ~2200 cycles per 128x128 tile; the register cap becomes 65536 / 640 = 102 per thread.
-// Opt-in: this instantiation has not run on a GPU yet (tests/kernel_cases.py PENDING_CASES).
+// MINB = 2 (d=40 with 64-key tiles: 224 TMEM columns, 93 KB of shared memory) puts TWO such CTAs on an SM —
+// 16 softmax warps instead of the 8 of the one-Q-tile kernel at two CTAs per SM; the register cap becomes
+// 65536 / 640 = 102 per thread.  Used for large grids (mdb_attention_f16: >= 2048 CTAs at d=40; MINB = 1 at d=80
+// from 512 CTAs, where the one-Q-tile kernel only fits one CTA = four softmax warps per SM).
 template <int D, int BKV, int MINB = 1>
 __global__ void __launch_bounds__(kAttn2Threads, MINB) attn2_tc_kernel(const __grid_constant__ AttnKParams p) {
   using C = Attn2Cfg<D, BKV>;

@@ -204,15 +204,15 @@ class GraphedDenoiser:
         self.emb_tab_unet = self.emb_tab_pose = None
         self.g_step = self.g_bank = None
         self.replayed_launches = 0
-        import os
-        self.side = torch.cuda.Stream(device=dev) if os.environ.get("MDB_DUAL_STREAM", "1") != "0" else None
+        self.side = torch.cuda.Stream(device=dev)  # the pose ControlNet's stream (joins the UNet at the middle block)
         # auxiliary streams for independent branches inside a block (engine._fork): lane 0 (UNet pass) -> lane 2,
         # lane 1 (ControlNet pass on the side stream) -> lane 3
         # (kept on THIS object and handed to the engine only for the duration of _step_body: eager calls through the
         # same engine must not inherit the fork/join path and its scratch lanes)
         self.aux_streams = None
-        if os.environ.get("MDB_AUX_STREAMS", "1") != "0" and batch <= 2:
+        if batch <= 2:
             self.aux_streams = {0: (torch.cuda.Stream(device=dev), 2), 1: (torch.cuda.Stream(device=dev), 3)}
+
     # the two bodies, written against the static buffers only
     def _step_body(self):
         """One DDIM step.  The pose ControlNet and the UNet's encoder half are independent (the pose
@@ -230,14 +230,10 @@ class GraphedDenoiser:
         t = self.t_cur  # one timestep for the whole batch
         bank_kv = self.layout.views(self.bank_cur, self.tokens, 1)
         main = torch.cuda.current_stream()
-        if self.side is not None:
-            self.side.wait_stream(main)
-            with torch.cuda.stream(self.side), ops.workspace_lane(1):
-                pose = eng.controlnet(self.x, self.hint, t, self.ctx, emb_all=self.emb_pose)
-            join = lambda: main.wait_stream(self.side)
-        else:
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side), ops.workspace_lane(1):
             pose = eng.controlnet(self.x, self.hint, t, self.ctx, emb_all=self.emb_pose)
-            join = None
+        join = lambda: main.wait_stream(self.side)
         eps_c, eps_u = eng.unet_forward(self.x, t, self.ctx, bank_kv=bank_kv, pose=pose, cfg_pair=True, before_pose=join,
                                         emb_all=self.emb_unet)
         # x advances in place (x_prev and pred_x0 are also kept for the callers)
