@@ -70,7 +70,8 @@ typedef struct mdb_gemm_desc {
   const void* a2;  /* optional 2nd source for K columns [k1, K) (fused torch.cat along channels) */
   int64_t lda2;
   int32_t k1;      /* columns taken from a; == k when a2 == NULL                                  */
-  int32_t conv;    /* 0 plain, 1 = 3x3 stride-1 pad-1 implicit GEMM (K = 9*c, M = nb*h*w)         */
+  int32_t conv;    /* 0 plain; 1 | 2 = 3x3 pad-1 implicit GEMM with stride 1 | 2 over the NHWC input
+                      (K = 9*c, M = nb*ho*wo, ho = (h-1)/stride+1): no im2col buffer (TMA element strides) */
   int32_t nb, h, w, c;
   const void* b;   /* fp16 [N][K], row stride ldb                                                 */
   int64_t ldb;

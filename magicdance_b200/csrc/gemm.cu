@@ -47,7 +47,8 @@ struct GemmKParams {
   int splits;
   int conv;            // conv mode
   int chunks_per_tap;  // c / 64
-  int w, hw;           // conv geometry
+  int w, hw;           // conv geometry of the OUTPUT (== input for stride 1)
+  int cs;              // conv stride (1 | 2): input pixel = cs * output pixel + tap - 1
   int cluster_reduce;  // split-K partners form a cluster (1,1,splits) and reduce through distributed smem
   // LayerNorm folded into this GEMM (gemm_tc_kernel only): D = rstd_r (A W'^T - mean_r u) + bias with W' = W diag(gamma),
   // u[n] = sum_k W'[n][k]; the epilogue warps compute (mean_r, rstd_r) of their A rows from the staged tiles
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
           const int tap = kc / p.chunks_per_tap;
           const int cc = kc - tap * p.chunks_per_tap;
           const int kh = tap / 3, kw = tap - kh * 3;
-          tma_load_4d(sa, &p.tmA, &full_bar[s], cc * kBK, x0 + kw - 1, y0 + kh - 1, b0);
+          tma_load_4d(sa, &p.tmA, &full_bar[s], cc * kBK, p.cs * x0 + kw - 1, p.cs * y0 + kh - 1, b0);
         } else if (kc < p.k1_chunks) {
           tma_load_2d(sa, &p.tmA, &full_bar[s], kc * kBK, m0);
         } else {
@@ -604,7 +605,7 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
             const int tap = kc / p.chunks_per_tap;
             const int cc = kc - tap * p.chunks_per_tap;
             const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d_pair(sa, &p.tmA, fb, cc * kBK, x0 + kw - 1, y0 + kh - 1, b0);
+            tma_load_4d_pair(sa, &p.tmA, fb, cc * kBK, p.cs * x0 + kw - 1, p.cs * y0 + kh - 1, b0);
           } else if (kc < p.k1_chunks) {
             tma_load_2d_pair(sa, &p.tmA, fb, kc * kBK, m0);
           } else {
@@ -857,7 +858,8 @@ __global__ void splitk_finalize_kernel(GemmKParams p) {
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
 static int make_tmap_f16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                            const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+                            const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle,
+                            const uint32_t* elem_strides = nullptr) {
   if (g_encode == nullptr) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -875,7 +877,7 @@ static int make_tmap_f16_sw(CUtensorMap* out, const void* base, int rank, const 
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
@@ -1016,28 +1018,35 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     MDB_REQUIRE(g->a2 == nullptr, "mdb_gemm_f16: conv mode takes a single source");
     MDB_REQUIRE(g->c % kBK == 0 && g->k == 9 * g->c, "mdb_gemm_f16: conv needs c %% 64 == 0 and k == 9c (c=%d k=%d)",
                 g->c, g->k);
-    MDB_REQUIRE(g->m == g->nb * g->h * g->w, "mdb_gemm_f16: conv m != nb*h*w");
-    const int hw = g->h * g->w;
+    // conv == 1: stride 1; conv == 2: stride 2 (Downsample.op, openaimodel.py:175): the output pixel (y, x) reads input
+    // (2y + kh - 1, 2x + kw - 1) — the same shifted boxes with TMA element strides of 2 along w and h, no im2col buffer
+    const int cs = g->conv == 2 ? 2 : 1;
+    const int ho = (g->h - 1) / cs + 1, wo = (g->w - 1) / cs + 1;
+    MDB_REQUIRE(g->m == g->nb * ho * wo, "mdb_gemm_f16: conv m != nb*ho*wo");
+    const int hw = ho * wo;  // OUTPUT pixels per image: tiles are cut over these
     uint32_t box[4];
-    if (g->w > kBM) {
+    if (wo > kBM) {
       // rows wider than the tile (the VAE's 256- and 512-pixel levels): a tile is 128 consecutive pixels of ONE row
-      MDB_REQUIRE(g->w % kBM == 0, "mdb_gemm_f16: conv rows wider than 128 pixels need 128 | w (w=%d)", g->w);
+      MDB_REQUIRE(wo % kBM == 0 && cs == 1, "mdb_gemm_f16: conv rows wider than 128 pixels need 128 | w and stride 1 (w=%d)", g->w);
       box[0] = kBK; box[1] = kBM; box[2] = 1; box[3] = 1;
     } else if (hw >= kBM) {
-      MDB_REQUIRE(kBM % g->w == 0 && hw % kBM == 0,
-                  "mdb_gemm_f16: conv tile needs w | 128 and 128 | h*w (h=%d w=%d)", g->h, g->w);
-      box[0] = kBK; box[1] = g->w; box[2] = kBM / g->w; box[3] = 1;
+      MDB_REQUIRE(kBM % wo == 0 && hw % kBM == 0,
+                  "mdb_gemm_f16: conv tile needs w | 128 and 128 | h*w (output h=%d w=%d)", ho, wo);
+      box[0] = kBK; box[1] = cs * wo; box[2] = cs * (kBM / wo); box[3] = 1;
     } else {
-      MDB_REQUIRE(kBM % hw == 0, "mdb_gemm_f16: conv tile needs h*w | 128 (h=%d w=%d)", g->h, g->w);
-      box[0] = kBK; box[1] = g->w; box[2] = g->h; box[3] = kBM / hw;
+      MDB_REQUIRE(kBM % hw == 0, "mdb_gemm_f16: conv tile needs h*w | 128 (output h=%d w=%d)", ho, wo);
+      box[0] = kBK; box[1] = cs * wo; box[2] = cs * ho; box[3] = kBM / hw;
     }
+    MDB_REQUIRE(box[1] <= 256 && box[2] <= 256, "mdb_gemm_f16: conv TMA box too large");
     uint64_t dims[4] = {(uint64_t)g->c, (uint64_t)g->w, (uint64_t)g->h, (uint64_t)g->nb};
-    uint64_t str[3] = {(uint64_t)g->c * 2, (uint64_t)g->c * g->w * 2, (uint64_t)g->c * hw * 2};
-    rc = make_tmap_f16(&kp.tmA, g->a, 4, dims, str, box);
+    uint64_t str[3] = {(uint64_t)g->c * 2, (uint64_t)g->c * g->w * 2, (uint64_t)g->c * g->h * g->w * 2};
+    const uint32_t estr[4] = {1u, (uint32_t)cs, (uint32_t)cs, 1u};
+    rc = make_tmap_f16_sw(&kp.tmA, g->a, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, cs == 2 ? estr : nullptr);
     if (rc) return rc;
     kp.chunks_per_tap = g->c / kBK;
-    kp.w = g->w;
+    kp.w = wo;
     kp.hw = hw;
+    kp.cs = cs;
     kp.k1_chunks = kp.k_chunks;
   } else {
     const int k1 = g->a2 ? g->k1 : g->k;

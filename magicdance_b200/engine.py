@@ -448,9 +448,12 @@ class DenoiseEngine:
                                       state.get("bank_batches", 0))
                 state["attn_i"] = i + 1
             elif kind == "down":
-                col = ops.im2col3x3(x.data, batch=x.b, h=x.h, w=x.w, c=x.c, stride=2)
                 ho, wo = (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1
-                y = ops.gemm(col, lw[0], bias=lw[1])
+                if _igemm_ok(ho, wo, x.c):  # stride-2 implicit GEMM: TMA element strides of 2, no im2col buffer
+                    y = ops.gemm(x.data, lw[0], bias=lw[1], conv=(x.b, x.h, x.w, x.c), conv_stride=2)
+                else:
+                    col = ops.im2col3x3(x.data, batch=x.b, h=x.h, w=x.w, c=x.c, stride=2)
+                    y = ops.gemm(col, lw[0], bias=lw[1])
                 x = Act(y, x.b, ho, wo)
             elif kind == "up":
                 up = ops.upsample2x(x.data, batch=x.b, h=x.h, w=x.w, c=x.c)

@@ -121,7 +121,7 @@ def _workspace(key, numel, dtype, device, zero=False):
 
 
 def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, residual=None, epilogue=EPI_NONE,
-         a2=None, conv=None, splits=0, m=None, ln_u=None, ln_eps=1e-5):
+         a2=None, conv=None, conv_stride=1, splits=0, m=None, ln_u=None, ln_eps=1e-5):
     """D = epilogue(A @ W^T).  a: [M, K1] fp16 (last dim contiguous, row stride arbitrary) or, with
     conv=(nb, h, w, c), an NHWC activation; w: [N, K] fp16; a2: optional second K-range source.
     splits: 0 = the library picks tile width and split-K (1/2/4/8, reduced inside a thread-block cluster),
@@ -135,9 +135,9 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
     n, k = w.shape
     if conv is not None:
         nb, h, wd, c = conv
-        m = nb * h * wd
-        assert a.is_contiguous() and a.numel() == m * c
-        g.conv, g.nb, g.h, g.w, g.c = 1, nb, h, wd, c
+        assert conv_stride in (1, 2) and a.is_contiguous() and a.numel() == nb * h * wd * c
+        m = nb * ((h - 1) // conv_stride + 1) * ((wd - 1) // conv_stride + 1)  # output pixels (3x3, pad 1)
+        g.conv, g.nb, g.h, g.w, g.c = conv_stride, nb, h, wd, c  # descriptor: conv = 1 (stride 1) | 2 (stride 2)
         g.a, g.lda, g.k1 = a.data_ptr(), c, k
     else:
         assert a.dim() == 2 and a.stride(1) == 1
@@ -172,7 +172,7 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
         g.ln_u, g.ln_eps = ln_u.data_ptr(), float(ln_eps)
         splits = 1
     if TRACE is not None:
-        TRACE.append((m, n, k, tuple(conv) if conv is not None else None, epilogue, splits,
+        TRACE.append((m, n, k, (tuple(conv) + (conv_stride,)) if conv is not None else None, epilogue, splits,
                       a2.shape[1] if a2 is not None else 0))
     if splits > 1 and splits not in (2, 4, 8):
         ws = _workspace("splitk", splits * m * n, torch.float32, a.device)

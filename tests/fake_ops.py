@@ -12,7 +12,7 @@ def _h(t):
 
 
 def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, residual=None, epilogue=0, a2=None,
-         conv=None, splits=1, m=None, ln_u=None, ln_eps=1e-5):
+         conv=None, conv_stride=1, splits=1, m=None, ln_u=None, ln_eps=1e-5):
     """D = epilogue(A @ W^T) exactly as include/magicdance_b200.h describes mdb_gemm_f16 (dual-source A, conv mode,
     per-batch bias rows, residual, GEGLU over [value | gate] blocks of 32 interleaved columns)."""
     assert a.dtype == torch.float16 and w.dtype == torch.float16
@@ -23,7 +23,7 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
         assert a2 is None and k == 9 * cin and a.numel() == b * h * ww * cin
         x = a.float().reshape(b, h, ww, cin).permute(0, 3, 1, 2)
         wt = w.float().reshape(n, 3, 3, cin).permute(0, 3, 1, 2)
-        y = F.conv2d(x, wt, None, padding=1).permute(0, 2, 3, 1).reshape(b * h * ww, n)
+        y = F.conv2d(x, wt, None, padding=1, stride=conv_stride).permute(0, 2, 3, 1).reshape(-1, n)
     else:
         af = a.float() if a2 is None else torch.cat([a.float(), a2.float()], dim=1)
         if m is not None:

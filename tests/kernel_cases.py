@@ -124,6 +124,17 @@ def case_conv(batch, h, w, cin, cout, bias=True, residual=False, splits=1, seed=
     return rel(out.float(), ref), 2e-3, f"conv3x3 igemm B={batch} {h}x{w} {cin}->{cout} splits={splits}"
 
 
+def case_conv_s2(batch, h, w, cin, cout, seed=0):
+    """3x3 stride-2 pad-1 conv (Downsample.op, openaimodel.py:175) as implicit GEMM: TMA element strides of 2"""
+    x = _rand(batch * h * w, cin, seed=seed).half()
+    wt = _rand(cout, 3, 3, cin, seed=seed + 1, scale=(9 * cin) ** -0.5).half()
+    b = _rand(cout, seed=seed + 2).float()
+    out = ops.gemm(x, wt.reshape(cout, 9 * cin), bias=b, conv=(batch, h, w, cin), conv_stride=2)
+    xr = x.float().reshape(batch, h, w, cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(xr, wt.float().permute(0, 3, 1, 2), b, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, cout)
+    return rel(out.float(), ref), 2e-3, f"conv 3x3 stride 2 (implicit GEMM) B={batch} {h}x{w} {cin}->{cout}"
+
+
 def case_conv_direct(batch, h, w, cin, cout, stride, silu, residual=False, seed=0):
     x = _rand(batch, cin, h, w, seed=seed).half()
     wt = _rand(cout, cin, 3, 3, seed=seed + 1, scale=(9 * cin) ** -0.5).half()
@@ -393,6 +404,11 @@ ALL_CASES = [
     (case_conv_direct, (1, 256, 256, 3, 16, 1, True)),
     (case_conv_direct, (1, 128, 128, 16, 32, 2, True)),
     (case_conv_direct, (1, 64, 64, 96, 256, 2, True)),
+    (case_conv_s2, (2, 64, 64, 320, 320)),        # the three Downsample convs of one frame (cond | uncond)
+    (case_conv_s2, (2, 32, 32, 640, 640)),
+    (case_conv_s2, (2, 16, 16, 1280, 1280)),       # 8x8 output: two images per 128-row tile
+    (case_conv_s2, (1, 16, 16, 1280, 1280)),       # ControlNet at one frame: half a tile
+    (case_tuned, (PAIR, case_conv_s2, 16, 64, 64, 320, 320)),   # eight frames: the pair kernel
     (case_down, (2, 32, 32, 640)),
     (case_down, (1, 24, 16, 640)),
     (case_conv_im2col, (1, 12, 8, 1280, 1280)),
