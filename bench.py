@@ -195,10 +195,7 @@ def roofline_probe(torch, ops, trace, peaks, frames_per_gpu=1):
         w = torch.randn(n, k, device="cuda", dtype=torch.float16) * k ** -0.5
         if conv is not None:
             a = torch.randn(conv[0] * conv[1] * conv[2], conv[3], device="cuda", dtype=torch.float16)
-            mode = conv[4] if len(conv) > 4 else 1  # 1 | 2: conv stride; 3: one phase of the upsample conv
-            kw = dict(conv=conv[:4], conv_stride=2 if mode == 2 else 1)
-            if mode == 3:
-                kw.update(up_phase=0, out=torch.empty(4 * m, n, device="cuda", dtype=torch.float16))
+            kw = dict(conv=conv[:4], conv_stride=conv[4] if len(conv) > 4 else 1)
         elif k2:
             a = torch.randn(m, k - k2, device="cuda", dtype=torch.float16)
             kw = dict(a2=torch.randn(m, k2, device="cuda", dtype=torch.float16))

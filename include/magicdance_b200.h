@@ -71,12 +71,7 @@ typedef struct mdb_gemm_desc {
   int64_t lda2;
   int32_t k1;      /* columns taken from a; == k when a2 == NULL                                  */
   int32_t conv;    /* 0 plain; 1 | 2 = 3x3 pad-1 implicit GEMM with stride 1 | 2 over the NHWC input
-                      (K = 9*c, M = nb*ho*wo, ho = (h-1)/stride+1): no im2col buffer (TMA element strides);
-                      3 = ONE PHASE (up_phase = 2a + b) of conv3x3(nearest_upsample_2x(input)) (Upsample,
-                      openaimodel.py:129-139): output pixel (2y+a, 2x+b) = sum over the 2x2 input neighbourhood
-                      (y+dy+a-1, x+dx+b-1) with the 3x3 taps that fall on the same input pixel pre-summed into B
-                      (K = 4*c, M = nb*h*w INPUT pixels; D is the full [nb*2h*2w][N] output, a call writes a quarter
-                      of its rows): no upsampled tensor, 2.25x fewer flops than the 3x3 conv over it */
+                      (K = 9*c, M = nb*ho*wo, ho = (h-1)/stride+1): no im2col buffer (TMA element strides) */
   int32_t nb, h, w, c;
   const void* b;   /* fp16 [N][K], row stride ldb                                                 */
   int64_t ldb;
@@ -98,7 +93,6 @@ typedef struct mdb_gemm_desc {
    * GEGLU epilogue, single-CTA tiles).  NULL = off. */
   const float* ln_u;
   float ln_eps;
-  int32_t up_phase;           /* conv == 3 only: 2a + b */
 } mdb_gemm_desc;
 
 int mdb_gemm_f16(const mdb_gemm_desc* desc, mdb_stream_t stream);

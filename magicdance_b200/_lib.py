@@ -21,7 +21,7 @@ class GemmDesc(C.Structure):
         ("bias", c_void_p), ("bias_batch_stride", c_int64), ("rows_per_batch", c_int32), ("epilogue", c_int32),
         ("residual", c_void_p), ("ldr", c_int64),
         ("m", c_int32), ("n", c_int32), ("k", c_int32), ("splits", c_int32), ("splitk_ws", c_void_p),
-        ("ln_u", c_void_p), ("ln_eps", c_float), ("up_phase", c_int32),
+        ("ln_u", c_void_p), ("ln_eps", c_float),
     ]
 
 

@@ -48,11 +48,7 @@ struct GemmKParams {
   int conv;            // conv mode
   int chunks_per_tap;  // c / 64
   int w, hw;           // conv geometry of the OUTPUT (== input for stride 1)
-  int cs;              // conv stride (1 | 2): input pixel = cs * output pixel + tap + (ox, oy)
-  int taps_w;          // taps per kernel row: 3 (3x3 conv) or 2 (one phase of the conv over a nearest-x2 upsampled input)
-  int ox, oy;          // offset of tap (0, 0): -1 for the 3x3 conv; (b - 1, a - 1) for upsample phase (a, b)
-  int up;              // != 0: rows are INPUT pixels (y, x) of an h x w image and go to output pixel (2y + up_a, 2x + up_b)
-  int up_a, up_b;
+  int cs;              // conv stride (1 | 2): input pixel = cs * output pixel + tap - 1
   int cluster_reduce;  // split-K partners form a cluster (1,1,splits) and reduce through distributed smem
   // LayerNorm folded into this GEMM (gemm_tc_kernel only): D = rstd_r (A W'^T - mean_r u) + bias with W' = W diag(gamma),
   // u[n] = sum_k W'[n][k]; the epilogue warps compute (mean_r, rstd_r) of their A rows from the staged tiles
@@ -76,16 +72,6 @@ struct GemmSmem {
   static constexpr int kTotal = STAGES * kStageBytes + 1024;  // + alignment slack
 };
 
-// row of D that GEMM row `row` is written to: itself, or — for one phase of the upsample conv — pixel (2y + a, 2x + b)
-// of the twice-as-large output image
-__device__ __forceinline__ long long out_row(const GemmKParams& p, long long row) {
-  if (!p.up) return row;
-  const long long img = row / p.hw;
-  const int r = static_cast<int>(row - img * p.hw);
-  const int y = r / p.w, x = r - y * p.w;
-  return (img * (2 * (p.hw / p.w)) + 2 * y + p.up_a) * (2 * p.w) + 2 * x + p.up_b;
-}
-
 __device__ __forceinline__ void epi_store_chunk(const GemmKParams& p, long long row, int col0, int ncols,
                                                 float (&v)[32], const float* bias_chunk, const uint4* res_pref) {
   // v holds columns col0 .. col0+31 of `row` (fp32 accumulators); bias + residual, then fp16 store.
@@ -93,7 +79,7 @@ __device__ __forceinline__ void epi_store_chunk(const GemmKParams& p, long long 
   // bias_chunk: this chunk's 32 bias values (shared or global memory) or nullptr;
   // res_pref:   this chunk's residual, prefetched into registers during the main loop, or nullptr.
   const __half* rp = (p.residual != nullptr) ? p.residual + row * p.ldr + col0 : nullptr;
-  __half* dp = p.d + out_row(p, row) * p.ldd + col0;
+  __half* dp = p.d + row * p.ldd + col0;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (q * 8 + 8 <= ncols) {
@@ -209,8 +195,8 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
         if (p.conv) {
           const int tap = kc / p.chunks_per_tap;
           const int cc = kc - tap * p.chunks_per_tap;
-          const int kh = tap / p.taps_w, kw = tap - kh * p.taps_w;
-          tma_load_4d(sa, &p.tmA, &full_bar[s], cc * kBK, p.cs * x0 + kw + p.ox, p.cs * y0 + kh + p.oy, b0);
+          const int kh = tap / 3, kw = tap - kh * 3;
+          tma_load_4d(sa, &p.tmA, &full_bar[s], cc * kBK, p.cs * x0 + kw - 1, p.cs * y0 + kh - 1, b0);
         } else if (kc < p.k1_chunks) {
           tma_load_2d(sa, &p.tmA, &full_bar[s], kc * kBK, m0);
         } else {
@@ -475,12 +461,12 @@ __global__ void __launch_bounds__(kGemmThreads, (kStages <= 3) ? 2 : 1)
           o4.y = pack_half2(o[2], o[3]);
           o4.z = pack_half2(o[4], o[5]);
           o4.w = pack_half2(o[6], o[7]);
-          *reinterpret_cast<uint4*>(p.d + out_row(p, row) * p.ldd + col0) = o4;
+          *reinterpret_cast<uint4*>(p.d + row * p.ldd + col0) = o4;
         } else {
           for (int e = 0; e < ncols; ++e) {
             float x = o[e];
             if (p.residual != nullptr) x += __half2float(p.residual[row * p.ldr + col0 + e]);
-            p.d[out_row(p, row) * p.ldd + col0 + e] = __float2half_rn(x);
+            p.d[row * p.ldd + col0 + e] = __float2half_rn(x);
           }
         }
       }
@@ -618,8 +604,8 @@ __global__ void __launch_bounds__(kPairqThreads, 1)
           if (p.conv) {
             const int tap = kc / p.chunks_per_tap;
             const int cc = kc - tap * p.chunks_per_tap;
-            const int kh = tap / p.taps_w, kw = tap - kh * p.taps_w;
-            tma_load_4d_pair(sa, &p.tmA, fb, cc * kBK, p.cs * x0 + kw + p.ox, p.cs * y0 + kh + p.oy, b0);
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d_pair(sa, &p.tmA, fb, cc * kBK, p.cs * x0 + kw - 1, p.cs * y0 + kh - 1, b0);
           } else if (kc < p.k1_chunks) {
             tma_load_2d_pair(sa, &p.tmA, fb, kc * kBK, m0);
           } else {
@@ -847,7 +833,7 @@ __global__ void splitk_finalize_kernel(GemmKParams p) {
       uint2 o;
       o.x = pack_half2(a.x, a.y);
       o.y = pack_half2(a.z, a.w);
-      *reinterpret_cast<uint2*>(p.d + out_row(p, row) * p.ldd + col) = o;
+      *reinterpret_cast<uint2*>(p.d + row * p.ldd + col) = o;
     }
     return;
   }
@@ -862,7 +848,7 @@ __global__ void splitk_finalize_kernel(GemmKParams p) {
       v += p.bias[brow * p.bias_batch_stride + col];
     }
     if (p.residual != nullptr) v += __half2float(p.residual[row * p.ldr + col]);
-    p.d[out_row(p, row) * p.ldd + col] = __float2half_rn(v);
+    p.d[row * p.ldd + col] = __float2half_rn(v);
   }
 }
 
@@ -1030,11 +1016,8 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   int rc;
   if (g->conv) {
     MDB_REQUIRE(g->a2 == nullptr, "mdb_gemm_f16: conv mode takes a single source");
-    const bool up = g->conv == 3;  // one phase of conv3x3(nearest_upsample_2x(x)): a 2x2 conv over the INPUT image
-    MDB_REQUIRE(g->c % kBK == 0 && g->k == (up ? 4 : 9) * g->c,
-                "mdb_gemm_f16: conv needs c %% 64 == 0 and k == 9c (4c for an upsample phase) (c=%d k=%d)", g->c, g->k);
-    MDB_REQUIRE(!up || (g->up_phase >= 0 && g->up_phase < 4 && g->residual == nullptr && !geglu),
-                "mdb_gemm_f16: upsample phase must be 0..3, without residual / GEGLU");
+    MDB_REQUIRE(g->c % kBK == 0 && g->k == 9 * g->c, "mdb_gemm_f16: conv needs c %% 64 == 0 and k == 9c (c=%d k=%d)",
+                g->c, g->k);
     // conv == 1: stride 1; conv == 2: stride 2 (Downsample.op, openaimodel.py:175): the output pixel (y, x) reads input
     // (2y + kh - 1, 2x + kw - 1) — the same shifted boxes with TMA element strides of 2 along w and h, no im2col buffer
     const int cs = g->conv == 2 ? 2 : 1;
@@ -1064,12 +1047,6 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
     kp.w = wo;
     kp.hw = hw;
     kp.cs = cs;
-    kp.taps_w = up ? 2 : 3;
-    kp.up = up ? 1 : 0;
-    kp.up_a = up ? g->up_phase / 2 : 0;
-    kp.up_b = up ? g->up_phase % 2 : 0;
-    kp.ox = up ? kp.up_b - 1 : -1;
-    kp.oy = up ? kp.up_a - 1 : -1;
     kp.k1_chunks = kp.k_chunks;
   } else {
     const int k1 = g->a2 ? g->k1 : g->k;
@@ -1093,8 +1070,7 @@ extern "C" int mdb_gemm_f16(const mdb_gemm_desc* g, mdb_stream_t stream) {
   // CTA-pair kernel with 256 x {320, 256, 160, 128} tiles — widest first: fewest L2 -> SM bytes per flop; the
   // 320-wide tile (two 160-wide MMAs per K step, single accumulator buffer) only for long K.
   const int m_tiles = (g->m + kBM - 1) / kBM;
-  // (the pair kernel has neither the LN fusion nor the scattered rows of an upsample phase: its epilogue is a TMA store)
-  bool pair = g->splits <= 1 && m_tiles >= 2 && g->n % 8 == 0 && g->ln_u == nullptr && g->conv != 3;
+  bool pair = g->splits <= 1 && m_tiles >= 2 && g->n % 8 == 0 && g->ln_u == nullptr;  // (the pair kernel has no LN fusion)
   int bn = 0;
   if (pair) {
     if (geglu) bn = (g->n % 256 == 0) ? 256 : 0;

@@ -104,27 +104,6 @@ def pack_conv3x3(w, device):
     return _f16(w.detach().to(device).permute(0, 2, 3, 1).reshape(o, kh * kw * i), device)
 
 
-def pack_upconv(w, device):
-    """Upsample (openaimodel.py:129-139) = conv3x3(nearest_upsample_2x(x)).  Output pixel (2y+a, 2x+b) only sees the 2x2
-    input neighbourhood (y+dy+a-1, x+dx+b-1): the 3x3 taps that land on the same input pixel are summed (in fp32) into
-    one 2x2 kernel per phase -> [4 phases (2a+b)][O][dy][dx][I] fp16 viewed as [4, O, 4*I].  2.25x fewer flops, and the
-    upsampled tensor never exists."""
-    wf = w.detach().to(device).float()  # O I kh kw
-    rows = {(0, 0): (0,), (0, 1): (1, 2), (1, 0): (0, 1), (1, 1): (2,)}  # (phase bit, d) -> 3x3 taps on that input pixel
-    o, i = wf.shape[:2]
-    out = torch.zeros((4, o, 2, 2, i), dtype=torch.float32, device=device)
-    for a in (0, 1):
-        for b in (0, 1):
-            for dy in (0, 1):
-                for dx in (0, 1):
-                    acc = 0
-                    for kh in rows[(a, dy)]:
-                        for kw in rows[(b, dx)]:
-                            acc = acc + wf[:, :, kh, kw]
-                    out[2 * a + b, :, dy, dx, :] = acc
-    return out.reshape(4, o, 4 * i).to(torch.float16).contiguous()
-
-
 def pack_conv1x1(w, device):
     return _f16(w.detach().reshape(w.shape[0], w.shape[1]), device)
 
@@ -205,8 +184,7 @@ class PackedNet:
                 elif kind_ == "down":
                     self.layers[p] = (pack_conv3x3(g(p + "op.weight"), device), _f32(g(p + "op.bias"), device))
                 elif kind_ == "up":
-                    self.layers[p] = (pack_conv3x3(g(p + "conv.weight"), device), _f32(g(p + "conv.bias"), device),
-                                      pack_upconv(g(p + "conv.weight"), device))
+                    self.layers[p] = (pack_conv3x3(g(p + "conv.weight"), device), _f32(g(p + "conv.bias"), device))
         self.emb_w = _f16(torch.cat(emb_w, 0), device)
         self.emb_b = _f32(torch.cat(emb_b, 0), device)
         self.emb_total = off
@@ -478,15 +456,8 @@ class DenoiseEngine:
                     y = ops.gemm(col, lw[0], bias=lw[1])
                 x = Act(y, x.b, ho, wo)
             elif kind == "up":
-                if _igemm_ok(x.h, x.w, x.c) and cout % 8 == 0 and cout >= 64:
-                    # four 2x2 phase convs over the INPUT image, each writing a quarter of the output's pixels
-                    y = torch.empty((x.b * 4 * x.hw, cout), dtype=torch.float16, device=self.device)
-                    for ph in range(4):
-                        ops.gemm(x.data, lw[2][ph], bias=lw[1], conv=(x.b, x.h, x.w, x.c), up_phase=ph, out=y)
-                    x = Act(y, x.b, 2 * x.h, 2 * x.w)
-                else:
-                    up = ops.upsample2x(x.data, batch=x.b, h=x.h, w=x.w, c=x.c)
-                    x = self._conv3(Act(up, x.b, 2 * x.h, 2 * x.w), lw[0], lw[1], cout=cout)
+                up = ops.upsample2x(x.data, batch=x.b, h=x.h, w=x.w, c=x.c)
+                x = self._conv3(Act(up, x.b, 2 * x.h, 2 * x.w), lw[0], lw[1], cout=cout)
         return x
 
     # ---- the three networks -------------------------------------------------------------------

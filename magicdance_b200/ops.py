@@ -121,13 +121,11 @@ def _workspace(key, numel, dtype, device, zero=False):
 
 
 def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, residual=None, epilogue=EPI_NONE,
-         a2=None, conv=None, conv_stride=1, up_phase=None, splits=0, m=None, ln_u=None, ln_eps=1e-5):
+         a2=None, conv=None, conv_stride=1, splits=0, m=None, ln_u=None, ln_eps=1e-5):
     """D = epilogue(A @ W^T).  a: [M, K1] fp16 (last dim contiguous, row stride arbitrary) or, with
     conv=(nb, h, w, c), an NHWC activation; w: [N, K] fp16; a2: optional second K-range source.
     splits: 0 = the library picks tile width and split-K (1/2/4/8, reduced inside a thread-block cluster),
     1 = no split, n = exactly n splits (a count other than 2, 4, 8 goes through an fp32 workspace).
-    conv_stride=2: the stride-2 Downsample conv; up_phase=2a+b (with out = the full [nb*2h*2w, N] result): one phase of
-    conv3x3(nearest_upsample_2x(a)) — w is that phase's pre-summed 2x2 kernel [N, 4c] (engine.pack_upconv).
     ln_u: LayerNorm over a's rows folded into the GEMM — w must be W diag(gamma), bias W beta (+ b), ln_u the row sums
     of w (engine.fold_layernorm); D = rstd_r (a w^T - mean_r ln_u) + bias.  Small grids only."""
     lib = _lib.load()
@@ -140,9 +138,6 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
         assert conv_stride in (1, 2) and a.is_contiguous() and a.numel() == nb * h * wd * c
         m = nb * ((h - 1) // conv_stride + 1) * ((wd - 1) // conv_stride + 1)  # output pixels (3x3, pad 1)
         g.conv, g.nb, g.h, g.w, g.c = conv_stride, nb, h, wd, c  # descriptor: conv = 1 (stride 1) | 2 (stride 2)
-        if up_phase is not None:  # rows = INPUT pixels; they land on a quarter of the rows of the 2h x 2w output
-            assert conv_stride == 1 and out is not None and out.shape[0] == 4 * m and residual is None
-            g.conv, g.up_phase = 3, int(up_phase)
         g.a, g.lda, g.k1 = a.data_ptr(), c, k
     else:
         assert a.dim() == 2 and a.stride(1) == 1
@@ -177,7 +172,7 @@ def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, re
         g.ln_u, g.ln_eps = ln_u.data_ptr(), float(ln_eps)
         splits = 1
     if TRACE is not None:
-        TRACE.append((m, n, k, (tuple(conv) + (conv_stride if up_phase is None else 3,)) if conv is not None else None, epilogue, splits,
+        TRACE.append((m, n, k, (tuple(conv) + (conv_stride,)) if conv is not None else None, epilogue, splits,
                       a2.shape[1] if a2 is not None else 0))
     if splits > 1 and splits not in (2, 4, 8):
         ws = _workspace("splitk", splits * m * n, torch.float32, a.device)

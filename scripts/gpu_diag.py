@@ -20,7 +20,7 @@ GROUPS = {
     "misc": ("case_layout", "case_add", "case_upsample", "case_time_path", "case_cfg_ddim", "case_layernorm",
              "case_groupnorm", "case_conv_direct"),
     "gemm": ("case_gemm", "case_gemm_ln", "case_gemm_batch_bias", "case_gemm_dual", "case_gemm_strided_out", "case_geglu"),
-    "conv": ("case_conv", "case_conv_s2", "case_upconv", "case_down", "case_conv_im2col"),
+    "conv": ("case_conv", "case_conv_s2", "case_down", "case_conv_im2col"),
     "attn": ("case_attention",),
     "tuned": ("case_tuned",),
 }

@@ -12,22 +12,12 @@ def _h(t):
 
 
 def gemm(a, w, *, out=None, bias=None, bias_batch_stride=0, rows_per_batch=0, residual=None, epilogue=0, a2=None,
-         conv=None, conv_stride=1, up_phase=None, splits=1, m=None, ln_u=None, ln_eps=1e-5):
+         conv=None, conv_stride=1, splits=1, m=None, ln_u=None, ln_eps=1e-5):
     """D = epilogue(A @ W^T) exactly as include/magicdance_b200.h describes mdb_gemm_f16 (dual-source A, conv mode,
     per-batch bias rows, residual, GEGLU over [value | gate] blocks of 32 interleaved columns)."""
     assert a.dtype == torch.float16 and w.dtype == torch.float16
     n, k = w.shape
     assert k % 64 == 0, "K must be a multiple of 64"
-    if conv is not None and up_phase is not None:
-        # one phase (a, b) of conv3x3(nearest_upsample_2x(x)): a 2x2 conv over the input, scattered to (2y+a, 2x+b)
-        b, h, ww, cin = conv
-        pa, pb = divmod(int(up_phase), 2)
-        assert k == 4 * cin and out is not None and out.shape[0] == 4 * b * h * ww
-        x = F.pad(a.float().reshape(b, h, ww, cin).permute(0, 3, 1, 2), (1, 1, 1, 1))[:, :, pa:pa + h + 1, pb:pb + ww + 1]
-        wt = w.float().reshape(n, 2, 2, cin).permute(0, 3, 1, 2)
-        y = F.conv2d(x, wt, bias if bias is not None else None)  # [b, n, h, w]
-        out.view(b, h, 2, ww, 2, n)[:, :, pa, :, pb, :] = _h(y.permute(0, 2, 3, 1))
-        return out
     if conv is not None:
         b, h, ww, cin = conv
         assert a2 is None and k == 9 * cin and a.numel() == b * h * ww * cin

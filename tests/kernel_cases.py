@@ -135,22 +135,6 @@ def case_conv_s2(batch, h, w, cin, cout, seed=0):
     return rel(out.float(), ref), 2e-3, f"conv 3x3 stride 2 (implicit GEMM) B={batch} {h}x{w} {cin}->{cout}"
 
 
-def case_upconv(batch, h, w, cin, cout, seed=0):
-    """conv3x3(nearest_upsample_2x(x)) (Upsample, openaimodel.py:129-139) as four 2x2 phase convs over the input
-    (engine.pack_upconv + ops.gemm(up_phase=...)) against F.interpolate + F.conv2d in fp32"""
-    from magicdance_b200.engine import pack_upconv
-    x = _rand(batch * h * w, cin, seed=seed).half()
-    wt = _rand(cout, cin, 3, 3, seed=seed + 1, scale=(9 * cin) ** -0.5)
-    b = _rand(cout, seed=seed + 2).float()
-    phases = pack_upconv(wt, DEV)
-    out = torch.empty(batch * 4 * h * w, cout, dtype=torch.float16, device=DEV)
-    for ph in range(4):
-        ops.gemm(x, phases[ph], bias=b, conv=(batch, h, w, cin), up_phase=ph, out=out)
-    xr = F.interpolate(x.float().reshape(batch, h, w, cin).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
-    ref = F.conv2d(xr, wt.float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, cout)
-    return rel(out.float(), ref), 2e-3, f"upsample conv (4 phases) B={batch} {h}x{w} {cin}->{cout}"
-
-
 def case_conv_direct(batch, h, w, cin, cout, stride, silu, residual=False, seed=0):
     x = _rand(batch, cin, h, w, seed=seed).half()
     wt = _rand(cout, cin, 3, 3, seed=seed + 1, scale=(9 * cin) ** -0.5).half()
@@ -425,10 +409,6 @@ ALL_CASES = [
     (case_conv_s2, (2, 16, 16, 1280, 1280)),       # 8x8 output: two images per 128-row tile
     (case_conv_s2, (1, 16, 16, 1280, 1280)),       # ControlNet at one frame: half a tile
     (case_tuned, (PAIR, case_conv_s2, 16, 64, 64, 320, 320)),   # eight frames: the pair kernel
-    (case_upconv, (2, 8, 8, 1280, 1280)),          # the three Upsample convs of one frame (cond | uncond)
-    (case_upconv, (2, 16, 16, 1280, 1280)),
-    (case_upconv, (2, 32, 32, 640, 640)),
-    (case_upconv, (16, 32, 32, 640, 640)),         # eight frames
     (case_down, (2, 32, 32, 640)),
     (case_down, (1, 24, 16, 640)),
     (case_conv_im2col, (1, 12, 8, 1280, 1280)),
