@@ -312,3 +312,23 @@ def ddim_update(x, e_t, index, sched):
     dir_xt = math.sqrt(1.0 - a_prev - sigma ** 2) * e_t
     x_prev = math.sqrt(a_prev) * pred_x0 + dir_xt
     return x_prev, pred_x0
+
+
+# ----------------------------------------------------------------------------- training caller (rows a15 / a16)
+def q_sample(x0, t, noise, alphas_cumprod):
+    """ddpm.py:356-359: sqrt(acp_t) x0 + sqrt(1 - acp_t) eps, per-sample t."""
+    a = torch.as_tensor(alphas_cumprod[t.cpu().numpy()], dtype=x0.dtype, device=x0.device).reshape(-1, 1, 1, 1)
+    return a.sqrt() * x0 + (1 - a).sqrt() * noise
+
+
+def p_losses(sd, x0, t, noise, context, pose_map, reference_latent, cfg=DEFAULT_NET_CFG, x_noisy=None):
+    """LatentDiffusionReferenceOnly.p_losses, ddpm.py:2165-2212, as train_tiktok.py:1212-1214 reaches it: 'eps'
+    parameterisation, wonoise (the reference latent stays clean), l_simple_weight 1, logvar == 0 (not learned),
+    original_elbo_weight 0 -> loss = mean_b mean_chw (eps_pred - eps)^2.  Differentiable: tensors of `sd` that require
+    grad receive the gradients loss.backward() gives the reference's parameters (CheckpointFunction, util.py:118-187,
+    recomputes the same values — tests/golden/grad16.npz holds both and their difference)."""
+    if x_noisy is None:
+        x_noisy = q_sample(x0, t, noise, make_schedule()["alphas_cumprod"])
+    eps = apply_model(sd, x_noisy, t, context, pose_map, reference_latent, uc=False, cfg=cfg)
+    loss_simple = ((eps - noise) ** 2).mean(dim=(1, 2, 3))
+    return loss_simple.mean(), loss_simple, eps

@@ -43,3 +43,19 @@ def small32_inputs():
 
 def full64_inputs():
     return synth.synth_inputs(1, 64, seed=0, shared_reference=True)
+
+
+def grad16_inputs():
+    """inputs of tests/golden/grad16.npz (oracle/make_golden_grad.py: grad_inputs)"""
+    inp = synth.synth_inputs(2, 16, seed=5, shared_reference=False)
+    g = torch.Generator().manual_seed(17)
+    inp["x0"] = 0.9 * torch.randn(2, 4, 16, 16, generator=g)
+    inp["noise"] = torch.randn(2, 4, 16, 16, generator=g)
+    inp["t_train"] = torch.tensor([812, 97], dtype=torch.long)
+    return inp
+
+
+def grad_sample_positions(numel, n=16):
+    if numel <= n:
+        return np.arange(numel)
+    return (np.arange(n, dtype=np.int64) * (numel - 1)) // (n - 1)
