@@ -24,14 +24,7 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n = 1);
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
-bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MDB_PDL");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return v != 0;
-}
+bool pdl_enabled() { return true; }  // every launch carries the programmatic-stream-serialization attribute
 
 // ---------------------------------------------------------------------------------------------
 // direct 3x3 conv, pad 1, stride 1|2, NHWC fp16, fp32 accumulate.
