@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 
 from .. import ops
-from ..engine import Act, DenoiseEngine
+from ..engine import DenoiseEngine
 from .ddpm import LatentDiffusionReferenceOnly
 from .modules import UNetModel
 from .util import instantiate_from_config

@@ -10,7 +10,6 @@ the frames of a video — the reference recomputes all of them for every frame a
 """
 from __future__ import annotations
 
-import os
 
 import numpy as np
 import torch
@@ -117,7 +116,7 @@ class DDIMSampler_ReferenceOnly(object):
         Python.  Returns None (the caller falls back to the eager loop) for anything the graphs do not cover: eta != 0,
         a noised or per-sample reference, no classifier-free guidance, CPU tensors."""
         from .. import parallel
-        from ..pipeline import GraphedDenoiser, plan_bank_chunks
+        from ..pipeline import GraphedDenoiser
         if not (isinstance(c, dict) and c.get("image_control") is not None and c.get("wonoise") and uc is not None
                 and uc.get("image_control") is None and scale != 1.0 and not c.get("overlap_sampling")
                 and not np.any(self.ddim_sigmas) and img.is_cuda):

@@ -19,7 +19,6 @@ path: torch only allocates buffers.
 """
 from __future__ import annotations
 
-import os
 from dataclasses import dataclass
 
 import torch

@@ -13,7 +13,7 @@ eps <= 5e-3.  SURVEY §8c proposed 2e-2 / 3e-2; the measured margins allow the t
 """
 import os
 
-import numpy as np
+
 import pytest
 import torch
 
