@@ -78,7 +78,9 @@ class DDIMSampler_ReferenceOnly(object):
                       noise_dropout=0., score_corrector=None, corrector_kwargs=None, unconditional_guidance_scale=1.,
                       unconditional_conditioning=None, dynamic_threshold=None, ucg_schedule=None, inpaint=None):
         """ddim.py:460-516"""
-        assert not ddim_use_original_steps and timesteps is None and mask is None and ucg_schedule is None
+        if ddim_use_original_steps or timesteps is not None or mask is not None or ucg_schedule is not None:
+            raise NotImplementedError("DDIMSampler_ReferenceOnly.ddim_sampling: ddim_use_original_steps / timesteps / mask / "
+                                      "ucg_schedule are not used by the MagicPose scripts and are not implemented")
         device = self.model.betas.device
         b = shape[0]
         img = torch.randn(shape, device=device) if x_T is None else x_T.to(device)
