@@ -78,3 +78,10 @@ def test_bank_allgather_uneven_world3_gloo():
     res = _run(3)
     assert [r[1] for r in res] == [True, True, True]
     assert [r[2] for r in res] == [4, 3, 3]
+
+
+def test_bank_allgather_world4_gloo():
+    """the 4-GPU leg of the scaling run: 10 timesteps -> 3, 3, 2, 2"""
+    res = _run(4)
+    assert [r[1] for r in res] == [True] * 4
+    assert [r[2] for r in res] == [3, 3, 2, 2]
