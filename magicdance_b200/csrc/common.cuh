@@ -387,7 +387,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-// Exact-GELU with a branch-free polynomial erf (opt-in kernels only until validated on a GPU): erf(z) ~ z P(z^2) on
+// Exact-GELU with a branch-free polynomial erf (the pair kernel's GEGLU epilogue; case_tuned PAIR): erf(z) ~ z P(z^2) on
 // |z| <= 3 (degree-8 P, weighted least-squares fit on Chebyshev nodes), clamped beyond (1 - erf(3) = 2.2e-5).
 // Max |error| of erf in fp32 Horner arithmetic: 2.1e-5 (scripts/fit_erf_poly.py), i.e. <= 5e-5 absolute on GELU for
 // |x| <= 4.2 — an order of magnitude below the fp16 rounding of the result.  ~16 FMA-pipe instructions, no MUFU, no

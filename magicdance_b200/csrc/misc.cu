@@ -265,7 +265,7 @@ __global__ void im2col3x3_kernel(const __half* __restrict__ x, __half* __restric
 
 // Same gather with the window anchored at the output pixel (no top/left halo) and zero fill past the bottom /
 // right edge: the first-stage VAE encoder's Downsample pads (0,1,0,1) and convolves with stride 2, padding 0
-// (ldm/modules/diffusionmodules/model.py:82-84).  Not yet run on a GPU (VAE encoder, opt-in).
+// (ldm/modules/diffusionmodules/model.py:82-84).  Used by the VAE encoder (tests/test_vae_gpu.py).
 __global__ void im2col3x3_br_kernel(const __half* __restrict__ x, __half* __restrict__ col, int batch, int h, int w,
                                     int c, int stride, int ho, int wo) {
   pdl_launch_dependents();

@@ -1,4 +1,4 @@
-"""GPU parity of the (not yet validated) VAE decoder and encoder in magicdance_b200/vae.py against the pinned CPU oracle and
+"""GPU parity of the VAE decoder and encoder in magicdance_b200/vae.py against the pinned CPU oracle and
 the reference goldens.  Run on a B200:
 
     python tests/gpu_vae_parity_report.py            # latent 16 (B=2) and latent 64 (B=1)

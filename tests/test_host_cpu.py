@@ -146,7 +146,7 @@ def test_header_is_plain_c_and_matches_the_ctypes_structs(tmp_path):
 
 
 def test_vae_decoder_packing_consumes_every_decoder_tensor():
-    """host logic of the (GPU-unvalidated, opt-in) VAE decoder: the repack reads every
+    """host logic of the VAE decoder: the repack reads every
     first_stage_model.{post_quant_conv,decoder}.* tensor of the reference state dict exactly once, and the folds
     (1/scale_factor into post_quant_conv, c^-0.5 into q, the v bias into proj_out) are the ones the oracle implies."""
     import json
